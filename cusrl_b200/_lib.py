@@ -1,0 +1,104 @@
+"""ctypes binding of ``libcusrl_b200.so`` (the C ABI declared in ``include/cusrl_b200.h``).
+
+There is deliberately NO fallback: if the library is missing the import of any product module that
+needs a kernel raises, and every wrapper raises ``RuntimeError`` on a non-zero return code.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import re
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libcusrl_b200.so"
+HEADER_PATH = PKG_DIR.parent / "include" / "cusrl_b200.h"
+
+
+class GatherField(ctypes.Structure):
+    """Mirror of ``cusrl_b200_gather_field``."""
+
+    _fields_ = [
+        ("src", c_void_p),
+        ("dst", c_void_p),
+        ("row_bytes", c_int64),
+        ("src_stride", c_int64),
+        ("dst_stride", c_int64),
+    ]
+
+
+P = c_void_p  # every device pointer crosses the ABI as void*
+
+_SIGNATURES: dict[str, tuple[object, list[object]]] = {
+    "cusrl_b200_abi_version": (c_int, []),
+    "cusrl_b200_last_error": (c_char_p, []),
+    "cusrl_b200_sm_count": (c_int, []),
+    "cusrl_b200_next_value_f32": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_float, P]),
+    "cusrl_b200_gae_f32": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_double, c_double, c_double, P]),
+    "cusrl_b200_gae_fused_f32": (
+        c_int,
+        [P, P, P, P, P, c_float, P, P, P, c_int64, c_int64, c_int64, c_double, c_double, c_double, P],
+    ),
+    "cusrl_b200_gae_set_config": (c_int, [c_int, c_int]),
+    "cusrl_b200_advantage_stats_scratch_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_advantage_stats_f32": (c_int, [P, c_int64, c_int64, P, P, c_size_t, P]),
+    "cusrl_b200_advantage_normalize_f32": (c_int, [P, c_int64, c_int64, P, c_float, P]),
+    "cusrl_b200_merge_mean_var_f32": (c_int, [P, c_int64, c_int64, P, P]),
+    "cusrl_b200_gather_rows": (c_int, [POINTER(GatherField), c_int, P, c_int64, c_int64, P]),
+    "cusrl_b200_ppo_loss_scratch_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_ppo_loss_f32": (
+        c_int,
+        [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int]
+        + [c_float] * 5
+        + [P] * 10
+        + [P, c_size_t, P],
+    ),
+    "cusrl_b200_scale_f32": (c_int, [P, c_int64, P, P]),
+    "cusrl_b200_policy_stats_scratch_bytes": (c_size_t, []),
+    "cusrl_b200_policy_stats_f32": (c_int, [P] * 7 + [c_int64, c_int64, P, P, c_size_t, P]),
+    "cusrl_b200_grad_sumsq_f32": (c_int, [P, c_int64, P, P]),
+    "cusrl_b200_clip_coef_f32": (c_int, [P, c_float, P, P, P]),
+    "cusrl_b200_adam_step_f32": (c_int, [P, P, P, P, c_int64, P] + [c_float] * 5 + [c_int64, P]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function name declared in ``include/cusrl_b200.h`` (used by the CPU symbol test)."""
+    text = HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cusrl_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib: ctypes.CDLL | None = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and attach argument/return types."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m cusrl_b200.build` "
+            "(cusrl_b200 has no CPU or PyTorch fallback for its kernels)"
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.cusrl_b200_abi_version() != 1:
+        raise RuntimeError("libcusrl_b200.so ABI version mismatch; rebuild with `python -m cusrl_b200.build -f`")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    """Raise like the reference's hooks do (ValueError for bad arguments, RuntimeError otherwise)."""
+    if code == 0:
+        return
+    msg = load().cusrl_b200_last_error().decode(errors="replace")
+    if code == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed with code {code}: {msg}")

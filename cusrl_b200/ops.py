@@ -1,0 +1,366 @@
+"""Thin Python wrappers: torch CUDA tensors -> raw pointers -> C ABI (``include/cusrl_b200.h``).
+
+PyTorch is plumbing here (device memory, streams).  Every function launches on the current CUDA
+stream, never synchronises, and refuses non-CUDA tensors: there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GatherField
+
+__all__ = [
+    "next_value",
+    "gae",
+    "gae_fused",
+    "advantage_stats",
+    "advantage_normalize_",
+    "merge_mean_var",
+    "gather_rows",
+    "ppo_loss",
+    "scale_",
+    "policy_stats",
+    "grad_sumsq_",
+    "clip_coef",
+    "adam_step_",
+]
+
+_scratch: dict[tuple[int, str], torch.Tensor] = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise ValueError(f"cusrl_b200: '{name}' must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"cusrl_b200: '{name}' must have dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _flag_ptr(t: torch.Tensor, name: str) -> int:
+    if t.dtype not in (torch.bool, torch.uint8):
+        raise TypeError(f"'{name}' must have dtype bool")
+    return _ptr(t, None, name)
+
+
+def _get_scratch(device: torch.device, key: str, nbytes: int) -> torch.Tensor:
+    k = (device.index or 0, key)
+    buf = _scratch.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _scratch[k] = buf
+    return buf
+
+
+def _tnd(t: torch.Tensor) -> tuple[int, int, int]:
+    if t.dim() != 3:
+        raise ValueError(f"expected a [T, N, Dv] tensor, got shape {tuple(t.shape)}")
+    return t.shape[0], t.shape[1], t.shape[2]
+
+
+# ---------------------------------------------------------------------------------------------- K3
+def next_value(
+    value: torch.Tensor,
+    terminated: torch.Tensor,
+    truncated: torch.Tensor,
+    boot_value: torch.Tensor,
+    termination_value: float = 0.0,
+    trunc_value: torch.Tensor | None = None,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """ValueComputation.pre_update arithmetic (reference hook/on_policy/value.py:68-82)."""
+    T, N, Dv = _tnd(value)
+    out = torch.empty_like(value) if out is None else out
+    code = _lib.load().cusrl_b200_next_value_f32(
+        _ptr(value, torch.float32, "value"),
+        _flag_ptr(terminated, "terminated"),
+        _flag_ptr(truncated, "truncated"),
+        _ptr(boot_value, torch.float32, "boot_value"),
+        _ptr(trunc_value, torch.float32, "trunc_value"),
+        _ptr(out, torch.float32, "next_value"),
+        T, N, Dv, float(termination_value), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "next_value")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- K1
+def gae(
+    reward: torch.Tensor,
+    done: torch.Tensor,
+    value: torch.Tensor,
+    next_value: torch.Tensor,
+    gamma: float,
+    lamda: float,
+    lamda_value: float | None = None,
+    advantage: torch.Tensor | None = None,
+    ret: torch.Tensor | None = None,
+    compute_return: bool = True,
+) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """GAE advantage (+return) scan (reference hook/on_policy/gae.py:8-20,85-110). Bit-exact."""
+    T, N, Dv = _tnd(value)
+    advantage = torch.empty_like(value) if advantage is None else advantage
+    if compute_return and ret is None:
+        ret = torch.empty_like(value)
+    code = _lib.load().cusrl_b200_gae_f32(
+        _ptr(reward, torch.float32, "reward"),
+        _flag_ptr(done, "done"),
+        _ptr(value, torch.float32, "value"),
+        _ptr(next_value, torch.float32, "next_value"),
+        _ptr(advantage, torch.float32, "advantage"),
+        _ptr(ret, torch.float32, "return"),
+        T, N, Dv, float(gamma), float(lamda), -1.0 if lamda_value is None else float(lamda_value), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "gae")
+    return advantage, ret
+
+
+def gae_fused(
+    reward: torch.Tensor,
+    terminated: torch.Tensor,
+    truncated: torch.Tensor,
+    value: torch.Tensor,
+    boot_value: torch.Tensor,
+    gamma: float,
+    lamda: float,
+    lamda_value: float | None = None,
+    termination_value: float = 0.0,
+    next_value_out: torch.Tensor | None = None,
+    advantage: torch.Tensor | None = None,
+    ret: torch.Tensor | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """K1 with K3 folded in: next_value is formed on the fly (value.py:68-82 + gae.py:8-20)."""
+    T, N, Dv = _tnd(value)
+    advantage = torch.empty_like(value) if advantage is None else advantage
+    ret = torch.empty_like(value) if ret is None else ret
+    code = _lib.load().cusrl_b200_gae_fused_f32(
+        _ptr(reward, torch.float32, "reward"),
+        _flag_ptr(terminated, "terminated"),
+        _flag_ptr(truncated, "truncated"),
+        _ptr(value, torch.float32, "value"),
+        _ptr(boot_value, torch.float32, "boot_value"),
+        float(termination_value),
+        _ptr(next_value_out, torch.float32, "next_value"),
+        _ptr(advantage, torch.float32, "advantage"),
+        _ptr(ret, torch.float32, "return"),
+        T, N, Dv, float(gamma), float(lamda), -1.0 if lamda_value is None else float(lamda_value), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "gae_fused")
+    return advantage, ret
+
+
+# ---------------------------------------------------------------------------------------------- K2
+def advantage_stats(advantage: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[mean(Dv) | unbiased var(Dv)] over all but the last dim (advantage.py:110-111)."""
+    Dv = advantage.shape[-1]
+    E = advantage.numel() // Dv
+    lib = _lib.load()
+    nbytes = lib.cusrl_b200_advantage_stats_scratch_bytes(Dv)
+    scratch = _get_scratch(advantage.device, "advstats", nbytes)
+    out = torch.empty(2 * Dv, dtype=torch.float32, device=advantage.device) if out is None else out
+    code = lib.cusrl_b200_advantage_stats_f32(
+        _ptr(advantage, torch.float32, "advantage"), E, Dv, _ptr(out, torch.float32, "mean_var"),
+        scratch.data_ptr(), scratch.numel(), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "advantage_stats")
+    return out
+
+
+def advantage_normalize_(advantage: torch.Tensor, mean_var: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """In-place (adv - mean) / sqrt(var + eps) (advantage.py:114-115)."""
+    Dv = advantage.shape[-1]
+    E = advantage.numel() // Dv
+    code = _lib.load().cusrl_b200_advantage_normalize_f32(
+        _ptr(advantage, torch.float32, "advantage"), E, Dv, _ptr(mean_var, torch.float32, "mean_var"),
+        float(eps), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "advantage_normalize")
+    return advantage
+
+
+def merge_mean_var(gathered: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Equal-weight cross-rank merge of stacked [mean | var] rows (utils/distributed.py:175-183)."""
+    W, two_dv = gathered.shape
+    out = torch.empty(two_dv, dtype=torch.float32, device=gathered.device) if out is None else out
+    code = _lib.load().cusrl_b200_merge_mean_var_f32(
+        _ptr(gathered, torch.float32, "gathered"), W, two_dv // 2, _ptr(out, torch.float32, "mean_var"), _stream()
+    )
+    _lib.check(code, "merge_mean_var")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- K8
+def gather_rows(
+    fields: list[tuple[torch.Tensor, torch.Tensor]],
+    index: torch.Tensor,
+) -> None:
+    """For every (src [E, ...], dst [n, ...]) pair: dst[i] = src[index[i]] in ONE launch.
+
+    Rows may be padded: only the last dim may be non-dense (stride(0) >= row payload); the padding
+    bytes of every destination row are written as zeros. Reference: mini_batch_sampler.py:76,89.
+    """
+    n_src = None
+    arr = (GatherField * len(fields))()
+    for k, (src, dst) in enumerate(fields):
+        if not (src.is_cuda and dst.is_cuda):
+            raise RuntimeError("cusrl_b200: gather_rows needs CUDA tensors (no CPU fallback exists)")
+        if src.dtype != dst.dtype:
+            raise TypeError("gather_rows: src/dst dtype mismatch")
+        s2 = src.reshape(src.shape[0], -1) if src.is_contiguous() else src
+        d2 = dst.reshape(dst.shape[0], -1) if dst.is_contiguous() else dst
+        if s2.dim() != 2 or d2.dim() != 2 or s2.stride(1) != 1 or d2.stride(1) != 1:
+            raise ValueError("gather_rows: fields must be [rows, width] with a dense last dim")
+        if d2.shape[0] != index.numel():
+            raise ValueError("gather_rows: destination row count must equal the number of indices")
+        item = src.element_size()
+        row_bytes = min(s2.shape[1], d2.shape[1]) * item
+        n_src = s2.shape[0] if n_src is None else n_src
+        if s2.shape[0] != n_src:
+            raise ValueError("gather_rows: all sources must have the same number of rows")
+        arr[k] = GatherField(s2.data_ptr(), d2.data_ptr(), row_bytes, s2.stride(0) * item, d2.stride(0) * item)
+    code = _lib.load().cusrl_b200_gather_rows(
+        arr, len(fields), _ptr(index, torch.int64, "index"), index.numel(), n_src, _stream()
+    )
+    _lib.check(code, "gather_rows")
+
+
+# ---------------------------------------------------------------------------------------------- K4
+def ppo_loss(
+    mean: torch.Tensor,
+    std: torch.Tensor,
+    action: torch.Tensor,
+    logp_old: torch.Tensor,
+    advantage: torch.Tensor,
+    ret: torch.Tensor | None,
+    value_old: torch.Tensor | None,
+    curr_value: torch.Tensor | None,
+    clip_ratio: float,
+    w_surrogate: float,
+    w_entropy: float,
+    w_value: float,
+    value_clip: float | None = None,
+    want_per_sample: bool = True,
+    want_grads: bool = True,
+) -> dict[str, torch.Tensor]:
+    """Fused PPO objective + unit gradients (see ``cusrl_b200_ppo_loss_f32`` in the header)."""
+    B, A = mean.shape
+    dev = mean.device
+    has_value = curr_value is not None
+    Dv = curr_value.shape[-1] if has_value else 1
+    f32 = torch.float32
+    out: dict[str, torch.Tensor] = {
+        "losses": torch.empty(3, dtype=f32, device=dev),
+        "metrics": torch.empty(3, dtype=f32, device=dev),
+    }
+    if want_per_sample:
+        for k in ("logp", "entropy", "logp_ratio", "prob_ratio"):
+            out[k] = torch.empty(B, 1, dtype=f32, device=dev)
+    if want_grads:
+        out["d_mean"] = torch.empty(B, A, dtype=f32, device=dev)
+        out["d_std_surr"] = torch.empty(A, dtype=f32, device=dev)
+        out["d_std_ent"] = torch.empty(A, dtype=f32, device=dev)
+        if has_value:
+            out["d_value"] = torch.empty(B, Dv, dtype=f32, device=dev)
+    lib = _lib.load()
+    scratch = _get_scratch(dev, "ppoloss", lib.cusrl_b200_ppo_loss_scratch_bytes(A))
+    g = out.get
+    code = lib.cusrl_b200_ppo_loss_f32(
+        _ptr(mean, f32, "mean"), _ptr(std, f32, "std"), _ptr(action, f32, "action"),
+        _ptr(logp_old, f32, "action_logp"), _ptr(advantage, f32, "advantage"), _ptr(ret, f32, "return"),
+        _ptr(value_old, f32, "value"), _ptr(curr_value, f32, "curr_value"),
+        B, A, Dv, int(has_value),
+        float(clip_ratio), float(w_surrogate), float(w_entropy), float(w_value),
+        -1.0 if value_clip is None else float(value_clip),
+        _ptr(g("logp")), _ptr(g("entropy")), _ptr(g("logp_ratio")), _ptr(g("prob_ratio")),
+        _ptr(out["losses"]), _ptr(out["metrics"]),
+        _ptr(g("d_mean")), _ptr(g("d_std_surr")), _ptr(g("d_std_ent")), _ptr(g("d_value")),
+        scratch.data_ptr(), scratch.numel(), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "ppo_loss")
+    return out
+
+
+def scale_(x: torch.Tensor, scale_dev: torch.Tensor) -> torch.Tensor:
+    """x *= scale (a 1-element device tensor) without reading the scalar on the host."""
+    code = _lib.load().cusrl_b200_scale_f32(
+        _ptr(x, torch.float32, "x"), x.numel(), _ptr(scale_dev, torch.float32, "scale"), _stream()
+    )
+    _lib.check(code, "scale")
+    return x
+
+
+def policy_stats(
+    mean_old: torch.Tensor,
+    std_old: torch.Tensor,
+    mean_new: torch.Tensor,
+    std_new: torch.Tensor,
+    action: torch.Tensor,
+    logp_old: torch.Tensor,
+    advantage: torch.Tensor,
+) -> torch.Tensor:
+    """[mean KL(old||new), mean importance-weighted advantage, mean std] (stats.py:29-40)."""
+    A = mean_old.shape[-1]
+    E = mean_old.numel() // A
+    lib = _lib.load()
+    scratch = _get_scratch(mean_old.device, "polstats", lib.cusrl_b200_policy_stats_scratch_bytes())
+    out = torch.empty(3, dtype=torch.float32, device=mean_old.device)
+    f32 = torch.float32
+    code = lib.cusrl_b200_policy_stats_f32(
+        _ptr(mean_old, f32, "mean_old"), _ptr(std_old, f32, "std_old"), _ptr(mean_new, f32, "mean_new"),
+        _ptr(std_new, f32, "std_new"), _ptr(action, f32, "action"), _ptr(logp_old, f32, "action_logp"),
+        _ptr(advantage, f32, "advantage"), E, A, _ptr(out), scratch.data_ptr(), scratch.numel(), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "policy_stats")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- K9
+def grad_sumsq_(grad: torch.Tensor, sumsq: torch.Tensor) -> torch.Tensor:
+    """sumsq (1 double on device) += sum(grad**2)."""
+    code = _lib.load().cusrl_b200_grad_sumsq_f32(
+        _ptr(grad, torch.float32, "grad"), grad.numel(), _ptr(sumsq, torch.float64, "sumsq"), _stream()
+    )
+    _lib.check(code, "grad_sumsq")
+    return sumsq
+
+
+def clip_coef(sumsq: torch.Tensor, max_norm: float, norm: torch.Tensor, coef: torch.Tensor) -> None:
+    """norm = sqrt(sumsq); coef = min(1, max_norm / (norm + 1e-6)) (torch clip_grad_norm_)."""
+    code = _lib.load().cusrl_b200_clip_coef_f32(
+        _ptr(sumsq, torch.float64, "sumsq"), float(max_norm), _ptr(norm, torch.float32, "norm"),
+        _ptr(coef, torch.float32, "coef"), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "clip_coef")
+
+
+def adam_step_(
+    param: torch.Tensor,
+    grad: torch.Tensor,
+    exp_avg: torch.Tensor,
+    exp_avg_sq: torch.Tensor,
+    step: int,
+    lr: float,
+    betas: tuple[float, float] = (0.9, 0.999),
+    eps: float = 1e-8,
+    weight_decay: float = 0.0,
+    coef: torch.Tensor | None = None,
+) -> None:
+    """Fused (clip-scale +) Adam step on flat arenas (torch.optim.Adam semantics)."""
+    f32 = torch.float32
+    code = _lib.load().cusrl_b200_adam_step_f32(
+        _ptr(param, f32, "param"), _ptr(grad, f32, "grad"), _ptr(exp_avg, f32, "exp_avg"),
+        _ptr(exp_avg_sq, f32, "exp_avg_sq"), param.numel(), _ptr(coef, f32, "coef"),
+        float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "adam_step")

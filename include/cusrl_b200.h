@@ -1,0 +1,174 @@
+/*
+ * cusrl_b200.h -- C ABI of the B200-native (sm_100a) on-policy PPO hot path for CusRL.
+ *
+ * The reference (chengruiz/cusrl) is pure Python/PyTorch: it has no FFI of its own.  The drop-in
+ * boundary is therefore its Python plugin surface (Hook / Sampler / ModuleFactory, see DESIGN.md and
+ * INTEGRATION.md); THIS header is the C-ABI layer underneath that surface (SURVEY.md section 8b,
+ * "C-ABI layer underneath").  Each entry point cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer; nothing is allocated, freed or retained by the library;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); no call synchronises
+ *     the device or the host;
+ *   - return value: 0 on success, a negative CUSRL_B200_E* code for argument errors, or a positive
+ *     cudaError_t when the launch itself failed.  cusrl_b200_last_error() gives a message for the
+ *     calling thread.  Nothing throws, nothing exits;
+ *   - tensors are dense row-major with the reference's layouts: rollout leaves are time-major
+ *     [T, N, C] (template/buffer.py:144), minibatch leaves are [B, C];
+ *   - bool leaves (terminated / truncated / done) are passed as uint8 (torch.bool storage);
+ *   - stateless and re-entrant: safe to call from several host threads on different streams.
+ */
+#ifndef CUSRL_B200_H_
+#define CUSRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUSRL_B200_ABI_VERSION 1
+
+#define CUSRL_B200_OK 0
+#define CUSRL_B200_EINVAL (-1)       /* null pointer, negative/zero size, bad hyper-parameter */
+#define CUSRL_B200_EALIGN (-2)       /* pointer or leading dimension not aligned as documented */
+#define CUSRL_B200_EUNSUPPORTED (-3) /* shape outside what the kernel supports               */
+#define CUSRL_B200_ESCRATCH (-4)     /* scratch buffer too small                               */
+#define CUSRL_B200_EDRIVER (-5)      /* CUDA driver entry point (TMA descriptor) unavailable  */
+
+int cusrl_b200_abi_version(void);
+const char* cusrl_b200_last_error(void);
+/* Number of SMs of the current device (grid sizing); <0 on error. */
+int cusrl_b200_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  next_value construction -- replaces ValueComputation.pre_update, hook/on_policy/value.py:68-82
+ *   nv[t]   = value[t+1]           (t < T-1)
+ *   nv[T-1] = boot_value[n]        (critic(next_state[-1]) computed by the caller)
+ *   nv[t,n] = termination_value    where terminated[t,n]
+ *   nv[t,n] = trunc_value[t,n]     where truncated[t,n]   (trunc_value==NULL: value[t,n], i.e. the
+ *                                   bootstrap_truncated_states=False branch, value.py:81-82)
+ *   applied in that order.  value,next_value: [T,N,Dv] f32; flags: [T,N] u8; boot_value: [N,Dv]. */
+int cusrl_b200_next_value_f32(const float* value, const uint8_t* terminated, const uint8_t* truncated,
+                              const float* boot_value, const float* trunc_value, float* next_value,
+                              int64_t T, int64_t N, int64_t Dv, float termination_value, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  GAE backward-in-time scan + return -- replaces _generalized_advantage_estimation and
+ *     GeneralizedAdvantageEstimation._compute_advantage_and_return, hook/on_policy/gae.py:8-20,85-110
+ *   adv[t] = (reward[t] + next_value[t]*f32(gamma)) - value[t]
+ *   adv[t] = adv[t] + ((done[t]?0:1) * f32(gamma*lamda)) * adv[t+1]      t = T-2..0, no FMA contraction
+ *   ret[t] = value[t] + adv[t]            (lamda_value < 0)
+ *   ret[t] = value[t] + adv_lv[t]         (lamda_value >= 0: second scan with lamda_value)
+ *   Bit-exact with the reference's op order.  reward,value,next_value,advantage,ret: [T,N,Dv] f32;
+ *   done: [T,N] u8 (broadcast over Dv).  `ret` may be NULL (advantage only). */
+int cusrl_b200_gae_f32(const float* reward, const uint8_t* done, const float* value,
+                       const float* next_value, float* advantage, float* ret, int64_t T, int64_t N,
+                       int64_t Dv, double gamma, double lamda, double lamda_value, void* stream);
+
+/* K1+K3 fused: next_value is formed on the fly from value/terminated/truncated/boot_value exactly as
+ * cusrl_b200_next_value_f32 would (trunc_value==NULL branch only), done = terminated | truncated
+ * (template/actor_critic.py:277).  `next_value_out` may be NULL (not materialised). */
+int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated,
+                             const float* value, const float* boot_value, float termination_value,
+                             float* next_value_out, float* advantage, float* ret, int64_t T, int64_t N,
+                             int64_t Dv, double gamma, double lamda, double lamda_value, void* stream);
+
+/* Tuning knob for K1 (process-wide): columns per thread (1, 2 or 4) and threads per block
+ * (multiple of 32, <= 256).  Results are bit-identical for every setting. */
+int cusrl_b200_gae_set_config(int vec, int threads);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  advantage statistics + normalisation -- replaces AdvantageNormalization.normalize_,
+ *     hook/on_policy/advantage.py:108-115 (torch.var_mean with correction=1 over all but the last dim)
+ *   stats:      mean_var[0:Dv] = mean, mean_var[Dv:2Dv] = unbiased variance of adv[E,Dv]
+ *   normalize:  adv = (adv - mean) / sqrt(var + eps)      (true division, in place)
+ *   Between the two calls the caller may merge mean_var across ranks (utils/distributed.py:175-183).
+ *   scratch: cusrl_b200_advantage_stats_scratch_bytes(Dv) bytes, any content, 16-byte aligned. */
+size_t cusrl_b200_advantage_stats_scratch_bytes(int64_t Dv);
+int cusrl_b200_advantage_stats_f32(const float* advantage, int64_t E, int64_t Dv, float* mean_var,
+                                   void* scratch, size_t scratch_bytes, void* stream);
+int cusrl_b200_advantage_normalize_f32(float* advantage, int64_t E, int64_t Dv, const float* mean_var,
+                                       float eps, void* stream);
+/* Equal-weight cross-rank merge of W stacked [mean(Dv) | var(Dv)] rows (utils/distributed.py:175-183):
+ *   mean_g = mean_r(mean_r);  var_g = mean_r(var_r + (mean_r - mean_g)^2).  gathered: [W, 2*Dv]. */
+int cusrl_b200_merge_mean_var_f32(const float* gathered, int64_t W, int64_t Dv, float* mean_var,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8  minibatch gather -- replaces MiniBatchSampler._sample `data.flatten(0,1)[indices]`,
+ *     sampler/mini_batch_sampler.py:76,89, for several leaves in ONE launch.
+ *   For field f and output row i:  dst_f[i, 0:row_bytes_f] = src_f[index[i], 0:row_bytes_f];
+ *   bytes row_bytes_f..dst_stride_f of each destination row are zero-filled (TMA-friendly padding).
+ *   Strides are in bytes.  src/dst row starts must be aligned to min(16, largest power of two
+ *   dividing both strides and row_bytes).  `fields_host` is a HOST array (copied into the launch). */
+typedef struct {
+  const void* src;     /* [E rows] device */
+  void* dst;           /* [n_index rows] device */
+  int64_t row_bytes;   /* payload bytes per row */
+  int64_t src_stride;  /* bytes between source rows (>= row_bytes) */
+  int64_t dst_stride;  /* bytes between destination rows (>= row_bytes) */
+} cusrl_b200_gather_field;
+#define CUSRL_B200_MAX_GATHER_FIELDS 24
+int cusrl_b200_gather_rows(const cusrl_b200_gather_field* fields_host, int n_fields,
+                           const int64_t* index, int64_t n_index, int64_t n_src_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  fused PPO objective, forward + unit gradients, one launch over the minibatch -- replaces
+ *     OnPolicyPreparation.objective (hook/on_policy/common.py:29-43) with NormalDist log_prob/entropy
+ *     (nn/module/distribution.py:195-213), _ppo_surrogate_loss / PpoSurrogateLoss / EntropyLoss
+ *     (hook/on_policy/ppo.py:10-18,50-55,82-84) and ValueLoss / _clipped_value_loss
+ *     (hook/on_policy/value.py:85-89,121-137), plus the autograd gradients of their weighted sum.
+ *   inputs  mean,action [B,A]; std [A] (state-independent StddevVector, distribution.py:232-245);
+ *           logp_old, advantage [B,1]; ret, value_old, curr_value [B,Dv]
+ *   per-sample outputs (any may be NULL): logp, entropy, logp_ratio, prob_ratio [B,1]
+ *   losses[0..2]  = value_loss*w_v, surrogate_loss*w_s, entropy_loss*w_e   (already weighted)
+ *   metrics[0..2] = mean|logp_ratio|, mean entropy, mean over B of sum_Dv curr_value
+ *                   (agent.record in common.py:45-49, value.py:139-141)
+ *   unit gradients d(loss_k)/d(.):  d_mean [B,A] (surrogate), d_std_surr [A], d_std_ent [A],
+ *                   d_value [B,Dv] (value loss).  Any gradient pointer may be NULL.
+ *   value_clip <= 0 selects plain MSE (value.py:131-133).  1 <= A <= 32, Dv >= 1.
+ *   has_value=0 skips the value loss (curr_value/ret/value_old may be NULL).
+ *   scratch: cusrl_b200_ppo_loss_scratch_bytes(A) bytes, 16-byte aligned. */
+size_t cusrl_b200_ppo_loss_scratch_bytes(int64_t A);
+int cusrl_b200_ppo_loss_f32(const float* mean, const float* std, const float* action,
+                            const float* logp_old, const float* advantage, const float* ret,
+                            const float* value_old, const float* curr_value, int64_t B, int64_t A,
+                            int64_t Dv, int has_value, float clip_ratio, float w_surrogate,
+                            float w_entropy, float w_value, float value_clip, float* logp,
+                            float* entropy, float* logp_ratio, float* prob_ratio, float* losses,
+                            float* metrics, float* d_mean, float* d_std_surr, float* d_std_ent,
+                            float* d_value, void* scratch, size_t scratch_bytes, void* stream);
+/* x[i] *= *scale_dev (in place, n floats); used to apply an upstream autograd scalar. */
+int cusrl_b200_scale_f32(float* x, int64_t n, const float* scale_dev, void* stream);
+
+/* Diagonal-normal KL(old||new) statistics for OnPolicyStatistics.post_update
+ * (hook/on_policy/stats.py:29-40, distribution.py:215-218).  All per-sample inputs are [E,A] or [E,1];
+ * std_new [A].  out[0..2] = mean KL, mean(advantage*exp(logp_new-logp_old)), mean(std_new). */
+size_t cusrl_b200_policy_stats_scratch_bytes(void);
+int cusrl_b200_policy_stats_f32(const float* mean_old, const float* std_old, const float* mean_new,
+                                const float* std_new, const float* action, const float* logp_old,
+                                const float* advantage, int64_t E, int64_t A, float* out,
+                                void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  gradient-norm clip + Adam on a flat parameter arena -- replaces GradientClipping.pre_optim
+ *     (hook/on_policy/gradient_clipping.py:56-75, torch clip_grad_norm_) and torch.optim.Adam.step
+ *     (preset/optimizer.py:9-23).
+ *   grad_sumsq: accumulates sum(g^2) of g[0:n] into *sumsq_dev (double; caller zeroes it first).
+ *   clip_coef:  *norm_dev = sqrt(sumsq); *coef_dev = min(1, max_norm / (norm + 1e-6)).
+ *   adam_step:  g' = g * (*coef_dev) (coef_dev==NULL: 1); m,v,p updated as torch.optim.Adam
+ *               (amsgrad=False, maximize=False); weight_decay is the L2 (non-decoupled) form. */
+int cusrl_b200_grad_sumsq_f32(const float* grad, int64_t n, double* sumsq_dev, void* stream);
+int cusrl_b200_clip_coef_f32(const double* sumsq_dev, float max_norm, float* norm_dev, float* coef_dev,
+                             void* stream);
+int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t n, const float* coef_dev, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSRL_B200_H_ */

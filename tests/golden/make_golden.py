@@ -1,0 +1,292 @@
+"""Generate the golden fixtures in this directory from the LIVE reference (chengruiz/cusrl).
+
+Run in the build container only (the reference is mounted read-only at /root/reference and does not
+exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own hooks / sampler / agent (with two tiny stand-in modules for the
+missing pure-Python deps ``gymnasium`` and ``objprint``, see ``_shims/``), feeds them seeded inputs and
+stores inputs + outputs as ``.npz``.  The fixtures pin ``oracle/ppo_path.py`` (tests/test_oracle_golden.py)
+and are what the ``-m gpu`` parity tests compare the CUDA path against.  Nothing here is product code.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+HERE = Path(__file__).resolve().parent
+REFERENCE = Path(os.environ.get("CUSRL_REFERENCE", "/root/reference"))
+sys.path.insert(0, str(HERE / "_shims"))
+sys.path.insert(0, str(REFERENCE))
+
+import contextlib  # noqa: E402
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import cusrl  # noqa: E402
+from cusrl.hook.on_policy.advantage import AdvantageNormalization  # noqa: E402
+from cusrl.hook.on_policy.gae import GeneralizedAdvantageEstimation, _generalized_advantage_estimation  # noqa: E402
+from cusrl.hook.on_policy.ppo import _ppo_surrogate_loss  # noqa: E402
+from cusrl.hook.on_policy.value import ValueComputation, _clipped_value_loss  # noqa: E402
+from cusrl.nn.module.distribution import NormalDist  # noqa: E402
+from cusrl.sampler.mini_batch_sampler import MiniBatchSampler, TemporalMiniBatchSampler  # noqa: E402
+from cusrl.template.buffer import Buffer  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def save(name: str, **arrays):
+    np.savez_compressed(HERE / f"{name}.npz", **{k: npy(v) for k, v in arrays.items()})
+    print(f"wrote {name}.npz: " + ", ".join(f"{k}{tuple(npy(v).shape)}" for k, v in arrays.items()))
+
+
+# ------------------------------------------------------------------------------------------------
+def make_gae():
+    cases = {}
+    g = torch.Generator().manual_seed(0)
+    for tag, (T, N, Dv, p_done, gamma, lamda, lamda_value) in {
+        "a": (24, 64, 1, 0.05, 0.99, 0.95, None),
+        "b": (24, 64, 1, 0.05, 0.99, 0.95, 0.9),
+        "c": (5, 7, 3, 0.3, 0.9, 0.8, None),
+        "d": (1, 4, 1, 0.5, 0.99, 0.95, 0.5),
+        "e": (33, 10, 2, 0.1, 0.995, 1.0, 0.0),
+    }.items():
+        reward = torch.randn(T, N, Dv, generator=g)
+        value = torch.randn(T, N, Dv, generator=g)
+        next_value = torch.randn(T, N, Dv, generator=g)
+        done = torch.rand(T, N, 1, generator=g) < p_done
+        hook = GeneralizedAdvantageEstimation(gamma=gamma, lamda=lamda, lamda_value=lamda_value)
+        data = {"reward": reward, "done": done, "value": value, "next_value": next_value}
+        hook._compute_advantage_and_return(data)
+        cases.update({
+            f"{tag}_reward": reward, f"{tag}_value": value, f"{tag}_next_value": next_value, f"{tag}_done": done,
+            f"{tag}_hyper": np.array([gamma, lamda, -1.0 if lamda_value is None else lamda_value], dtype=np.float64),
+            f"{tag}_advantage": data["advantage"], f"{tag}_return": data["return"],
+        })
+    # the reference's own known-answer case (cusrl_test/hook/on_policy/test_gae.py:8-16)
+    ka = _generalized_advantage_estimation(
+        reward=torch.ones(3, 1, 1), done=torch.tensor([[[False]], [[True]], [[False]]]),
+        value=torch.zeros(3, 1, 1), next_value=torch.zeros(3, 1, 1), gamma=0.5, lamda=1.0)
+    cases["known_answer"] = ka
+    save("gae", **cases)
+
+
+def make_advnorm():
+    g = torch.Generator().manual_seed(1)
+    out = {}
+    hook = AdvantageNormalization()
+    for tag, shape in {"a": (24, 64, 1), "b": (6, 10, 3), "c": (2, 1, 1)}.items():
+        adv = torch.randn(*shape, generator=g) * 3.0 + 1.5
+        out[f"{tag}_in"] = adv.clone()
+        hook.normalize_(adv)
+        out[f"{tag}_out"] = adv
+    # cross-rank merge arithmetic of utils/distributed.py:175-183, evaluated on stacked per-rank stats
+    means = torch.randn(4, 2, generator=g)
+    variances = torch.rand(4, 2, generator=g) + 0.5
+    mean = torch.mean(means, dim=0)
+    var = torch.mean(variances + (means - mean).square(), dim=0)
+    out.update(merge_means=means, merge_vars=variances, merge_mean=mean, merge_var=var)
+    save("advnorm", **out)
+
+
+def make_next_value():
+    g = torch.Generator().manual_seed(2)
+    out = {}
+    for tag, (T, N, Dv) in {"a": (24, 32, 1), "b": (4, 6, 2)}.items():
+        value = torch.randn(T, N, Dv, generator=g)
+        boot = torch.randn(N, Dv, generator=g)
+        terminated = torch.rand(T, N, 1, generator=g) < 0.1
+        truncated = (torch.rand(T, N, 1, generator=g) < 0.1) & ~terminated
+        next_obs = torch.randn(T, N, 3, generator=g)
+        buffer = Buffer(T, N, device="cpu")
+        buffer["value"] = value
+        buffer["terminated"] = terminated
+        buffer["truncated"] = truncated
+        buffer["next_observation"] = next_obs
+        hook = ValueComputation(termination_value=0.25 if tag == "b" else 0.0)
+        critic = SimpleNamespace(evaluate=lambda state, memory=None: boot)
+        hook.agent = SimpleNamespace(
+            critic=critic, autocast=contextlib.nullcontext,
+            environment_spec=SimpleNamespace(final_state_is_missing=True))
+        hook.init()  # -> bootstrap_truncated_states = False (IsaacLab-style env, value.py:38-40)
+        hook.pre_update(buffer)
+        out.update({f"{tag}_value": value, f"{tag}_boot": boot, f"{tag}_terminated": terminated,
+                    f"{tag}_truncated": truncated, f"{tag}_termination_value": np.float32(hook.termination_value),
+                    f"{tag}_next_value": buffer["next_value"]})
+    save("next_value", **out)
+
+
+def make_objective():
+    g = torch.Generator().manual_seed(3)
+    out = {}
+    for tag, (B, A, Dv, value_clip) in {"a": (256, 12, 1, None), "b": (100, 12, 1, 0.2), "c": (37, 5, 2, None)}.items():
+        dist = NormalDist(8, A)
+        with torch.no_grad():
+            dist.std.param.copy_(torch.rand(A, generator=g) * 0.8 + 0.4)
+        mean = torch.randn(B, A, generator=g).requires_grad_(True)
+        action = (mean.detach() + torch.randn(B, A, generator=g) * 0.7)
+        std = dist.std(mean)  # StddevVector.forward: param.repeat(B, 1)
+        params = {"mean": mean, "std": std}
+        logp = dist.compute_logp(params, action)
+        entropy = dist.compute_entropy(params)
+        logp_old = (logp.detach() + torch.randn(B, 1, generator=g) * 0.3)
+        advantage = torch.randn(B, 1, generator=g)
+        if Dv != 1:
+            advantage = advantage  # surrogate requires [B,1]; value dims are independent
+        ret = torch.randn(B, Dv, generator=g)
+        value_old = ret + torch.randn(B, Dv, generator=g) * 0.5
+        curr_value = (value_old + torch.randn(B, Dv, generator=g) * 0.3).requires_grad_(True)
+        logp_ratio = logp - logp_old
+        prob_ratio = logp_ratio.exp()
+        w_v, w_s, w_e, clip = 0.5, 1.0, 0.005, 0.2
+        l_v = (torch.nn.functional.mse_loss(ret, curr_value) if value_clip is None
+               else _clipped_value_loss(value_old, curr_value, ret, value_clip)) * w_v
+        l_s = _ppo_surrogate_loss(advantage, prob_ratio, clip) * w_s
+        l_e = -entropy.mean() * w_e
+        loss = sum({"value_loss": l_v, "surrogate_loss": l_s, "entropy_loss": l_e}.values())
+        loss.backward()
+        out.update({
+            f"{tag}_mean": mean, f"{tag}_std_param": dist.std.param, f"{tag}_action": action,
+            f"{tag}_logp_old": logp_old, f"{tag}_advantage": advantage, f"{tag}_return": ret,
+            f"{tag}_value_old": value_old, f"{tag}_curr_value": curr_value,
+            f"{tag}_hyper": np.array([clip, w_s, w_e, w_v, -1.0 if value_clip is None else value_clip]),
+            f"{tag}_logp": logp, f"{tag}_entropy": entropy, f"{tag}_logp_ratio": logp_ratio,
+            f"{tag}_prob_ratio": prob_ratio,
+            f"{tag}_losses": torch.stack([l_v, l_s, l_e]), f"{tag}_total": loss,
+            f"{tag}_d_mean": mean.grad, f"{tag}_d_std": dist.std.param.grad, f"{tag}_d_value": curr_value.grad,
+        })
+        # KL / statistics (hook/on_policy/stats.py:29-40)
+        mean_old = mean.detach() + torch.randn(B, A, generator=g) * 0.1
+        std_old = std.detach() * (1.0 + torch.rand(B, A, generator=g) * 0.1)
+        kl = dist.compute_kl_div({"mean": mean_old, "std": std_old}, {"mean": mean.detach(), "std": std.detach()})
+        iwa = advantage * (dist.compute_logp({"mean": mean.detach(), "std": std.detach()}, action) - logp_old).exp()
+        out.update({f"{tag}_mean_old": mean_old, f"{tag}_std_old": std_old,
+                    f"{tag}_stats": torch.stack([kl.mean(), iwa.mean(), std.detach().mean()])})
+    # reference known-answer tests (cusrl_test/hook/on_policy/test_ppo.py:8-14)
+    out["known_surrogate"] = _ppo_surrogate_loss(torch.tensor([[1.0], [-2.0]]), torch.tensor([[1.5], [0.5]]), 0.2)
+    save("objective", **out)
+
+
+def make_sampler():
+    out = {}
+    T, N = 6, 8
+    buffer = Buffer(T, N, device="cpu")
+    buffer["observation"] = torch.arange(T * N * 3, dtype=torch.float32).reshape(T, N, 3)
+    buffer["flag"] = (torch.arange(T * N).reshape(T, N, 1) % 3) == 0
+    buffer.full = True
+    for cls, tag in ((MiniBatchSampler, "flat"), (TemporalMiniBatchSampler, "temporal")):
+        torch.manual_seed(1234)
+        sampler = cls(num_epochs=3, num_mini_batches=4 if tag == "flat" else 2)
+        idx_rows, obs_rows, meta_rows = [], [], []
+        # capture the index slices through the public _sample hook
+        captured = []
+        orig = sampler._sample
+
+        def spy(name, data, indices, _orig=orig):
+            if name == "observation":
+                captured.append(indices.clone())
+            return _orig(name, data, indices)
+
+        sampler._sample = spy
+        for meta, batch in sampler(buffer):
+            obs_rows.append(batch["observation"].clone())
+            meta_rows.append([meta["epoch_index"], meta["mini_batch_index"], meta["total_epochs"],
+                              meta["total_mini_batches"], int(meta["temporal"])])
+        out[f"{tag}_indices"] = torch.stack(captured)
+        out[f"{tag}_obs"] = torch.stack(obs_rows)
+        out[f"{tag}_meta"] = np.array(meta_rows)
+    out["obs"] = buffer["observation"]
+    save("sampler", **out)
+
+
+def make_iteration():
+    """A whole reference PPO iteration (rollout + update) on CPU at a small size."""
+    from cusrl.template.environment import EnvironmentSpec
+
+    obs_dim, act_dim, N, T = 19, 5, 16, 6
+    hidden = (32, 16, 8)
+    torch.manual_seed(7)
+    factory = cusrl.preset.ppo.PpoAgentFactory(
+        num_steps_per_update=T, actor_hidden_dims=hidden, critic_hidden_dims=hidden, activation_fn="ELU", lr=1e-3,
+        sampler_epochs=5, sampler_mini_batches=4, orthogonal_init=False, entropy_loss_weight=0.005,
+        desired_kl_divergence=0.015, device="cpu")
+    spec = EnvironmentSpec(num_instances=N, observation_dim=obs_dim, action_dim=act_dim, reward_dim=1,
+                           autoreset=True, final_state_is_missing=True)
+    agent = factory(spec)
+    init_state = {net: {k: v.clone() for k, v in agent.state_dict()[net].items()} for net in ("actor", "critic")}
+    out = {}
+    for net in ("actor", "critic"):
+        for k, v in init_state[net].items():
+            out[f"param0/{net}.{k}"] = v
+    g = torch.Generator().manual_seed(11)
+    obs = torch.randn(N, obs_dim, generator=g)
+    noises = []
+    for t in range(T):
+        # make action sampling reproducible outside the reference: capture the noise rsample draws
+        torch.manual_seed(1000 + t)
+        action = agent.act(obs)
+        noises.append((action - agent.transition["action_dist"]["mean"]) / agent.transition["action_dist"]["std"])
+        next_obs = torch.randn(N, obs_dim, generator=g)
+        reward = torch.randn(N, 1, generator=g)
+        terminated = torch.rand(N, 1, generator=g) < 0.15
+        truncated = (torch.rand(N, 1, generator=g) < 0.1) & ~terminated
+        ready = agent.step(next_obs, reward, terminated, truncated)
+        obs = next_obs
+    assert ready
+    for key, leaf in agent.buffer.storage.items():
+        out[f"buffer/{key}"] = leaf.clone()
+    out["noise"] = torch.stack(noises)
+
+    perms, minibatch_logs = [], []
+    real_randperm = torch.randperm
+
+    def spy_randperm(*args, **kwargs):
+        r = real_randperm(*args, **kwargs)
+        perms.append(r.clone())
+        return r
+
+    real_record = agent.record
+
+    def spy_record(metrics=None, /, **kwargs):
+        if "surrogate_loss" in kwargs:
+            minibatch_logs.append([float(kwargs["value_loss"]), float(kwargs["surrogate_loss"]), float(kwargs["entropy_loss"])])
+        return real_record(metrics, **kwargs)
+
+    torch.manual_seed(99)
+    torch.randperm = spy_randperm
+    agent.record = spy_record
+    try:
+        metrics = agent.update()
+    finally:
+        torch.randperm = real_randperm
+    out["perms"] = torch.stack(perms[:5])          # 5 training epochs (mini_batch_sampler.py:56,68)
+    out["stats_perm"] = perms[5]                   # OnPolicyStatistics' sampler (stats.py:32)
+    out["minibatch_losses"] = np.array(minibatch_logs, dtype=np.float64)
+    for key in ("advantage", "return", "next_value"):
+        out[f"post/{key}"] = agent.buffer.storage[key].clone()
+    final_state = agent.state_dict()
+    for net in ("actor", "critic"):
+        for k, v in final_state[net].items():
+            out[f"param1/{net}.{k}"] = v
+    out["metric_names"] = np.array(sorted(metrics))
+    out["metric_values"] = np.array([metrics[k] for k in sorted(metrics)], dtype=np.float64)
+    out["lr_after"] = np.float64(agent.optimizer.param_groups[0]["lr"])
+    save("iteration", **out)
+
+
+if __name__ == "__main__":
+    make_gae()
+    make_advnorm()
+    make_next_value()
+    make_objective()
+    make_sampler()
+    make_iteration()
