@@ -1,0 +1,332 @@
+"""Benchmark of the B200 PPO hot path (contract: see the task statement / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs 65536] [--rollout 24]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one PPO iteration on synthetic Anymal-C-rough-shaped data: 24 x (agent.act + agent.step) +
+agent.update() (5 epochs x 4 minibatches), i.e. exactly the sections the reference times as "agent"
+(cusrl/template/trainer.py:296-321, Perf/agent_fps at :385-393).  metric = env-steps/s = rollout * envs_global /
+time.  Strong scaling: the 65536 environments of BASELINE.json are split over the ranks.
+
+Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+OBS, ACT = 235, 12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="global number of environments")
+    ap.add_argument("--rollout", type=int, default=24)
+    ap.add_argument("--cpu-envs", type=int, default=2048, help="environments of the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks() -> tuple[dict, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return json.loads(f.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+class RolloutData:
+    """Synthetic env stream: obs ~ N(0,1), reward ~ N(0,1), terminated ~ B(0.01),
+    truncated ~ B(0.001); generated once, either resident in HBM or in pinned host memory."""
+
+    def __init__(self, T: int, N: int, device, seed: int, pinned_host: bool):
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.obs = torch.randn(T + 1, N, OBS, device=device, generator=g)
+        self.reward = torch.randn(T, N, 1, device=device, generator=g)
+        self.terminated = torch.rand(T, N, 1, device=device, generator=g) < 0.01
+        self.truncated = torch.rand(T, N, 1, device=device, generator=g) < 0.001
+        if pinned_host:
+            for k in ("obs", "reward", "terminated", "truncated"):
+                setattr(self, k, getattr(self, k).cpu().pin_memory())
+        self.T, self.N = T, N
+
+
+def run_iteration(agent, data: RolloutData) -> dict:
+    """24 x (act, step) + update: the reference's "agent" timer sections."""
+    for t in range(data.T):
+        action = agent.act(data.obs[t])
+        ready = agent.step(data.obs[t + 1], data.reward[t], data.terminated[t], data.truncated[t])
+    assert ready
+    del action
+    return agent.update()
+
+
+def time_iterations(agent, data, steps: int, warmup: int, distributed: bool) -> tuple[float, dict]:
+    """(seconds for `steps` iterations as the max over ranks, last metrics); device-timed with CUDA events."""
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        metrics = run_iteration(agent, data)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        metrics = run_iteration(agent, data)
+    end.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    seconds = start.elapsed_time(end) * 1e-3
+    if distributed:
+        t = torch.tensor([seconds], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = t.item()
+    return seconds, metrics
+
+
+# ------------------------------------------------------------------------------------------------
+def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
+    """Achieved HBM bandwidth of the GAE scan kernel, timed live: a CUDA graph of launches over rotating buffer
+    sets whose footprint exceeds L2, CUDA events on the launching stream."""
+    from cusrl_b200 import ops
+
+    E = T * N
+    n_sets = max(2, int(300e6 // (21 * E)) + 1)
+    sets = []
+    for _ in range(n_sets):
+        d = {k: torch.randn(T, N, 1, device="cuda") for k in ("reward", "value", "nv", "adv", "ret")}
+        d["done"] = torch.rand(T, N, 1, device="cuda") < 0.011
+        sets.append(d)
+
+    def launch_all():
+        for d in sets:
+            ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95, advantage=d["adv"], ret=d["ret"])
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        launch_all()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        launch_all()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) * 1e-3 / n_sets)
+    sec = sum(times) / len(times)
+    achieved = 21 * E / sec / 1e9
+    peak = float(peaks["hbm_gbs"])
+    return {"kernel": "gae_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+            "bytes_per_launch": 21 * E, "us_per_launch": round(sec * 1e6, 2)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_iteration_rate(envs: int, T: int, iters: int, warmup: int, threads: int) -> tuple[float, float]:
+    """env-steps/s of the CPU oracle port (the reference's PyTorch-CPU arithmetic restated, oracle/ppo_path.py)
+    on `threads` host threads, for a bounded sample of `envs` environments."""
+    from oracle import ppo_path as O
+
+    torch.set_num_threads(threads)
+    cfg = O.PpoConfig()
+    g = torch.Generator().manual_seed(0)
+    agent = O.OraclePpo(cfg, O.init_mlp_params_ref(cfg.obs_dim, cfg.act_dim, cfg.hidden, generator=g))
+    obs = torch.randn(T + 1, envs, cfg.obs_dim, generator=g)
+    reward = torch.randn(T, envs, 1, generator=g)
+    term = torch.rand(T, envs, 1, generator=g) < 0.01
+    trunc = torch.rand(T, envs, 1, generator=g) < 0.001
+
+    def iteration():
+        leaves = {k: [] for k in ("observation", "action", "action_logp", "action_dist.mean", "action_dist.std", "value")}
+        for t in range(T):
+            tr = agent.act(obs[t], torch.randn(envs, cfg.act_dim, generator=g))
+            for k in leaves:
+                leaves[k].append(tr[k])
+        buf = {k: torch.stack(v) for k, v in leaves.items()}
+        buf.update(next_observation=obs[1:], reward=reward.clone(), terminated=term, truncated=trunc, done=term | trunc)
+        perms = [torch.randperm(T * envs, generator=g) for _ in range(cfg.epochs)]
+        agent.update(buf, perms)
+
+    for _ in range(warmup):
+        iteration()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        iteration()
+    dt = (time.perf_counter() - t0) / iters
+    return T * envs / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    T = args.rollout
+    host_threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # the reference's own CPU path (oracle port), rank 0 only, bounded sample of the same workload
+        if rank != 0:
+            return
+        rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=max(1, args.steps), warmup=min(1, args.warmup),
+                                           threads=host_threads)
+        line = {
+            "impl": "reference", "metric": "ppo_env_steps_per_sec", "value": round(rate, 1), "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": round(rate, 1), "unit": "env-steps/s", "cores": host_threads, "kind": "port",
+                             "sample": f"{args.cpu_envs} envs x {T} steps per iteration (of {args.envs}), same preset"},
+            "e2e": {"value": round(rate, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    import cusrl_b200 as C
+    from cusrl_b200 import ops
+    from cusrl_b200.runtime import CONFIG, configure_distributed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (cusrl_b200 has no CPU fallback)")
+    distributed = world > 1
+    if distributed:
+        configure_distributed()
+    device = CONFIG.device
+    if args.envs % world:
+        raise SystemExit("--envs must be divisible by the number of ranks")
+    N = args.envs // world
+    peaks, which = measured_peaks()
+
+    torch.manual_seed(42 + rank)  # per-rank seed like the reference (utils/misc.py:163)
+    env = C.SyntheticEnvironment(N, OBS, ACT, device=device, seed=42 + rank)
+    agent = C.anymal_c_rough_ppo(device=device).from_environment(env)
+
+    # ---- value: inputs resident in HBM
+    data = RolloutData(T, N, device, seed=1000 + rank, pinned_host=False)
+    launches0 = ops.launch_count()
+    with ClockSampler(device.index or 0) as clocks:
+        seconds, metrics = time_iterations(agent, data, args.steps, args.warmup, distributed)
+    launches = (ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    value = args.steps * T * args.envs / seconds
+
+    # ---- e2e: the same iterations driven through agent.act / agent.step with HOST (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        del data
+        host = RolloutData(T, N, device, seed=1000 + rank, pinned_host=True)
+        e_steps = max(1, min(args.steps, 3))
+        e_sec, _ = time_iterations(agent, host, e_steps, 1, distributed)
+        per_iter_in = T * N * (OBS * 4 + 4 + 1 + 1) * 2  # obs_t for act + next_obs_t for step, reward, flags
+        per_iter_out = T * N * ACT * 4 + 4 * 16
+        e2e = {"value": round(e_steps * T * args.envs / e_sec, 1), "unit": "env-steps/s",
+               "h2d_bytes_per_step": per_iter_in * world, "d2h_bytes_per_step": per_iter_out * world,
+               "steps": e_steps, "note": "pinned host tensors through agent.act/agent.step; metrics read back per update"}
+        del host
+
+    line = None
+    if rank == 0:
+        roof = gae_roofline(T, N, peaks, which)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=2, warmup=1, threads=host_threads)
+            cpu = {"value": round(rate, 1), "unit": "env-steps/s", "cores": host_threads, "kind": "port",
+                   "sample": f"{args.cpu_envs} envs x {T} steps, 1 warm-up + 2 timed iterations ({dt:.2f} s each)"}
+        line = {
+            "metric": "ppo_env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "last_metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")},
+        }
+    if distributed:
+        torch.distributed.barrier()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int) -> dict:
+    return {
+        "workload": "synthetic Anymal-C-rough-shaped obs/act (235/12), MLP 512-256-128 ELU actor-critic PPO, "
+                    f"{args.envs} envs x {args.rollout} steps, 5 epochs x 4 minibatches",
+        "envs_global": args.envs, "envs_per_rank": args.envs // max(world, 1), "rollout_steps": args.rollout,
+        "parallelism": f"dp{world} (env axis), NCCL flat-gradient allreduce per minibatch",
+        "l2_policy": "working set (rollout buffer >= 0.4 GB per rank, minibatches >= 100 MB) exceeds the 126 MB L2",
+        "timed_region": "24 x (agent.act + agent.step) + agent.update per step; synthetic env data precomputed",
+    }
+
+
+if __name__ == "__main__":
+    main()

@@ -94,9 +94,14 @@ def load() -> ctypes.CDLL:
     return lib
 
 
-def check(code: int, what: str) -> None:
+KERNEL_LAUNCHES = 0  # launches of cusrl_b200 kernels issued through this binding (bench.py's gpu_launches)
+
+
+def check(code: int, what: str, launches: int = 1) -> None:
     """Raise like the reference's hooks do (ValueError for bad arguments, RuntimeError otherwise)."""
+    global KERNEL_LAUNCHES
     if code == 0:
+        KERNEL_LAUNCHES += launches
         return
     msg = load().cusrl_b200_last_error().decode(errors="replace")
     if code == -1:

@@ -83,39 +83,42 @@ struct GaeParams {
   int two_lambda;
 };
 
-template <int VEC, int U, bool FUSED>
-__global__ void __launch_bounds__(256) gae_kernel(const GaeParams p) {
-  const int64_t C = p.N * p.Dv;
-  const int64_t c0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * VEC;
+template <int VEC, int U, bool FUSED, typename idx_t>
+__global__ void __launch_bounds__(128, (U * VEC >= 16 ? 4 : 6)) gae_kernel(const GaeParams p) {
+  const idx_t C = (idx_t)(p.N * p.Dv);
+  const idx_t N = (idx_t)p.N;
+  const idx_t c0 = (idx_t)(blockIdx.x * (idx_t)blockDim.x + threadIdx.x) * VEC;
   if (c0 >= C) return;
   // flag column: done broadcasts over Dv (gae.py:19); VEC > 1 is only launched with Dv == 1
-  const int64_t n0 = (VEC == 1) ? c0 / p.Dv : c0;
+  const idx_t n0 = (VEC == 1) ? (idx_t)(c0 / (idx_t)p.Dv) : c0;
+  const int T = (int)p.T;
 
   float adv_next[VEC], adv2_next[VEC], v_next[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) adv_next[k] = 0.f, adv2_next[k] = 0.f, v_next[k] = 0.f;
   if (FUSED) VecLoad<VEC>::ld(p.boot + c0, v_next);
 
-  for (int64_t t_hi = p.T; t_hi > 0; t_hi -= U) {
+  for (int t_hi = T; t_hi > 0; t_hi -= U) {
     float r[U][VEC], v[U][VEC], nv[U][VEC];
     uint8_t f0[U][VEC], f1[U][VEC];
     // ---- issue every load of the chunk first
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t t = t_hi - 1 - u;
+      const int t = t_hi - 1 - u;
       if (t >= 0) {
-        const int64_t off = t * C + c0;
+        const idx_t off = (idx_t)t * C + c0;
+        const idx_t foff = (idx_t)t * N + n0;
         VecLoad<VEC>::ld(p.reward + off, r[u]);
         VecLoad<VEC>::ld(p.value + off, v[u]);
         if (!FUSED) VecLoad<VEC>::ld(p.next_value + off, nv[u]);
-        VecLoad<VEC>::ldf(p.done + t * p.N + n0, f0[u]);
-        if (FUSED) VecLoad<VEC>::ldf(p.truncated + t * p.N + n0, f1[u]);
+        VecLoad<VEC>::ldf(p.done + foff, f0[u]);
+        if (FUSED) VecLoad<VEC>::ldf(p.truncated + foff, f1[u]);
       }
     }
     // ---- then the sequential recurrence
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t t = t_hi - 1 - u;
+      const int t = t_hi - 1 - u;
       if (t >= 0) {
         float adv[VEC], rt[VEC];
 #pragma unroll
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeParams p) {
           // gae.py:17  advantage = reward + next_value * gamma - value
           const float delta = __fsub_rn(__fadd_rn(r[u][k], __fmul_rn(nvk, p.gamma)), v[u][k]);
           float a = delta, a2 = delta;
-          if (t != p.T - 1) {
+          if (t != T - 1) {
             // gae.py:19  advantage[t] += not_done[t] * (gamma*lamda) * advantage[t+1]
             const float m = done ? 0.f : p.c_adv;
             a = __fadd_rn(delta, __fmul_rn(m, adv_next[k]));
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeParams p) {
           // gae.py:99-110  return = value + advantage (or the lamda_value scan)
           rt[k] = __fadd_rn(v[u][k], p.two_lambda ? a2 : a);
         }
-        const int64_t off = t * C + c0;
+        const idx_t off = (idx_t)t * C + c0;
         VecLoad<VEC>::st(p.advantage + off, adv);
         if (p.ret) VecLoad<VEC>::st(p.ret + off, rt);
         if (FUSED && p.next_value_out) VecLoad<VEC>::st(p.next_value_out + off, nv[u]);
@@ -161,7 +164,32 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeParams p) {
   }
 }
 
-static int g_gae_vec = 2, g_gae_threads = 128;  // tuning knobs, see cusrl_b200_gae_set_config
+static int g_gae_vec = 1, g_gae_threads = 128;  // tuning knobs, see cusrl_b200_gae_set_config
+
+template <int VEC, bool FUSED, typename idx_t>
+static void launch_gae_u(const GaeParams& p, unsigned grid, int threads, cudaStream_t s) {
+  // U >= T puts the whole rollout of a column in registers: every load of the kernel is issued
+  // before the first dependent instruction (one DRAM round trip instead of T/U of them).
+  if constexpr (VEC == 1) {
+    if (p.T <= 8)
+      gae_kernel<1, 8, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+    else if (p.T <= 16)
+      gae_kernel<1, 16, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+    else if (p.T <= 24)
+      gae_kernel<1, 24, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+    else if (p.T <= 32)
+      gae_kernel<1, 32, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+    else
+      gae_kernel<1, 16, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+  } else if constexpr (VEC == 2) {
+    if (p.T <= 12 || p.T == 24)
+      gae_kernel<2, 12, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+    else
+      gae_kernel<2, 8, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+  } else {
+    gae_kernel<4, 6, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
+  }
+}
 
 template <bool FUSED>
 static int launch_gae(const GaeParams& p, cudaStream_t s) {
@@ -183,13 +211,17 @@ static int launch_gae(const GaeParams& p, cudaStream_t s) {
   const int threads = g_gae_threads;
   const int64_t nthreads = (C + vec - 1) / vec;
   const unsigned grid = (unsigned)((nthreads + threads - 1) / threads);
-  constexpr int U = 8;
-  if (vec == 4)
-    gae_kernel<4, 6, FUSED><<<grid, threads, 0, s>>>(p);
-  else if (vec == 2)
-    gae_kernel<2, U, FUSED><<<grid, threads, 0, s>>>(p);
-  else
-    gae_kernel<1, U, FUSED><<<grid, threads, 0, s>>>(p);
+  // 64-bit indexing everywhere: ptxas strength-reduces it to pointer increments (fewer live
+  // registers than 32-bit offsets, checked with -Xptxas -v)
+#define CUSRL_GAE_DISPATCH(V) launch_gae_u<V, FUSED, int64_t>(p, grid, threads, s);
+  if (vec == 4) {
+    CUSRL_GAE_DISPATCH(4)
+  } else if (vec == 2) {
+    CUSRL_GAE_DISPATCH(2)
+  } else {
+    CUSRL_GAE_DISPATCH(1)
+  }
+#undef CUSRL_GAE_DISPATCH
   return check_launch("gae_kernel");
 }
 
@@ -326,7 +358,7 @@ using namespace cusrl_b200;
 extern "C" {
 
 int cusrl_b200_gae_set_config(int vec, int threads) {
-  if ((vec != 1 && vec != 2 && vec != 4) || threads < 32 || threads > 256 || (threads % 32)) return CUSRL_B200_EINVAL;
+  if ((vec != 1 && vec != 2 && vec != 4) || threads < 32 || threads > 128 || (threads % 32)) return CUSRL_B200_EINVAL;
   g_gae_vec = vec;
   g_gae_threads = threads;
   return 0;

@@ -32,6 +32,11 @@ __all__ = [
 _scratch: dict[tuple[int, str], torch.Tensor] = {}
 
 
+def launch_count() -> int:
+    """Number of cusrl_b200 kernel launches issued so far by this process."""
+    return _lib.KERNEL_LAUNCHES
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -173,7 +178,7 @@ def advantage_stats(advantage: torch.Tensor, out: torch.Tensor | None = None) ->
         _ptr(advantage, torch.float32, "advantage"), E, Dv, _ptr(out, torch.float32, "mean_var"),
         scratch.data_ptr(), scratch.numel(), _stream(),
     )  # fmt: skip
-    _lib.check(code, "advantage_stats")
+    _lib.check(code, "advantage_stats", launches=2)
     return out
 
 
@@ -287,7 +292,7 @@ def ppo_loss(
         _ptr(g("d_mean")), _ptr(g("d_std_surr")), _ptr(g("d_std_ent")), _ptr(g("d_value")),
         scratch.data_ptr(), scratch.numel(), _stream(),
     )  # fmt: skip
-    _lib.check(code, "ppo_loss")
+    _lib.check(code, "ppo_loss", launches=2)
     return out
 
 
@@ -321,7 +326,7 @@ def policy_stats(
         _ptr(std_new, f32, "std_new"), _ptr(action, f32, "action"), _ptr(logp_old, f32, "action_logp"),
         _ptr(advantage, f32, "advantage"), E, A, _ptr(out), scratch.data_ptr(), scratch.numel(), _stream(),
     )  # fmt: skip
-    _lib.check(code, "policy_stats")
+    _lib.check(code, "policy_stats", launches=2)
     return out
 
 
@@ -364,3 +369,55 @@ def adam_step_(
         float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _stream(),
     )  # fmt: skip
     _lib.check(code, "adam_step")
+
+
+# ---------------------------------------------------------------------------------------------- K6
+# Dense layers.  TEMPORARY (round-1 bring-up): these four functions call cuBLAS through torch so that
+# the end-to-end path and its parity tests exist before the tcgen05 kernels land; they are replaced by
+# the C-ABI entry points cusrl_b200_linear_{fwd,dgrad,wgrad}_tf32 and must not survive the round.
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+
+
+def _apply_act(z: torch.Tensor, act: int) -> torch.Tensor:
+    if act == 1:
+        return torch.nn.functional.elu(z)
+    if act == 2:
+        return torch.relu(z)
+    return z
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act: int) -> torch.Tensor:
+    """Y = act(X W^T + b) (reference nn/module/mlp.py:77-90: nn.Linear + activation)."""
+    _require_cuda(x, "x")
+    return _apply_act(torch.nn.functional.linear(x, w, b), act)
+
+
+def act_backward(dy: torch.Tensor, y: torch.Tensor, act: int) -> torch.Tensor:
+    """dZ = dY * act'(Z) expressed through the stored post-activation Y (ELU: y>0 ? 1 : y+1)."""
+    _require_cuda(dy, "dy")
+    if act == 1:
+        return dy * torch.where(y > 0, torch.ones_like(y), y + 1.0)
+    if act == 2:
+        return dy * (y > 0).to(dy.dtype)
+    return dy
+
+
+def linear_dgrad(dz: torch.Tensor, w: torch.Tensor, y_prev: torch.Tensor | None, act: int) -> torch.Tensor:
+    """dX = dZ W, multiplied by act'(previous layer output) when y_prev is given."""
+    _require_cuda(dz, "dz")
+    dx = dz @ w
+    return dx if y_prev is None else act_backward(dx, y_prev, act)
+
+
+def linear_wgrad(dz: torch.Tensor, x: torch.Tensor, out_w: torch.Tensor | None = None,
+                 out_b: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """dW = dZ^T X, db = column sums of dZ; accumulated into out_w / out_b when given."""
+    _require_cuda(dz, "dz")
+    if out_w is not None:
+        out_w.addmm_(dz.t(), x)
+        if out_b is not None:
+            out_b.add_(dz.sum(dim=0))
+        return out_w, out_b
+    return dz.t() @ x, dz.sum(dim=0)

@@ -1,0 +1,327 @@
+"""The on-policy actor-critic agent: rollout (`act` / `step`) and the hook-driven update loop.
+
+Interface-compatible with the reference's ``ActorCritic`` / ``ActorCriticFactory`` / ``HookList``
+(cusrl/template/actor_critic.py:23-320, cusrl/template/agent.py:25-391): same constructor arguments, same
+hook call order in ``update`` / ``_train_step``, same transition keys, numpy/torch I/O preservation in
+``act``.  Differences are confined to the implementation: parameters live in a flat arena
+(template/optimizer.py), the gradient allreduce is one in-place collective on that arena, metrics are
+flushed with one device-to-host copy, and ``autocast`` / ``compile`` are refused.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Iterable, Mapping
+from contextlib import contextmanager, nullcontext
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import distributed
+from ..environment import EnvironmentSpec
+from ..metrics import Metrics
+from ..runtime import device as resolve_device
+from .buffer import Buffer, Sampler
+from .hook import Hook, HookComposite
+
+__all__ = ["ActorCritic", "ActorCriticFactory", "HookList"]
+
+
+class HookList(list):
+    """List of hooks addressable by name (reference actor_critic.py:23-62)."""
+
+    def to_dict(self) -> dict[str, Hook]:
+        return {hook.name: hook for hook in self}
+
+    @classmethod
+    def from_dict(cls, data: dict[str, Hook]) -> "HookList":
+        return cls(hook.name_(name) for name, hook in data.items())
+
+    def __getattr__(self, name: str) -> Any:
+        for hook in self:
+            if hook.name == name:
+                return hook
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+
+    @classmethod
+    def coerce(cls, data: Any) -> "HookList":
+        if isinstance(data, (cls, list, tuple)):
+            return cls(data)
+        if isinstance(data, dict):
+            return cls.from_dict(data)
+        raise TypeError(f"Unsupported hooks payload: {type(data)!r}")
+
+
+@dataclass(kw_only=True)
+class ActorCriticFactory:
+    """Configuration that builds an :class:`ActorCritic` for an environment spec."""
+
+    num_steps_per_update: int
+    actor_factory: Any
+    critic_factory: Any
+    optimizer_factory: Any
+    sampler: Sampler
+    hooks: list
+    name: str = "Agent"
+    device: torch.device | str | None = None
+    compile: bool | str = False
+    autocast: bool | None | torch.dtype | str = False
+
+    def __post_init__(self):
+        self.hooks = HookList.coerce(self.hooks)
+
+    def __call__(self, environment_spec: EnvironmentSpec) -> "ActorCritic":
+        return ActorCritic(
+            environment_spec=environment_spec, actor_factory=self.actor_factory, critic_factory=self.critic_factory,
+            optimizer_factory=self.optimizer_factory, sampler=self.sampler, hooks=self.hooks,
+            num_steps_per_update=self.num_steps_per_update, name=self.name, device=self.device,
+            compile=self.compile, autocast=self.autocast)
+
+    def from_environment(self, environment) -> "ActorCritic":
+        return self(environment.spec)
+
+    def register_hook(self, hook: Hook, index: int | None = None, before: str | None = None, after: str | None = None):
+        """Insert a hook by index or relative to a named hook (reference actor_critic.py:97-137)."""
+        if (index is not None) + (before is not None) + (after is not None) > 1:
+            raise ValueError("Only one of index, before, or after can be specified")
+        if before is not None:
+            index = self.get_hook_index(before)
+        elif after is not None:
+            index = self.get_hook_index(after) + 1
+        elif index is None:
+            index = len(self.hooks)
+        self.hooks.insert(index, hook)
+        return self
+
+    def get_hook(self, hook_name: str) -> Hook:
+        return self.hooks[self.get_hook_index(hook_name)]
+
+    def get_hook_index(self, hook_name: str) -> int:
+        for i, hook in enumerate(self.hooks):
+            if hook.name == hook_name:
+                return i
+        raise ValueError(f"No hook named '{hook_name}' is registered")
+
+
+class ActorCritic:
+    """PPO-family agent whose algorithm is an ordered list of hooks."""
+
+    Factory = ActorCriticFactory
+    MODULES = ["actor", "critic", "hook"]
+    STATEFULS = ["optimizer"]
+
+    def __init__(self, environment_spec: EnvironmentSpec, actor_factory, critic_factory, optimizer_factory,
+                 sampler: Sampler, hooks: Iterable[Hook], num_steps_per_update: int, name: str = "Agent",
+                 device: torch.device | str | None = None, compile: bool | str = False,
+                 autocast: bool | None | torch.dtype | str = False):
+        if compile not in (False, None):
+            raise ValueError("cusrl_b200 runs hand-written sm_100a kernels: 'compile' must be False")
+        if autocast not in (False, None):
+            raise ValueError("cusrl_b200 computes in fp32 like the reference presets: 'autocast' must be False")
+        self.environment_spec = environment_spec
+        self.observation_dim = environment_spec.observation_dim
+        self.action_dim = environment_spec.action_dim
+        self.has_state = environment_spec.state_dim is not None
+        self.state_dim = environment_spec.state_dim or self.observation_dim
+        self.parallelism = environment_spec.num_instances
+        self.value_dim = environment_spec.reward_dim
+        self.num_steps_per_update = num_steps_per_update
+        self.buffer_capacity = num_steps_per_update
+        self.name = name
+        self.device = resolve_device(device)
+        self.compile, self.autocast_enabled, self.dtype = False, False, torch.float32
+        self.inference_mode = False
+        self.deterministic = False
+        self.transition: dict[str, Any] = {}
+        self.metrics = Metrics()
+        self.iteration = 0
+        self.step_index = 0
+
+        self.actor_factory, self.critic_factory, self.optimizer_factory = actor_factory, critic_factory, optimizer_factory
+        self.hook = HookComposite(hooks)
+        self.hook.pre_init(self)
+        self.actor = actor_factory(self.observation_dim, self.action_dim)
+        self.critic = critic_factory(self.state_dim, self.value_dim)
+        self.buffer = Buffer(self.buffer_capacity, self.parallelism, device=self.device)
+        self.sampler = sampler
+        self.actor_memory = None
+        self.hook.init()
+        self.actor = self.setup_module(self.actor)
+        self.critic = self.setup_module(self.critic)
+        self.optimizer = self.optimizer_factory(self.named_parameters())
+        self._set_training_mode(False)
+        self.hook.post_init()
+        distributed.broadcast_parameters([self.optimizer.flat_param] if hasattr(self.optimizer, "flat_param")
+                                         else self.parameters())
+        self.hook.apply_schedule(0)
+
+    # ---- parameters / modules --------------------------------------------------------------------
+    def named_parameters(self):
+        for name in self.MODULES:
+            module = getattr(self, name, None)
+            if module is not None:
+                yield from module.named_parameters(prefix=name)
+
+    def parameters(self):
+        for _name, param in self.named_parameters():
+            yield param
+
+    def setup_module(self, module):
+        return module.to(device=self.device)
+
+    def autocast(self):
+        return nullcontext()
+
+    def record(self, metrics: Mapping[str, Any] | None = None, /, **kwargs) -> None:
+        self.metrics.record(metrics, **kwargs)
+
+    def to_tensor(self, value) -> torch.Tensor:
+        tensor = torch.as_tensor(value, device=self.device)
+        return tensor.clone() if tensor is value else tensor
+
+    def to_nested_tensor(self, value):
+        if value is None:
+            return None
+        if isinstance(value, (tuple, list)):
+            return tuple(self.to_nested_tensor(v) for v in value)
+        if isinstance(value, Mapping):
+            return {k: self.to_nested_tensor(v) for k, v in value.items()}
+        return self.to_tensor(value)
+
+    # ---- rollout ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def act(self, observation, state=None):
+        """actor_critic.py:227-253; output array type follows the input (agent.py:376-391)."""
+        self.transition.clear()
+        self._save_transition(observation=observation, state=state)
+        self.hook.pre_act(self.transition)
+        action_dist, (action, action_logp), next_memory = self.actor.explore(
+            self.transition["observation"], memory=self.actor_memory, deterministic=self.deterministic)
+        self._save_transition(actor_memory=self.actor_memory, action_dist=action_dist, action=action,
+                              action_logp=action_logp)
+        self.actor_memory = next_memory
+        self.hook.post_act(self.transition)
+        action = self.transition["action"]
+        if isinstance(observation, np.ndarray):
+            out = action.cpu().numpy()
+            return out.astype(observation.dtype) if np.issubdtype(out.dtype, np.floating) else out
+        return action.to(device=observation.device, dtype=observation.dtype if torch.is_floating_point(action) else None)
+
+    @torch.no_grad()
+    def step(self, next_observation, reward, terminated, truncated, next_state=None, **kwargs) -> bool:
+        """actor_critic.py:255-291."""
+        self._save_transition(next_observation=next_observation, next_state=next_state, reward=reward,
+                              terminated=terminated, truncated=truncated, **kwargs)
+        if self.transition["terminated"].dtype != torch.bool:
+            raise TypeError("'terminated' must have dtype bool")
+        if self.transition["truncated"].dtype != torch.bool:
+            raise TypeError("'truncated' must have dtype bool")
+        self.transition["done"] = self.transition["terminated"] | self.transition["truncated"]
+        self.hook.post_step(self.transition)
+        if not self.inference_mode:
+            self.buffer.push(self.transition)
+        self.actor.reset_memory(self.actor_memory, self.transition["done"])
+        if self.inference_mode:
+            return False
+        self.step_index += 1
+        return self.step_index >= self.num_steps_per_update and self.hook.should_update(self.transition)
+
+    # ---- update ----------------------------------------------------------------------------------
+    def update(self) -> dict[str, float]:
+        """actor_critic.py:293-300."""
+        self.hook.pre_update(self.buffer)
+        with self._training_mode():
+            for metadata, batch in self.sampler(self.buffer):
+                self._train_step(metadata, batch)
+        self.hook.post_update()
+        self.hook.apply_schedule(self.iteration + 1)
+        self.step_index = 0
+        self.iteration += 1
+        summary = self.metrics.summary(self.name)
+        self.metrics.clear()
+        return summary
+
+    def _train_step(self, metadata: dict[str, Any], batch: dict[str, Any]) -> None:
+        """actor_critic.py:302-320 (no GradScaler: fp32 only)."""
+        self.actor.clear_intermediate_repr()
+        self.critic.clear_intermediate_repr()
+        self.hook.pre_objective(metadata, batch)
+        objectives = self.hook.objective(metadata, batch)
+        if objectives is not None:
+            loss = sum(objectives.values())
+            self.optimizer.zero_grad()
+            loss.backward()
+            distributed.reduce_gradients(self.optimizer)
+            self.hook.pre_optim(self.optimizer)
+            self.optimizer.step()
+            self.hook.post_optim()
+            self.record(**objectives)
+        self.hook.post_objective(metadata, batch)
+
+    def set_inference_mode(self, mode: bool = True, deterministic: bool | None = True) -> None:
+        self.inference_mode = mode
+        if deterministic is not None:
+            self.deterministic = mode and deterministic
+
+    def set_iteration(self, iteration: int) -> None:
+        if iteration < 0:
+            raise ValueError("Iteration must be non-negative")
+        if iteration != self.iteration:
+            self.iteration = iteration
+            self.hook.apply_schedule(iteration)
+
+    # ---- checkpointing (agent.py:283-330) ---------------------------------------------------------
+    def state_dict(self) -> dict[str, Any]:
+        out = {}
+        for name in self.MODULES + self.STATEFULS:
+            obj = getattr(self, name, None)
+            if obj is not None:
+                out[name] = obj.state_dict()
+        return out
+
+    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        keys = set(state_dict)
+        for name in self.MODULES + self.STATEFULS:
+            obj = getattr(self, name, None)
+            if obj is None:
+                continue
+            if (state := state_dict.get(name)) is None:
+                self.warn(f"No state_dict entry was found for '{name}'")
+                continue
+            keys.discard(name)
+            try:
+                obj.load_state_dict(state)
+            except (RuntimeError, ValueError) as error:
+                self.warn(f"Mismatched state_dict for '{name}': {error}")
+        if keys:
+            self.warn(f"Unused state_dict keys: {keys}.")
+
+    @classmethod
+    def warn(cls, message: str) -> None:
+        if distributed.is_main_process():
+            print(f"\033[1;33mAgent: {message}\033[0m")
+
+    # ---- internals -------------------------------------------------------------------------------
+    def _save_transition(self, **kwargs) -> None:
+        for key, value in kwargs.items():
+            if value is None:
+                continue
+            try:
+                self.transition[key] = self.to_nested_tensor(value)
+            except Exception as error:
+                raise ValueError(f"Failed to convert transition field '{key}' to a tensor") from error
+
+    def _set_training_mode(self, mode: bool = True) -> None:
+        for name in self.MODULES:
+            module = getattr(self, name, None)
+            if module is not None:
+                module.train(mode)
+
+    @contextmanager
+    def _training_mode(self):
+        self._set_training_mode(True)
+        try:
+            yield
+        finally:
+            self._set_training_mode(False)

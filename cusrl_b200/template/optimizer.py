@@ -1,0 +1,144 @@
+"""Flat parameter / gradient arenas and the fused clip+Adam optimizer (K9).
+
+Replaces the reference's ``OptimizerFactory`` -> ``torch.optim.Adam`` (cusrl/template/optimizer.py:94-251,
+cusrl/preset/optimizer.py:9-23) on the hot path.  All trainable parameters of the agent (actor, critic,
+hook modules) are re-pointed at slices of ONE contiguous fp32 arena; gradients live in a second arena
+of the same layout.  That makes
+
+* the per-minibatch gradient allreduce a single in-place collective (no cat / copy-back), and
+* grad-norm clipping + Adam two streaming kernels over 2.3 MB instead of ~10 foreach launches.
+
+``param_groups`` keeps the keys the reference's hooks read (``params``, ``param_names``, ``lr``) so
+``GradientClipping`` and the KL-adaptive LR schedule work unchanged.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Iterable
+from typing import Any
+
+import torch
+from torch import nn
+
+from .. import ops
+
+__all__ = ["AdamFactory", "FlatAdam", "ParamArena"]
+
+
+class ParamArena:
+    """Re-homes parameters into one flat tensor (16-byte aligned slices) with a matching grad arena."""
+
+    ALIGN = 4  # floats
+
+    def __init__(self, named_parameters: Iterable[tuple[str, nn.Parameter]]):
+        self.names: list[str] = []
+        self.params: list[nn.Parameter] = []
+        self.offsets: list[int] = []
+        total = 0
+        for name, p in named_parameters:
+            if not p.requires_grad:
+                continue
+            if p.dtype != torch.float32:
+                raise TypeError(f"parameter '{name}' must be float32")
+            self.names.append(name)
+            self.params.append(p)
+            self.offsets.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if not self.params:
+            raise ValueError("No trainable parameters matched the optimizer filter")
+        device = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        for p, off in zip(self.params, self.offsets):
+            n = p.numel()
+            self.flat[off : off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off : off + n].view_as(p)
+            p.grad = self.flat_grad[off : off + n].view_as(p)
+        self.numel = total
+
+    def segment(self, name_prefix: str) -> list[tuple[int, int]]:
+        """(offset, count) ranges of every parameter whose name equals or starts with `prefix.`."""
+        out = []
+        for name, p, off in zip(self.names, self.params, self.offsets):
+            if name == name_prefix or name.startswith(name_prefix + "."):
+                out.append((off, p.numel()))
+        return out
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (amsgrad=False) on a :class:`ParamArena`, one kernel per step."""
+
+    def __init__(self, named_parameters, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        self.arena = ParamArena(named_parameters)
+        self.defaults = {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay}
+        self.param_groups: list[dict[str, Any]] = [
+            {"params": list(self.arena.params), "param_names": list(self.arena.names), **self.defaults}
+        ]
+        dev = self.arena.flat.device
+        self.exp_avg = torch.zeros_like(self.arena.flat)
+        self.exp_avg_sq = torch.zeros_like(self.arena.flat)
+        self.step_count = 0
+        # clip state written by GradientClipping.pre_optim, consumed (then cleared) by step()
+        self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.clip_coef = torch.ones(1, dtype=torch.float32, device=dev)
+        self._clip_pending = False
+
+    # the two arenas, exposed for the collective (distributed.reduce_gradients) and for kernels
+    @property
+    def flat_param(self) -> torch.Tensor:
+        return self.arena.flat
+
+    @property
+    def flat_grad(self) -> torch.Tensor:
+        return self.arena.flat_grad
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Gradients are accumulated in place by the wgrad kernels, so zero the arena (one memset)."""
+        self.arena.flat_grad.zero_()
+
+    def compute_grad_norm(self, max_norm: float) -> torch.Tensor:
+        """L2 norm of the whole arena + clip coefficient (torch clip_grad_norm_ arithmetic), no host sync.
+        The scaling itself is folded into the Adam kernel."""
+        self.grad_sumsq.zero_()
+        ops.grad_sumsq_(self.arena.flat_grad, self.grad_sumsq)
+        ops.clip_coef(self.grad_sumsq, max_norm, self.grad_norm, self.clip_coef)
+        self._clip_pending = True
+        return self.grad_norm
+
+    def step(self) -> None:
+        g = self.param_groups[0]
+        self.step_count += 1
+        ops.adam_step_(
+            self.arena.flat, self.arena.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
+            g["betas"], g["eps"], g["weight_decay"], coef=self.clip_coef if self._clip_pending else None)
+        self._clip_pending = False
+
+    def state_dict(self) -> dict[str, Any]:
+        return {
+            "step": self.step_count,
+            "exp_avg": self.exp_avg.clone(),
+            "exp_avg_sq": self.exp_avg_sq.clone(),
+            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+        }
+
+    def load_state_dict(self, state: dict[str, Any]) -> None:
+        self.step_count = int(state["step"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        for g, saved in zip(self.param_groups, state.get("param_groups", [])):
+            g.update({k: v for k, v in saved.items() if k not in ("params", "param_names")})
+
+
+class AdamFactory:
+    """Builds a :class:`FlatAdam` from named parameters (reference preset/optimizer.py:9-23)."""
+
+    def __init__(self, defaults: dict[str, Any] | None = None):
+        self.defaults = dict(defaults or {})
+        unknown = set(self.defaults) - {"lr", "betas", "eps", "weight_decay"}
+        if unknown:
+            raise ValueError(f"unsupported Adam options: {sorted(unknown)}")
+
+    def __call__(self, named_parameters) -> FlatAdam:
+        return FlatAdam(named_parameters, **self.defaults)

@@ -77,7 +77,7 @@ int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, con
                              int64_t Dv, double gamma, double lamda, double lamda_value, void* stream);
 
 /* Tuning knob for K1 (process-wide): columns per thread (1, 2 or 4) and threads per block
- * (multiple of 32, <= 256).  Results are bit-identical for every setting. */
+ * (multiple of 32, <= 128).  Results are bit-identical for every setting. */
 int cusrl_b200_gae_set_config(int vec, int threads);
 
 /* ------------------------------------------------------------------------------------------------

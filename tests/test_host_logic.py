@@ -1,0 +1,174 @@
+"""CPU: host-side mirror of the reference's plugin surface (Buffer, samplers' index generation, hook
+registry / ordering, factories).  Modelled on the reference's own tests: cusrl_test/template/test_buffer.py,
+cusrl_test/sampler/test_mini_batch_sampler.py, cusrl_test/hook/on_policy/test_gae.py:34-46."""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+import cusrl_b200 as C
+from cusrl_b200.template.buffer import padded_width
+
+
+def make_buffer(T=6, N=8):
+    buf = C.Buffer(T, N, device="cpu")
+    for t in range(T):
+        buf.push({
+            "observation": torch.full((N, 3), float(t)),
+            "flag": torch.zeros(N, 1, dtype=torch.bool),
+            "action_dist": {"mean": torch.ones(N, 2) * t, "std": torch.ones(N, 2)},
+            "skipped": None,
+        })
+    return buf
+
+
+def test_buffer_push_wraps_and_preserves_dtype():
+    buf = make_buffer()
+    assert buf.full and buf.cursor == 0
+    assert buf["flag"].dtype == torch.bool
+    assert buf["observation"].shape == (6, 8, 3)
+    assert set(buf.storage) == {"observation", "flag", "action_dist.mean", "action_dist.std"}
+    assert buf["action_dist"]["mean"][4, 0, 0] == 4.0
+    assert "skipped" not in buf
+
+
+def test_buffer_shape_validation_and_schema():
+    buf = C.Buffer(4, 3, device="cpu")
+    with pytest.raises(ValueError, match="Parallelism mismatch"):
+        buf.push({"x": torch.zeros(5, 2)})
+    buf.push({"x": torch.zeros(3, 2)})
+    with pytest.raises(ValueError, match="Schema mismatch"):
+        buf.push({"x": {"a": torch.zeros(3, 2)}})
+    with pytest.raises(ValueError, match="Capacity mismatch"):
+        buf["y"] = torch.zeros(5, 3, 1)
+    buf["y"] = torch.ones(4, 3, 1)
+    assert buf["y"].sum() == 12
+    del buf["y"]
+    assert "y" not in buf and "y" not in buf.storage
+
+
+def test_buffer_pads_wide_rows_to_16_bytes():
+    assert padded_width(235, torch.float32) == 236
+    assert padded_width(12, torch.float32) == 12     # < 64 bytes: left dense
+    assert padded_width(512, torch.float32) == 512
+    buf = C.Buffer(2, 4, device="cpu")
+    buf.push({"observation": torch.randn(4, 235)})
+    assert buf["observation"].shape == (2, 4, 235)
+    assert buf.backing("observation").shape == (2, 4, 236)
+    assert buf["observation"].stride() == (944, 236, 1)
+    assert buf.backing("observation")[..., 235:].abs().sum() == 0
+
+
+def test_sampler_requires_full_buffer():
+    buf = C.Buffer(4, 2, device="cpu")
+    buf.push({"x": torch.zeros(2, 1)})
+    with pytest.raises(RuntimeError, match="requires a full buffer"):
+        next(iter(C.MiniBatchSampler().indices(buf)))
+
+
+def test_sampler_argument_validation():
+    with pytest.raises(ValueError):
+        C.MiniBatchSampler(num_epochs=0)
+    with pytest.raises(ValueError):
+        C.MiniBatchSampler(num_mini_batches=0)
+    with pytest.raises(ValueError):
+        C.MiniBatchSampler(num_epochs=2, num_mini_batches=[1, 2, 3])
+
+
+def test_sampler_permutations_bit_exact_with_reference(golden):
+    """Same seed, same device -> the same randperm call pattern gives the reference's exact index slices."""
+    g = golden("sampler")
+    buf = make_buffer(6, 8)
+    torch.manual_seed(1234)
+    ref = g.t("flat_indices")
+    # slices are views of one index tensor that later epochs overwrite in place (as in the reference): compare on the fly
+    for row, (meta, idx) in enumerate(C.MiniBatchSampler(num_epochs=3, num_mini_batches=4).indices(buf)):
+        assert torch.equal(idx, ref[row])
+        assert [meta["epoch_index"], meta["mini_batch_index"], meta["total_epochs"], meta["total_mini_batches"],
+                int(meta["temporal"])] == g.np("flat_meta")[row].tolist()
+    torch.manual_seed(1234)
+    assert row == ref.shape[0] - 1
+    for row, (meta, idx) in enumerate(C.TemporalMiniBatchSampler(num_epochs=3, num_mini_batches=2).indices(buf)):
+        assert torch.equal(idx, g.t("temporal_indices")[row])
+        assert meta["temporal"] is True
+
+
+def test_sampler_coverage_and_remainder():
+    buf = make_buffer(5, 7)  # 35 samples, 4 minibatches -> size 8, 3 dropped (mini_batch_sampler.py:66)
+    for meta, idx in C.MiniBatchSampler(num_epochs=1, num_mini_batches=4).indices(buf):
+        assert idx.numel() == 8
+    seen = torch.cat([idx.clone() for _, idx in C.MiniBatchSampler(num_epochs=1, num_mini_batches=5).indices(buf)])
+    assert sorted(seen.tolist()) == list(range(35))
+
+
+def test_auto_sampler_picks_temporal_on_memory_fields():
+    buf = make_buffer()
+    assert not next(iter(C.AutoMiniBatchSampler().indices(buf)))[0]["temporal"]
+    buf2 = C.Buffer(2, 4, device="cpu")
+    for _ in range(2):
+        buf2.push({"observation": torch.zeros(4, 3), "actor_memory": {"hidden": torch.zeros(4, 5)}})
+    assert next(iter(C.AutoMiniBatchSampler().indices(buf2)))[0]["temporal"]
+
+
+def test_hook_names_and_validation():
+    assert C.GeneralizedAdvantageEstimation().name == "generalized_advantage_estimation"
+    assert C.PpoSurrogateLoss().name == "ppo_surrogate_loss"
+    for kwargs in ({"gamma": -0.1}, {"gamma": 1.0}, {"lamda": -0.1}, {"lamda": 1.1}, {"lamda_value": 1.1}):
+        with pytest.raises(ValueError):
+            C.GeneralizedAdvantageEstimation(**kwargs)
+    with pytest.raises(ValueError):
+        C.PpoSurrogateLoss(clip_ratio=0.0)
+    with pytest.raises(ValueError):
+        C.ValueLoss(weight=0.0)
+    with pytest.raises(ValueError):
+        C.EntropyLoss(weight=-1.0)
+    hook = C.GeneralizedAdvantageEstimation()
+    hook.update_attribute("gamma", 0.9)
+    assert hook.gamma == 0.9
+    with pytest.raises(ValueError, match="not mutable"):
+        hook.update_attribute("recompute", True)
+
+
+def test_factory_hook_order_and_registration():
+    factory = C.anymal_c_rough_ppo(device="cpu").to_underlying()
+    names = [h.name for h in factory.hooks]
+    assert names == ["module_initialization", "value_computation", "generalized_advantage_estimation",
+                     "advantage_normalization", "value_loss", "on_policy_preparation", "ppo_surrogate_loss",
+                     "entropy_loss", "gradient_clipping", "on_policy_statistics", "adaptive_lr_schedule"]
+
+    class Probe(C.Hook):
+        pass
+
+    factory.register_hook(Probe(), before="value_computation")
+    assert factory.hooks[1].name == "probe" and factory.hooks.probe is factory.hooks[1]
+    with pytest.raises(ValueError):
+        factory.register_hook(Probe().name_("p2"), before="a", after="b")
+    with pytest.raises(ValueError, match="No hook named"):
+        factory.get_hook("missing")
+
+
+def test_agent_construction_parameter_names_and_arena():
+    spec = C.EnvironmentSpec(8, 235, 12, autoreset=True, final_state_is_missing=True)
+    agent = C.anymal_c_rough_ppo(device="cpu")(spec)
+    names = [n for n, _ in agent.named_parameters()]
+    assert "actor.backbone.layers.4.weight" in names and "actor.distribution.std.param" in names
+    assert "critic.value_head.bias" in names
+    assert sum(p.numel() for p in agent.parameters()) == 571801  # reference count
+    flat = agent.optimizer.flat_param
+    p = dict(agent.named_parameters())["critic.value_head.weight"]
+    assert p.data_ptr() >= flat.data_ptr() and p.grad is not None and p.grad.shape == p.shape
+    # value_computation disabled bootstrapping because the env omits final states (value.py:38-40)
+    assert agent.hook["value_computation"].bootstrap_truncated_states is False
+    with pytest.raises(ValueError, match="compile"):
+        C.anymal_c_rough_ppo(device="cpu", compile=True)(spec)
+    with pytest.raises(ValueError, match="autocast"):
+        C.anymal_c_rough_ppo(device="cpu", autocast=True)(spec)
+
+
+def test_adaptive_lr_schedule_host_logic():
+    hook = C.AdaptiveLRSchedule(0.015)
+    # accumulated log error crosses +1 after a few large-KL iterations -> LR shrinks by exp(-clip(avg)*0.2)
+    scales = [hook._compute_scale(0.03) for _ in range(2)]
+    assert scales[0] is None and scales[1] == pytest.approx(torch.exp(torch.tensor(-0.2 * 0.6931471805599453)).item())
+    assert hook._accumulated_log_error == 0.0 and hook._count == 0

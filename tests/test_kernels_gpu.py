@@ -74,7 +74,7 @@ def test_gae_vs_oracle_bit_exact(ops, T, N, Dv, lamda_value):
     assert torch.equal(ret.cpu(), ref_ret)
 
 
-@pytest.mark.parametrize("vec,threads", [(1, 128), (2, 64), (4, 128), (4, 256)])
+@pytest.mark.parametrize("vec,threads", [(1, 128), (2, 64), (4, 128), (1, 32)])
 def test_gae_all_vector_widths(ops, vec, threads):
     from cusrl_b200 import _lib
 
@@ -89,7 +89,7 @@ def test_gae_all_vector_widths(ops, vec, threads):
         adv, ret = ops.gae(reward.to(DEV), done.to(DEV), value.to(DEV), nv.to(DEV), 0.99, 0.95)
         assert torch.equal(adv.cpu(), ref_adv) and torch.equal(ret.cpu(), ref_ret)
     finally:
-        lib.cusrl_b200_gae_set_config(2, 128)
+        lib.cusrl_b200_gae_set_config(1, 128)
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
@@ -306,7 +306,7 @@ def test_clip_and_adam_vs_torch(ops, n):
         ops.grad_sumsq_(gd, sumsq)
         ops.clip_coef(sumsq, 1.0, norm, coef)
         ops.adam_step_(p, gd, m, v, step, 1e-3, coef=coef)
-        rel_close(norm, ref_norm.reshape(1), rtol=1e-6)
+        rel_close(norm, ref_norm.reshape(1), rtol=1e-5)  # torch's fp32 norm vs our fp64 accumulation
         rel_close(p, ref_p.detach(), rtol=1e-5, atol=1e-7)
     # oracle restatement agrees with torch too
     po, mo, vo = O.adam_step_ref(p0, O.clip_grad_norm_ref([grads[0]], 1.0)[1][0], torch.zeros(n), torch.zeros(n), 1, 1e-3)

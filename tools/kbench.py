@@ -29,23 +29,36 @@ def hbm_peak() -> tuple[float, str]:
 
 
 class Timer:
-    def __init__(self, reps: int, flush_mb: int = 384):
-        self.reps = reps
-        self.flush = torch.empty(flush_mb * 1024 * 1024 // 4, device="cuda")
+    """Times `fns` (a list of equivalent launches on DIFFERENT buffer sets whose total footprint exceeds
+    the 126 MB L2, so every launch streams from HBM) as one CUDA graph: no host launch overhead inside
+    the timed region.  Returns (mean, best) seconds per launch."""
 
-    def __call__(self, fn, warmup: int = 3) -> tuple[float, float]:
+    def __init__(self, reps: int):
+        self.reps = reps
+
+    def __call__(self, fns, warmup: int = 3) -> tuple[float, float]:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for f in fns:
+                f()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for f in fns:
+                f()
         for _ in range(warmup):
-            fn()
+            graph.replay()
+        torch.cuda.synchronize()
         times = []
         for _ in range(self.reps):
-            self.flush.add_(1.0)  # evict L2 (126 MB) so the timed launch reads HBM
-            torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            fn()
+            graph.replay()
             b.record()
             torch.cuda.synchronize()
-            times.append(a.elapsed_time(b) * 1e-3)
+            times.append(a.elapsed_time(b) * 1e-3 / len(fns))
         return sum(times) / len(times), min(times)
 
 
@@ -62,9 +75,10 @@ def main():
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--sets", type=int, default=8, help="rotating buffer sets (total footprint must exceed L2)")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
-    T, N = args.steps, args.envs
+    T, N, S = args.steps, args.envs, args.sets
     E = T * N
     B = E // 4
     peak, which = hbm_peak()
@@ -73,36 +87,50 @@ def main():
     lib = _lib.load()
     want = lambda k: not args.only or args.only in k  # noqa: E731
 
-    reward, value, nv = (torch.randn(T, N, 1, device=dev) for _ in range(3))
-    term = torch.rand(T, N, 1, device=dev) < 0.01
-    trunc = torch.rand(T, N, 1, device=dev) < 0.001
-    done = term | trunc
-    boot = torch.randn(N, 1, device=dev)
-    adv, ret = torch.empty_like(value), torch.empty_like(value)
+    sets = []
+    for _ in range(S):
+        d = {k: torch.randn(T, N, 1, device=dev) for k in ("reward", "value", "nv", "adv", "ret")}
+        d["term"] = torch.rand(T, N, 1, device=dev) < 0.01
+        d["trunc"] = torch.rand(T, N, 1, device=dev) < 0.001
+        d["done"] = d["term"] | d["trunc"]
+        d["boot"] = torch.randn(N, 1, device=dev)
+        d["mv"] = torch.empty(2, device=dev)
+        sets.append(d)
 
     if want("gae"):
-        for vec, threads in ((1, 128), (1, 256), (2, 64), (2, 128), (2, 256), (4, 64), (4, 128)):
+        for vec, threads in ((1, 64), (1, 128), (2, 64), (2, 128), (4, 64), (4, 128)):
             lib.cusrl_b200_gae_set_config(vec, threads)
-            m, b = timer(lambda: ops.gae(reward, done, value, nv, 0.99, 0.95, advantage=adv, ret=ret))
+            m, b = timer([lambda d=d: ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95,
+                                              advantage=d["adv"], ret=d["ret"]) for d in sets])
             report("gae", 21 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
-            m, b = timer(lambda: ops.gae_fused(reward, term, trunc, value, boot, 0.99, 0.95, advantage=adv, ret=ret))
-            report("gae_fused(19B/elt)", 19 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
-        lib.cusrl_b200_gae_set_config(2, 128)
+            m, b = timer([lambda d=d: ops.gae_fused(d["reward"], d["term"], d["trunc"], d["value"], d["boot"], 0.99, 0.95,
+                                                    advantage=d["adv"], ret=d["ret"]) for d in sets])
+            report("gae_fused(18B/elt)", 18 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
+        lib.cusrl_b200_gae_set_config(1, 128)
     if want("next_value"):
-        m, b = timer(lambda: ops.next_value(value, term, trunc, boot, out=nv))
+        m, b = timer([lambda d=d: ops.next_value(d["value"], d["term"], d["trunc"], d["boot"], out=d["nv"]) for d in sets])
         report("next_value", 10 * E, m, b, peak, which)
     if want("advnorm"):
-        mv = torch.empty(2, device=dev)
-        m, b = timer(lambda: ops.advantage_stats(adv, out=mv))
-        report("advantage_stats", 4 * E, m, b, peak, which)
-        m, b = timer(lambda: ops.advantage_normalize_(adv, mv))
+        m, b = timer([lambda d=d: ops.advantage_stats(d["adv"], out=d["mv"]) for d in sets] * 4)
+        report("advantage_stats(2 launches)", 4 * E, m, b, peak, which)
+        m, b = timer([lambda d=d: ops.advantage_normalize_(d["adv"], d["mv"]) for d in sets] * 4)
         report("advantage_normalize", 8 * E, m, b, peak, which)
+    del sets
     if want("loss"):
-        mean, action = torch.randn(B, 12, device=dev), torch.randn(B, 12, device=dev)
+        ls = []
+        for _ in range(4):
+            d = {"mean": torch.randn(B, 12, device=dev), "action": torch.randn(B, 12, device=dev)}
+            for k in ("lp", "a", "r", "vo", "v"):
+                d[k] = torch.randn(B, 1, device=dev)
+            ls.append(d)
         std = torch.ones(12, device=dev)
-        lp, a, r, vo, v = (torch.randn(B, 1, device=dev) for _ in range(5))
-        m, b = timer(lambda: ops.ppo_loss(mean, std, action, lp, a, r, vo, v, 0.2, 1.0, 0.005, 0.5))
-        report("ppo_loss(fwd+grads+per-sample)", (112 + 52 + 16) * B, m, b, peak, which, B=B)
+        outs = [ops.ppo_loss(d["mean"], std, d["action"], d["lp"], d["a"], d["r"], d["vo"], d["v"], 0.2, 1.0, 0.005, 0.5)
+                for d in ls]
+        del outs
+        m, b = timer([lambda d=d: ops.ppo_loss(d["mean"], std, d["action"], d["lp"], d["a"], d["r"], d["vo"], d["v"],
+                                               0.2, 1.0, 0.005, 0.5) for d in ls])
+        report("ppo_loss(fwd+grads+per-sample, 2 launches)", (112 + 52 + 16) * B, m, b, peak, which, B=B)
+        del ls
     if want("gather"):
         obs = torch.randn(E, 240, device=dev)
         action = torch.randn(E, 12, device=dev)
@@ -111,7 +139,7 @@ def main():
         d_obs, d_act = torch.empty(B, 240, device=dev), torch.empty(B, 12, device=dev)
         d_sc = [torch.empty(B, 1, device=dev) for _ in range(4)]
         fields = [(obs, d_obs), (action, d_act)] + list(zip(sc, d_sc))
-        m, b = timer(lambda: ops.gather_rows(fields, idx))
+        m, b = timer([lambda: ops.gather_rows(fields, idx)] * 2)
         report("gather(obs240+act12+4 scalars)", 2 * (960 + 48 + 16) * B + 8 * B, m, b, peak, which, B=B)
     if want("adam"):
         n = 571801
@@ -126,8 +154,8 @@ def main():
             ops.clip_coef(sumsq, 1.0, norm, coef)
             ops.adam_step_(p, g, m1, v1, 1, 1e-3, coef=coef)
 
-        m, b = timer(step)
-        report("clip+adam(4 launches)", 32 * n, m, b, peak, which, n=n)
+        m, b = timer([step] * 8)
+        report("clip+adam(memset + 3 launches, L2-resident)", 32 * n, m, b, peak, which, n=n)
 
 
 if __name__ == "__main__":
