@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="global number of environments")
     ap.add_argument("--rollout", type=int, default=24)
-    ap.add_argument("--cpu-envs", type=int, default=2048, help="environments of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-envs", type=int, default=1024, help="environments of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -300,9 +300,9 @@ def main():
         roof = gae_roofline(T, N, peaks, which)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=2, warmup=1, threads=host_threads)
+            rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=1, warmup=1, threads=host_threads)
             cpu = {"value": round(rate, 1), "unit": "env-steps/s", "cores": host_threads, "kind": "port",
-                   "sample": f"{args.cpu_envs} envs x {T} steps, 1 warm-up + 2 timed iterations ({dt:.2f} s each)"}
+                   "sample": f"{args.cpu_envs} envs x {T} steps, 1 warm-up + 1 timed iteration ({dt:.2f} s)"}
         line = {
             "metric": "ppo_env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3),

@@ -1,0 +1,415 @@
+// K6: dense layers of the MLP actor / critic on the 5th-generation tensor cores.
+//
+//   D[M,N] = epilogue( A[M,K] @ B[N,K]^T ),  A and B both K-major (row-major with K contiguous), fp32 in HBM.
+//
+// * forward   : A = X,  B = W        epilogue  y = act(d + bias)                      (nn.Linear + ELU/ReLU)
+// * data grad : A = dZ, B = W^T copy epilogue  dx = d * act'(y_prev)                  (autograd of the layer below)
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled tiles -> shared memory ring, mbarrier tx
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       : tcgen05.ld -> registers -> bias/activation -> 128-bit global stores
+//   warps 8-11  splitter (3xTF32 only): rewrites the A tile in place as hi = A & ~0x1fff and writes lo = A - hi
+// Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Precision.  The reference computes these layers with fp32 SGEMM.  PASSES = 3 is the error-compensated
+// "3xTF32" scheme: x = hi + lo with hi, lo both TF32-representable, D = Ahi*Bhi + Ahi*Blo + Alo*Bhi (fp32
+// accumulate), which restores ~fp32 accuracy at one third of the TF32 tensor rate.  hi parts are masked
+// explicitly so the result does not depend on whether the tensor core truncates or rounds its inputs.
+// PASSES = 1 is plain single-pass TF32.
+#include "tc_common.cuh"
+
+namespace cusrl_b200 {
+
+using namespace tc;
+
+constexpr int BM = 128;           // rows per CTA tile (UMMA M)
+constexpr int BK = 32;            // fp32 per k-block = 128 bytes = one SWIZZLE_128B span
+constexpr int UMMA_K = 8;         // tf32 elements per tcgen05.mma
+constexpr int kGemmThreads = 384;
+constexpr int kSmemBudget = 220 * 1024;
+
+enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1 };
+
+struct GemmParams {
+  float* out;
+  int64_t ldo;
+  const float* bias;   // EPI_BIAS_ACT (may be null)
+  const float* aux;    // EPI_ACT_GRAD: post-activation output of the layer below (may be null: plain copy)
+  int64_t ldaux;
+  int M, N, K, act;
+  int num_m_tiles, num_n_tiles;
+};
+
+template <int BN, int PASSES>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 6 ? 6 : (kSmemBudget / STAGE_BYTES);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static_assert(STAGES >= 2, "tile does not fit in shared memory");
+};
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return z > 0.f ? z : expm1f(z);  // ELU(alpha=1), same as torch.nn.functional.elu
+  if (act == 2) return fmaxf(z, 0.f);
+  return z;
+}
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  if (act == 1) return y > 0.f ? 1.f : y + 1.f;  // d/dz ELU(z) = exp(z) = y + 1 for z <= 0
+  if (act == 2) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+  using Cfg = GemmCfg<BN, PASSES>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto sAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto sB = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * (PASSES == 3 ? 2 : 1); };
+  auto sBlo = [&](int s) { return sB(s) + Cfg::B_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                  // TMA bytes landed
+  uint64_t* split = bars + STAGES;        // A tile split into hi/lo (3xTF32)
+  uint64_t* empty = bars + 2 * STAGES;    // MMAs reading the stage retired
+  uint64_t* tfull = bars + 3 * STAGES;    // accumulator complete
+  uint64_t* tempty = tfull + 2;           // accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES * (PASSES == 3 ? 2 : 1));
+          tma_load_2d(sA(s), &tmA, kb * BK, m0, &full[s]);
+          tma_load_2d(sB(s), &tmB, kb * BK, n0, &full[s]);
+          if (PASSES == 3) tma_load_2d(sBlo(s), &tmBlo, kb * BK, n0, &full[s]);
+          if (++s == STAGES) s = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int a = local & 1;
+        const uint32_t aph = (local >> 1) & 1;
+        mbar_wait(&tempty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          if (PASSES == 3) mbar_wait(&split[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
+          const uint32_t alo_addr = smem_u32(sAlo(s)), blo_addr = smem_u32(sBlo(s));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major SWIZZLE_128B operands: 8-row groups are 1024 B apart (SBO); advancing K by 8 tf32 = +32 B
+            const uint32_t off = (uint32_t)k * UMMA_K * 4;
+            const uint64_t da = make_smem_desc_sw128(a_addr + off, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + off, 16, 1024);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            if (PASSES == 3) {
+              const uint64_t dalo = make_smem_desc_sw128(alo_addr + off, 16, 1024);
+              const uint64_t dblo = make_smem_desc_sw128(blo_addr + off, 16, 1024);
+              mma_tf32_ss(d_tmem, dalo, db, idesc, acc);   // small terms first
+              mma_tf32_ss(d_tmem, da, dblo, idesc, 1u);
+              mma_tf32_ss(d_tmem, da, db, idesc, 1u);
+            } else {
+              mma_tf32_ss(d_tmem, da, db, idesc, acc);
+            }
+          }
+          mma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+          if (++s == STAGES) s = 0, ph ^= 1;
+        }
+        mma_commit(&tfull[a]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================== epilogue ==========================================
+    const int ew = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int a = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      const int row = m0 + ew * 32 + lane;
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (row < p.M && col0 < p.N) {
+          float* orow = p.out + (int64_t)row * p.ldo + col0;
+          const float* arow = (EPI == EPI_ACT_GRAD && p.aux) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {  // N is a multiple of 4 (checked on the host)
+              float v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(r[j + q]);
+              if (EPI == EPI_BIAS_ACT) {
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = act_fwd(v[q], p.act);
+              } else if (arow) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(arow + j));
+                v[0] *= act_grad_from_output(y.x, p.act);
+                v[1] *= act_grad_from_output(y.y, p.act);
+                v[2] *= act_grad_from_output(y.z, p.act);
+                v[3] *= act_grad_from_output(y.w, p.act);
+              }
+              *reinterpret_cast<float4*>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+    }
+  } else if (PASSES == 3 && warp >= 8) {
+    // ===================================== splitter (3xTF32) =================================
+    const int t = threadIdx.x - 256;  // 0..127
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full[s], ph);
+        uint4* hi = reinterpret_cast<uint4*>(sA(s));
+        float4* lo = reinterpret_cast<float4*>(sAlo(s));
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+          const int idx = t + i * 128;  // elementwise at identical offsets: the swizzled layout is preserved
+          uint4 x = hi[idx];
+          uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
+          float4 l = make_float4(__uint_as_float(x.x) - __uint_as_float(h.x), __uint_as_float(x.y) - __uint_as_float(h.y),
+                                 __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[s]);
+        if (++s == STAGES) s = 0, ph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight operand preparation: hi / lo split (and transposed copies for the data-gradient GEMM) of a small
+// weight matrix, run once per optimizer step.
+// ------------------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ w, int N, int K, float* __restrict__ hi, float* __restrict__ lo,
+                                   int ld, float* __restrict__ hi_t, float* __restrict__ lo_t, int ldt) {
+  const int total = N * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    const float x = w[i];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const float l = x - h;
+    hi[(int64_t)n * ld + k] = h;
+    lo[(int64_t)n * ld + k] = l;
+    if (hi_t) {
+      hi_t[(int64_t)k * ldt + n] = h;
+      lo_t[(int64_t)k * ldt + n] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                       uint32_t box_inner, uint32_t box_outer, bool swizzle_32b_atom) {
+  EncodeTiledFn enc = get_encoder();
+  CUSRL_REQUIRE(enc != nullptr, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUSRL_REQUIRE(r == CUDA_SUCCESS, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace tc
+
+template <int BN, int PASSES, int EPI>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo, const GemmParams& p,
+                       cudaStream_t s) {
+  using Cfg = GemmCfg<BN, PASSES>;
+  auto kern = gemm_tf32_kernel<BN, PASSES, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, p);
+  return check_launch("gemm_tf32_kernel");
+}
+
+// Shared implementation of forward (EPI_BIAS_ACT) and data-gradient (EPI_ACT_GRAD) calls.
+static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* out, int64_t ldo,
+                       const float* bias, const float* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int act,
+                       int precision, int epi, void* stream) {
+  CUSRL_REQUIRE(A && Bhi && out, CUSRL_B200_EINVAL, "linear: null pointer");
+  CUSRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N <= 65536 && K <= 65536, CUSRL_B200_EINVAL,
+                "linear: bad problem size");
+  CUSRL_REQUIRE(precision == 1 || (precision == 3 && Blo), CUSRL_B200_EINVAL, "linear: precision must be 1 or 3 (3 needs W_lo)");
+  CUSRL_REQUIRE(act >= 0 && act <= 2, CUSRL_B200_EINVAL, "linear: unknown activation code %d", act);
+  CUSRL_REQUIRE((lda % 4) == 0 && (ldb % 4) == 0 && (ldo % 4) == 0 && (N % 4) == 0 && (!aux || (ldaux % 4) == 0),
+                CUSRL_B200_EALIGN, "linear: leading dimensions and N must be multiples of 4 floats");
+  CUSRL_REQUIRE(lda >= K && ldb >= K && ldo >= N, CUSRL_B200_EINVAL, "linear: leading dimension smaller than the row");
+  CUSRL_REQUIRE(aligned_to(A, 16) && aligned_to(Bhi, 16) && aligned_to(out, 16) && (!Blo || aligned_to(Blo, 16)) &&
+                    (!bias || aligned_to(bias, 16)) && (!aux || aligned_to(aux, 16)),
+                CUSRL_B200_EALIGN, "linear: pointers must be 16-byte aligned");
+  const int bn = N > 128 ? 256 : 128;
+  CUtensorMap tA, tB, tBlo;
+  if (int e = encode_tmap_2d_f32(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return e;
+  if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn)) return e;
+  if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn)) return e;
+  GemmParams p{};
+  p.out = out, p.ldo = ldo, p.bias = bias, p.aux = aux, p.ldaux = ldaux;
+  p.M = (int)M, p.N = (int)N, p.K = (int)K, p.act = act;
+  p.num_m_tiles = (int)((M + BM - 1) / BM);
+  p.num_n_tiles = (int)((N + bn - 1) / bn);
+  cudaStream_t s = (cudaStream_t)stream;
+#define CUSRL_GEMM_CASE(BN_, P_, E_) \
+  if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, p, s);
+  CUSRL_GEMM_CASE(256, 3, EPI_BIAS_ACT)
+  CUSRL_GEMM_CASE(128, 3, EPI_BIAS_ACT)
+  CUSRL_GEMM_CASE(256, 1, EPI_BIAS_ACT)
+  CUSRL_GEMM_CASE(128, 1, EPI_BIAS_ACT)
+  CUSRL_GEMM_CASE(256, 3, EPI_ACT_GRAD)
+  CUSRL_GEMM_CASE(128, 3, EPI_ACT_GRAD)
+  CUSRL_GEMM_CASE(256, 1, EPI_ACT_GRAD)
+  CUSRL_GEMM_CASE(128, 1, EPI_ACT_GRAD)
+#undef CUSRL_GEMM_CASE
+  set_last_error("linear: no kernel for this configuration");
+  return CUSRL_B200_EUNSUPPORTED;
+}
+
+}  // namespace cusrl_b200
+
+using namespace cusrl_b200;
+
+extern "C" {
+
+int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld, float* hi_t,
+                               float* lo_t, int64_t ldt, void* stream) {
+  CUSRL_REQUIRE(W && hi && lo, CUSRL_B200_EINVAL, "weight_prep: null pointer");
+  CUSRL_REQUIRE(N > 0 && K > 0 && ld >= K && N * K < (1ll << 31), CUSRL_B200_EINVAL, "weight_prep: bad sizes");
+  CUSRL_REQUIRE((hi_t == nullptr) == (lo_t == nullptr) && (!hi_t || ldt >= N), CUSRL_B200_EINVAL,
+                "weight_prep: transposed outputs must be given together with ldt >= N");
+  const int total = (int)(N * K);
+  int blocks = (total + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  weight_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, (int)N, (int)K, hi, lo, (int)ld, hi_t, lo_t, (int)ldt);
+  return check_launch("weight_prep_kernel");
+}
+
+int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, const float* W_lo, int64_t ldw,
+                               const float* bias, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act,
+                               int precision, void* stream) {
+  return gemm_kmajor(X, ldx, W_hi, W_lo, ldw, Y, ldy, bias, nullptr, 0, M, N, K, act, precision, EPI_BIAS_ACT, stream);
+}
+
+int cusrl_b200_linear_dgrad_tf32(const float* dY, int64_t lddy, const float* WT_hi, const float* WT_lo, int64_t ldwt,
+                                 const float* Xact, int64_t ldxa, float* dX, int64_t lddx, int64_t M, int64_t N, int64_t K,
+                                 int act, int precision, void* stream) {
+  // dX[M,K] = dY[M,N] @ W[N,K]: as a K-major GEMM the reduction runs over N and B is the transposed copy WT[K,N]
+  return gemm_kmajor(dY, lddy, WT_hi, WT_lo, ldwt, dX, lddx, nullptr, Xact, ldxa, M, /*N=*/K, /*K=*/N, act, precision,
+                     EPI_ACT_GRAD, stream);
+}
+
+}  // extern "C"

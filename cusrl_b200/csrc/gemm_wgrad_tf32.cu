@@ -1,0 +1,343 @@
+// K6 (weight gradient): dW[N,K] = dZ[M,N]^T @ X[M,K] on tcgen05, reduction over the huge batch dimension M.
+//
+// Both operands are "MN-major" for the tensor core: the reduction index (batch row) is the slow dimension of the
+// row-major activations, so each k-block of 32 batch rows is staged as 32-feature chunks of [32 rows][128 B]
+// (TMA box {32 features, 32 rows}, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) and described with UMMA MN-major descriptors of
+// layout type SWIZZLE_128B_BASE32B -- the only shared-memory layout the tensor core accepts for MN-major tf32
+// operands: 32-byte chunks XOR-ed with (row % 4), atoms of 4 rows x 128 B (LBO = chunk stride, SBO = 4-row group stride).
+//
+// Split-K over CTAs: every CTA owns one 128 x BN output tile and a contiguous slab of batch rows, keeps its fp32
+// accumulator in TMEM for the whole slab and finally writes a partial tile to a workspace; a second kernel adds
+// the partials in a fixed order (deterministic) into the gradient arena.  3xTF32 splits BOTH operands in shared
+// memory (they are activations / gradients, there is nothing to pre-split).
+#include "tc_common.cuh"
+
+namespace cusrl_b200 {
+
+using namespace tc;
+
+constexpr int WG_BM = 128;        // output features per tile (UMMA M)
+constexpr int WG_BKB = 32;        // batch rows per k-block
+constexpr int WG_CHUNK = 32;      // features per 128-byte swizzle span
+constexpr int WG_THREADS = 512;
+
+struct WgradParams {
+  float* partial;        // [splits][num_m_tiles*128][ldp]
+  int64_t ldp;           // padded K (multiple of 4)
+  int M, N, K;           // batch rows, output features, input features
+  int num_m_tiles, num_n_tiles, splits;
+  int rows_per_split;    // multiple of WG_BKB
+};
+
+template <int BN, int PASSES>
+struct WgradCfg {
+  static constexpr int A_BYTES = WG_BM * WG_BKB * 4;   // 16 KB: 4 chunks x [32 rows][128 B]
+  static constexpr int B_BYTES = BN * WG_BKB * 4;      // BN/32 chunks
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) > 6 ? 6 : (220 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static_assert(STAGES >= 2, "tile does not fit in shared memory");
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using Cfg = WgradCfg<BN, PASSES>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CHUNK_BYTES = WG_BKB * 128;  // 4096
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // stage layout: [A hi | B hi | A lo | B lo]  (hi parts are the raw TMA destinations, masked in place for 3x)
+  auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto sB = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto sLo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* split = bars + STAGES;
+  uint64_t* empty = bars + 2 * STAGES;
+  uint64_t* tfull = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % (p.num_m_tiles * p.num_n_tiles);
+  const int sp = blockIdx.x / (p.num_m_tiles * p.num_n_tiles);
+  const int f0 = (tile / p.num_n_tiles) * WG_BM;   // first output feature (row of dW)
+  const int k0 = (tile % p.num_n_tiles) * BN;      // first input feature (column of dW)
+  const int row_begin = sp * p.rows_per_split;
+  int row_end = row_begin + p.rows_per_split;
+  if (row_end > p.M) row_end = p.M;
+  const int num_kb = row_end > row_begin ? (row_end - row_begin + WG_BKB - 1) / WG_BKB : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDZ);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 8);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN <= 128 ? 128 : 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int r0 = row_begin + kb * WG_BKB;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        // rows beyond M (or beyond this split's slab end, when the slab is not a multiple of 32 -- it always is,
+        // except for the global tail) are zero-filled by TMA and contribute nothing
+#pragma unroll
+        for (int c = 0; c < WG_BM / WG_CHUNK; ++c) tma_load_2d(sA(s) + c * CHUNK_BYTES, &tmDZ, f0 + c * WG_CHUNK, r0, &full[s]);
+#pragma unroll
+        for (int c = 0; c < BN / WG_CHUNK; ++c) tma_load_2d(sB(s) + c * CHUNK_BYTES, &tmX, k0 + c * WG_CHUNK, r0, &full[s]);
+        if (++s == STAGES) s = 0, ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(WG_BM, BN, /*a MN-major*/ 1, /*b MN-major*/ 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        if (PASSES == 3) mbar_wait(&split[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
+        const uint32_t alo_addr = smem_u32(sLo(s)), blo_addr = alo_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_BKB / 8; ++k) {
+          // one MMA consumes 8 batch rows = two 4-row swizzle atoms (2 x 512 B) of every 32-feature chunk
+          const uint32_t off = (uint32_t)k * 1024;
+          const uint64_t da = make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1);
+          const uint64_t db = make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1);
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          if (PASSES == 3) {
+            const uint64_t dalo = make_smem_desc_sw128(alo_addr + off, CHUNK_BYTES, 512, 1);
+            const uint64_t dblo = make_smem_desc_sw128(blo_addr + off, CHUNK_BYTES, 512, 1);
+            mma_tf32_ss(tmem_base, dalo, db, idesc, acc);
+            mma_tf32_ss(tmem_base, da, dblo, idesc, 1u);
+            mma_tf32_ss(tmem_base, da, db, idesc, 1u);
+          } else {
+            mma_tf32_ss(tmem_base, da, db, idesc, acc);
+          }
+        }
+        mma_commit(&empty[s]);
+        if (++s == STAGES) s = 0, ph ^= 1;
+      }
+      mma_commit(tfull);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // epilogue: one partial tile per CTA
+    const int ew = warp - 4;
+    const int frow = f0 + ew * 32 + lane;  // output feature handled by this thread
+    float* prow = p.partial + ((int64_t)sp * p.num_m_tiles * WG_BM + frow) * p.ldp + k0;
+    if (num_kb > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (k0 + c0 + j < p.ldp)
+          *reinterpret_cast<uint4*>(prow + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    tc_fence_before();
+  } else if (PASSES == 3 && warp >= 8) {
+    // splitter: both operand tiles, hi masked in place, lo written to the mirror buffer at identical offsets
+    const int t = threadIdx.x - 256;  // 0..255
+    constexpr int VECS = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full[s], ph);
+      uint4* hi = reinterpret_cast<uint4*>(sA(s));
+      float4* lo = reinterpret_cast<float4*>(sLo(s));
+#pragma unroll 4
+      for (int idx = t; idx < VECS; idx += 256) {
+        const uint4 x = hi[idx];
+        const uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
+        hi[idx] = h;
+        lo[idx] = make_float4(__uint_as_float(x.x) - __uint_as_float(h.x), __uint_as_float(x.y) - __uint_as_float(h.y),
+                              __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+      if (++s == STAGES) s = 0, ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN <= 128 ? 128 : 256);
+  }
+}
+
+// dW[n,k] (+)= sum_s partial[s][n][k]  in a fixed order; accumulate != 0 adds to the existing gradient.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t split_stride, int64_t ldp,
+                                    float* __restrict__ dW, int64_t lddw, int N, int K, int accumulate) {
+  const int total = N * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    const float* src = partial + (int64_t)n * ldp + k;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[(int64_t)s * split_stride];
+    float* dst = dW + (int64_t)n * lddw + k;
+    *dst = accumulate ? *dst + acc : acc;
+  }
+}
+
+// db[n] (+)= sum_m dZ[m, n]   (bias gradient); block partials in double, fixed-order finalisation
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dz, int64_t ld, int M, int N,
+                                                             int rows_per_block, float* __restrict__ partial) {
+  // thread = (row lane, column): 256 threads = 8 row lanes x 32 columns per pass
+  const int col_lane = threadIdx.x & 31, row_lane = threadIdx.x >> 5;
+  __shared__ float red[8][33];
+  const int r0 = blockIdx.x * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    const int c = c0 + col_lane;
+    float acc = 0.f;
+    if (c < N)
+      for (int r = r0 + row_lane; r < r1; r += 8) acc += dz[(int64_t)r * ld + c];
+    red[row_lane][col_lane] = acc;
+    __syncthreads();
+    if (row_lane == 0 && c < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][col_lane];
+      partial[(int64_t)blockIdx.x * N + c] = s;
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ db,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * N + c];
+  db[c] = accumulate ? db[c] + (float)acc : (float)acc;
+}
+
+template <int BN, int PASSES>
+static int launch_wgrad(const CUtensorMap& tDZ, const CUtensorMap& tX, const WgradParams& p, cudaStream_t s) {
+  using Cfg = WgradCfg<BN, PASSES>;
+  auto kern = wgrad_tf32_kernel<BN, PASSES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  const int grid = p.num_m_tiles * p.num_n_tiles * p.splits;
+  kern<<<grid, WG_THREADS, Cfg::SMEM_BYTES, s>>>(tDZ, tX, p);
+  return check_launch("wgrad_tf32_kernel");
+}
+
+static void wgrad_plan(int64_t M, int64_t N, int64_t K, int* bn, int* mt, int* nt, int* splits, int* rows_per_split,
+                       int64_t* ldp) {
+  *bn = K > 128 ? 256 : 128;
+  *mt = (int)((N + WG_BM - 1) / WG_BM);
+  *nt = (int)((K + *bn - 1) / *bn);
+  const int tiles = *mt * *nt;
+  int sp = sm_count() / tiles;
+  if (sp < 1) sp = 1;
+  int64_t rps = ((M + sp - 1) / sp + WG_BKB - 1) / WG_BKB * WG_BKB;
+  sp = (int)((M + rps - 1) / rps);
+  *splits = sp;
+  *rows_per_split = (int)rps;
+  *ldp = (int64_t)*nt * *bn;
+}
+
+}  // namespace cusrl_b200
+
+using namespace cusrl_b200;
+
+extern "C" {
+
+size_t cusrl_b200_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int bn, mt, nt, splits, rps;
+  int64_t ldp;
+  wgrad_plan(M, N, K, &bn, &mt, &nt, &splits, &rps, &ldp);
+  const size_t partial = (size_t)splits * mt * WG_BM * ldp * sizeof(float);
+  const size_t colsum = (size_t)1184 * (size_t)N * sizeof(float);
+  return partial + colsum + 256;
+}
+
+int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, float* dW, int64_t lddw,
+                                 float* db, int64_t M, int64_t N, int64_t K, int precision, int accumulate,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  CUSRL_REQUIRE(dZ && X && dW && workspace, CUSRL_B200_EINVAL, "wgrad: null pointer");
+  CUSRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N <= 65536 && K <= 65536, CUSRL_B200_EINVAL,
+                "wgrad: bad problem size");
+  CUSRL_REQUIRE(precision == 1 || precision == 3, CUSRL_B200_EINVAL, "wgrad: precision must be 1 or 3");
+  CUSRL_REQUIRE((lddz % 4) == 0 && (ldx % 4) == 0 && lddz >= N && ldx >= K && lddw >= K, CUSRL_B200_EALIGN,
+                "wgrad: activation leading dimensions must be multiples of 4 floats and cover the row");
+  CUSRL_REQUIRE(aligned_to(dZ, 16) && aligned_to(X, 16) && aligned_to(workspace, 16), CUSRL_B200_EALIGN,
+                "wgrad: dZ, X and workspace must be 16-byte aligned");
+  CUSRL_REQUIRE(workspace_bytes >= cusrl_b200_wgrad_workspace_bytes(M, N, K), CUSRL_B200_ESCRATCH, "wgrad: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int bn, mt, nt, splits, rps;
+  int64_t ldp;
+  wgrad_plan(M, N, K, &bn, &mt, &nt, &splits, &rps, &ldp);
+  CUtensorMap tDZ, tX;
+  if (int e = encode_tmap_2d_f32(&tDZ, dZ, (uint64_t)N, (uint64_t)M, (uint64_t)lddz, WG_CHUNK, WG_BKB, true)) return e;
+  if (int e = encode_tmap_2d_f32(&tX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, WG_CHUNK, WG_BKB, true)) return e;
+  WgradParams p{};
+  p.partial = (float*)workspace, p.ldp = ldp, p.M = (int)M, p.N = (int)N, p.K = (int)K;
+  p.num_m_tiles = mt, p.num_n_tiles = nt, p.splits = splits, p.rows_per_split = rps;
+  int e = CUSRL_B200_EUNSUPPORTED;
+  if (bn == 256 && precision == 3) e = launch_wgrad<256, 3>(tDZ, tX, p, s);
+  else if (bn == 128 && precision == 3) e = launch_wgrad<128, 3>(tDZ, tX, p, s);
+  else if (bn == 256 && precision == 1) e = launch_wgrad<256, 1>(tDZ, tX, p, s);
+  else if (bn == 128 && precision == 1) e = launch_wgrad<128, 1>(tDZ, tX, p, s);
+  if (e) return e;
+  const int64_t split_stride = (int64_t)mt * WG_BM * ldp;
+  int blocks = (int)((N * K + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(p.partial, splits, split_stride, ldp, dW, lddw, (int)N, (int)K, accumulate);
+  if (int e2 = check_launch("wgrad_reduce_kernel")) return e2;
+  if (db) {
+    float* cs = p.partial + (int64_t)splits * split_stride;
+    int nb = sm_count() * 8;
+    if (nb > 1184) nb = 1184;
+    int rows_per_block = (int)((M + nb - 1) / nb);
+    nb = (int)((M + rows_per_block - 1) / rows_per_block);
+    colsum_partial_kernel<<<nb, 256, 0, s>>>(dZ, lddz, (int)M, (int)N, rows_per_block, cs);
+    if (int e3 = check_launch("colsum_partial_kernel")) return e3;
+    colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(cs, nb, (int)N, db, accumulate);
+    if (int e4 = check_launch("colsum_final_kernel")) return e4;
+  }
+  return 0;
+}
+
+}  // extern "C"

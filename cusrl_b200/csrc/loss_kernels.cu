@@ -242,6 +242,17 @@ __global__ void scale_kernel(float* __restrict__ x, int64_t n, const float* __re
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= s;
 }
 
+// dz = dy * act'(z) expressed through the stored post-activation y (ELU: y > 0 ? 1 : y + 1; ReLU: y > 0)
+__global__ void act_grad_mul_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                    int64_t n, int act) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float yi = y[i];
+    const float g = act == 1 ? (yi > 0.f ? 1.f : yi + 1.f) : (act == 2 ? (yi > 0.f ? 1.f : 0.f) : 1.f);
+    dz[i] = dy[i] * g;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // OnPolicyStatistics (hook/on_policy/stats.py:29-40): KL(old || new) of diagonal normals
 // (torch kl_divergence(Normal, Normal): 0.5*(var_ratio + t1 - 1 - log var_ratio), var_ratio=(s_p/s_q)^2,
@@ -363,6 +374,17 @@ int cusrl_b200_scale_f32(float* x, int64_t n, const float* scale_dev, void* stre
   if (blocks > cap) blocks = cap;
   scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
   return check_launch("scale_kernel");
+}
+
+int cusrl_b200_act_grad_mul_f32(const float* dy, const float* y, float* dz, int64_t n, int act, void* stream) {
+  CUSRL_REQUIRE(dy && y && dz, CUSRL_B200_EINVAL, "act_grad_mul: null pointer");
+  CUSRL_REQUIRE(n >= 0 && act >= 0 && act <= 2, CUSRL_B200_EINVAL, "act_grad_mul: bad arguments");
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  act_grad_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n, act);
+  return check_launch("act_grad_mul_kernel");
 }
 
 size_t cusrl_b200_policy_stats_scratch_bytes(void) { return (size_t)kLossMaxBlocks * kStatSlots * sizeof(double); }

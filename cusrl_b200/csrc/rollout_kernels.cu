@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128, (U * VEC >= 16 ? 4 : 6)) gae_kernel(const
   }
 }
 
-static int g_gae_vec = 1, g_gae_threads = 128;  // tuning knobs, see cusrl_b200_gae_set_config
+static int g_gae_vec = 1, g_gae_threads = 64;  // tuning knobs, see cusrl_b200_gae_set_config
 
 template <int VEC, bool FUSED, typename idx_t>
 static void launch_gae_u(const GaeParams& p, unsigned grid, int threads, cudaStream_t s) {

@@ -1,8 +1,16 @@
-"""Dense-layer primitives of the actor / critic networks.
+"""Dense-layer autograd nodes of the actor / critic networks, built on the K6 kernels.
 
-``mlp_forward`` is the single entry point used by :class:`cusrl_b200.nn.Mlp`; it owns forward AND backward
-of the whole trunk (one autograd node) so that activation derivatives are fused into the gradient GEMM
-epilogues and weight gradients are written straight into the flat gradient arena.
+One autograd node owns forward AND backward of a whole network (trunk + optional small output head):
+
+* forward  : per trunk layer one tcgen05 GEMM with fused bias + activation epilogue (``tc_linear_fwd``), then the
+             fp32 SIMT head (``head_fwd``);
+* backward : ``head_bwd`` produces the gradient w.r.t. the last trunk pre-activation directly (activation derivative
+             fused), then per layer a split-K tcgen05 weight-gradient GEMM writing straight into the flat gradient
+             arena and a data-gradient GEMM whose epilogue applies the next activation derivative.
+
+Activations are saved post-activation only (ELU' and ReLU' are functions of the output), nothing is recomputed.
+Reference arithmetic: nn.Linear + activation stacks of cusrl/nn/module/mlp.py:77-90, heads of
+cusrl/nn/module/distribution.py:56,272 and cusrl/nn/module/critic.py:87-88, and their autograd.
 """
 
 from __future__ import annotations
@@ -11,7 +19,7 @@ import torch
 
 from .. import ops
 
-__all__ = ["ACTIVATIONS", "mlp_forward", "head_linear"]
+__all__ = ["ACTIVATIONS", "mlp_forward", "mlp_head_forward"]
 
 ACTIVATIONS = {"Identity": 0, "ELU": 1, "ReLU": 2}
 
@@ -23,59 +31,103 @@ def _act_code(name: str) -> int:
         raise ValueError(f"cusrl_b200 supports activations {sorted(ACTIVATIONS)}; got '{name}'") from None
 
 
-class _MlpFunction(torch.autograd.Function):
-    """y = act(... act(x W0^T + b0) ... Wk^T + bk); activations after every layer except optionally the last."""
+def _rows_ok(x: torch.Tensor) -> torch.Tensor:
+    """2-D fp32 view with unit inner stride and a 16-byte-multiple row pitch (what TMA needs); copies only if not."""
+    if x.stride(-1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    width = x.shape[1]
+    padded = torch.zeros(x.shape[0], (width + 3) // 4 * 4, dtype=x.dtype, device=x.device)
+    padded[:, :width].copy_(x)
+    return padded[:, :width]
+
+
+def _wgrad(dz, inp, weight, bias, grads, slot):
+    """Weight / bias gradient of one layer: accumulate into the flat arena when the parameter has one."""
+    precision = ops.GEMM_PRECISION
+    w_grad, b_grad = weight.grad, (bias.grad if bias is not None else None)
+    if w_grad is not None and (bias is None or b_grad is not None) and w_grad.is_contiguous():
+        ops.tc_linear_wgrad(dz, inp, w_grad, b_grad, precision, accumulate=True)
+    else:
+        dw = torch.empty_like(weight)
+        db = torch.empty_like(bias) if bias is not None else None
+        ops.tc_linear_wgrad(dz, inp, dw, db, precision, accumulate=False)
+        grads[slot], grads[slot + 1] = dw, db
+
+
+class _MlpHeadFunction(torch.autograd.Function):
+    """(latent, out) = trunk(x), head(trunk(x)); `has_head=False` returns the trunk output only."""
 
     @staticmethod
-    def forward(ctx, x, act_code, last_act, *params):
-        weights, biases = params[0::2], params[1::2]
+    def forward(ctx, x, act_code, last_act, has_head, *params):
+        precision = ops.GEMM_PRECISION
+        n = (len(params) - (2 if has_head else 0)) // 2
+        weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
+        x = _rows_ok(x)
         acts = []
         h = x
-        n = len(weights)
-        for i, (w, b) in enumerate(zip(weights, biases)):
+        for i in range(n):
             code = act_code if (i < n - 1 or last_act) else 0
-            h = ops.linear_fwd(h, w, b, code)
+            h = ops.tc_linear_fwd(h, ops.prepared_weight(weights[i]), biases[i], weights[i].shape[0], code, precision)
             acts.append(h)
-        ctx.save_for_backward(x, *acts, *weights, *biases)
-        ctx.meta = (act_code, last_act, n, [w.requires_grad for w in weights], x.requires_grad)
+        if has_head:
+            head_w, head_b = params[2 * n], params[2 * n + 1]
+            out = ops.head_fwd(h, head_w, head_b)
+        ctx.save_for_backward(x, *acts, *params)
+        ctx.meta = (act_code, last_act, has_head, n)
+        if has_head:
+            ctx.mark_non_differentiable(h)
+            return out, h
         return h
 
     @staticmethod
-    def backward(ctx, grad_out):
-        act_code, last_act, n, w_req, x_req = ctx.meta
+    def backward(ctx, grad_out, *unused):
+        act_code, last_act, has_head, n = ctx.meta
+        x_req = ctx.needs_input_grad[0]
+        precision = ops.GEMM_PRECISION
         saved = ctx.saved_tensors
-        x, acts, weights, biases = saved[0], saved[1 : 1 + n], saved[1 + n : 1 + 2 * n], saved[1 + 2 * n :]
-        grads: list[torch.Tensor | None] = [None] * (2 * n)
-        # dZ of the last layer: grad_out * act'(y_last) (identity when the trunk does not end with an activation)
-        dz = ops.act_backward(grad_out.contiguous(), acts[-1], act_code if last_act else 0)
+        x, acts, params = saved[0], saved[1 : 1 + n], saved[1 + n :]
+        weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
+        grads: list[torch.Tensor | None] = [None] * len(params)
+        last_code = act_code if last_act else 0
+        if has_head:
+            head_w, head_b = params[2 * n], params[2 * n + 1]
+            hw_grad, hb_grad = head_w.grad, (head_b.grad if head_b is not None else None)
+            arena = hw_grad is not None and (head_b is None or hb_grad is not None)
+            dw = hw_grad if arena else torch.empty_like(head_w)
+            db = hb_grad if arena else (torch.empty_like(head_b) if head_b is not None else None)
+            # dZ of the last trunk layer = (dOut W_head) * act'(latent), fused in the head kernel
+            dz = ops.head_bwd(grad_out.contiguous(), acts[-1], head_w, last_code, dw, db, need_dh=True, accumulate=arena)
+            if not arena:
+                grads[2 * n], grads[2 * n + 1] = dw, db
+        else:
+            dz = ops.act_grad_mul(grad_out, acts[-1], last_code)
         for i in range(n - 1, -1, -1):
             inp = acts[i - 1] if i > 0 else x
-            if w_req[i]:
-                w_grad, b_grad = weights[i].grad, biases[i].grad
-                if w_grad is not None and b_grad is not None:
-                    # flat gradient arena (template/optimizer.py): accumulate in place, nothing for autograd to add
-                    ops.linear_wgrad(dz, inp, out_w=w_grad, out_b=b_grad)
-                else:
-                    grads[2 * i], grads[2 * i + 1] = ops.linear_wgrad(dz, inp)
+            if weights[i].requires_grad:
+                _wgrad(dz, inp, weights[i], biases[i], grads, 2 * i)
             if i > 0:
-                # dX = dZ W, multiplied in the epilogue by act'(previous layer's output) -> dZ of layer i-1
-                dz = ops.linear_dgrad(dz, weights[i], acts[i - 1], act_code)
+                dz = ops.tc_linear_dgrad(dz, ops.prepared_weight(weights[i]), acts[i - 1], weights[i].shape[1], act_code, precision)
             elif x_req:
-                dz = ops.linear_dgrad(dz, weights[0], None, 0)
-        return (dz if x_req else None, None, None, *grads)
+                dz = ops.tc_linear_dgrad(dz, ops.prepared_weight(weights[0]), None, weights[0].shape[1], 0, precision)
+        return (dz if x_req else None, None, None, None, *grads)
+
+
+def _flatten(x: torch.Tensor) -> tuple[torch.Tensor, tuple[int, ...]]:
+    return x.reshape(-1, x.shape[-1]), tuple(x.shape[:-1])
 
 
 def mlp_forward(x: torch.Tensor, weights, biases, activation: str, ends_with_activation: bool) -> torch.Tensor:
-    """Trunk forward over the trailing feature dim; leading dims are flattened into the GEMM M dimension."""
-    lead = x.shape[:-1]
-    x2 = x.reshape(-1, x.shape[-1])
+    """Trunk only (e.g. the RND networks): leading dims are flattened into the GEMM M dimension."""
+    x2, lead = _flatten(x)
     params = [t for pair in zip(weights, biases) for t in pair]
-    y = _MlpFunction.apply(x2, _act_code(activation), bool(ends_with_activation), *params)
+    y = _MlpHeadFunction.apply(x2, _act_code(activation), bool(ends_with_activation), False, *params)
     return y.reshape(*lead, y.shape[-1])
 
 
-def head_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
-    """Small-N fp32 output head (mean_head 128->12, value_head 128->1; reference LinearFp32, layer/linear.py)."""
-    lead = x.shape[:-1]
-    y = _MlpFunction.apply(x.reshape(-1, x.shape[-1]), 0, False, weight, bias)
-    return y.reshape(*lead, y.shape[-1])
+def mlp_head_forward(x: torch.Tensor, weights, biases, activation: str, head_weight: torch.Tensor,
+                     head_bias: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor]:
+    """(head output, latent) of an activation-terminated trunk followed by a small fp32 linear head."""
+    x2, lead = _flatten(x)
+    params = [t for pair in zip(weights, biases) for t in pair] + [head_weight, head_bias]
+    out, latent = _MlpHeadFunction.apply(x2, _act_code(activation), True, True, *params)
+    return out.reshape(*lead, out.shape[-1]), latent.reshape(*lead, latent.shape[-1])

@@ -139,12 +139,8 @@ class NormalDist(Module):
         self.mean_head = nn.Linear(input_dim, output_dim)
         self.std = StddevVector(output_dim, init_std)
 
-    def forward(self, backbone_feat: Tensor, **kwargs) -> dict[str, Tensor]:
-        mean = F.head_linear(backbone_feat, self.mean_head.weight, self.mean_head.bias)
+    def params_from_mean(self, mean: Tensor) -> dict[str, Tensor]:
         return {"mean": mean, "std": self.std(mean)}
-
-    def determine(self, backbone_feat: Tensor, **kwargs) -> Tensor:
-        return F.head_linear(backbone_feat, self.mean_head.weight, self.mean_head.bias)
 
     # torch Normal arithmetic (distribution.py:195-218), kept in torch for the small rollout-time tensors
     @staticmethod
@@ -169,9 +165,6 @@ class NormalDist(Module):
         sample = mean + eps * std
         return sample, self.compute_logp(dist_params, sample)
 
-    def sample(self, backbone_feat: Tensor, **kwargs):
-        dist_params = self(backbone_feat)
-        return dist_params, self.sample_from_dist(dist_params)
 
 
 @dataclass(slots=True)
@@ -195,24 +188,31 @@ class Actor(Module):
         self.backbone, self.distribution = backbone, distribution
         self.latent_dim = backbone.output_dim
 
-    def _features(self, observation: Tensor, memory=None, done=None, **kw):
+    def _mean(self, observation: Tensor, memory=None, done=None):
+        """backbone + mean head as ONE autograd node (trunk GEMMs on tcgen05, fp32 SIMT head)."""
+        head = self.distribution.mean_head
         if self.backbone.is_recurrent:
-            return self.backbone(observation, memory=memory, done=done, **kw)
-        return self.backbone(observation), memory
+            raise NotImplementedError("recurrent backbones are handled by cusrl_b200.nn.recurrent")
+        lins = self.backbone.linears()
+        if not self.backbone.ends_with_activation:
+            raise ValueError("Actor expects an activation-terminated Mlp backbone (reference preset/ppo.py:137-140)")
+        mean, latent = F.mlp_head_forward(observation, [m.weight for m in lins], [m.bias for m in lins],
+                                          self.backbone.activation, head.weight, head.bias)
+        self.intermediate_repr["backbone.output"] = latent
+        return mean, memory
 
     def forward(self, observation: Tensor, memory=None, done: Tensor | None = None, **kw):
-        feat, memory = self._features(observation, memory, done)
-        self.intermediate_repr["backbone.output"] = feat
-        return self.distribution(feat), memory
+        mean, memory = self._mean(observation, memory, done)
+        return self.distribution.params_from_mean(mean), memory
 
     def explore(self, observation: Tensor, memory=None, deterministic: bool = False, **kw):
-        feat, memory = self._features(observation, memory, None, **(kw.get("backbone_kwargs") or {}))
+        mean, memory = self._mean(observation, memory, None)
+        dist_params = self.distribution.params_from_mean(mean)
         if deterministic:
-            dist_params = self.distribution(feat)
-            action = dist_params["mean"]
+            action = mean
             logp = self.distribution.compute_logp(dist_params, action)
         else:
-            dist_params, (action, logp) = self.distribution.sample(feat)
+            action, logp = self.distribution.sample_from_dist(dist_params)
         return dist_params, (action, logp), memory
 
     def act(self, observation: Tensor, memory=None, deterministic: bool = False, **kw):
@@ -257,11 +257,14 @@ class Value(Module):
 
     def forward(self, state: Tensor, *, memory=None, done: Tensor | None = None, **kw):
         if self.backbone.is_recurrent:
-            latent, memory = self.backbone(state, memory=memory, done=done, **kw)
-        else:
-            latent = self.backbone(state)
+            raise NotImplementedError("recurrent backbones are handled by cusrl_b200.nn.recurrent")
+        lins = self.backbone.linears()
+        if not self.backbone.ends_with_activation:
+            raise ValueError("Value expects an activation-terminated Mlp backbone (reference preset/ppo.py:143-147)")
+        value, latent = F.mlp_head_forward(state, [m.weight for m in lins], [m.bias for m in lins],
+                                           self.backbone.activation, self.value_head.weight, self.value_head.bias)
         self.intermediate_repr["backbone.output"] = latent
-        return F.head_linear(latent, self.value_head.weight, self.value_head.bias), memory
+        return value, memory
 
     def evaluate(self, state: Tensor, *, memory=None, done: Tensor | None = None, **kw) -> Tensor:
         return self(state, memory=memory, done=done, **kw)[0]

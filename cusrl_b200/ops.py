@@ -372,52 +372,142 @@ def adam_step_(
 
 
 # ---------------------------------------------------------------------------------------------- K6
-# Dense layers.  TEMPORARY (round-1 bring-up): these four functions call cuBLAS through torch so that
-# the end-to-end path and its parity tests exist before the tcgen05 kernels land; they are replaced by
-# the C-ABI entry points cusrl_b200_linear_{fwd,dgrad,wgrad}_tf32 and must not survive the round.
-def _require_cuda(t: torch.Tensor, name: str) -> None:
+# Dense layers on tcgen05 (csrc/gemm_tf32.cu, csrc/gemm_wgrad_tf32.cu) and SIMT heads (csrc/head_kernels.cu).
+GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))  # 3 = 3xTF32 (fp32-equivalent), 1 = TF32
+
+_weights_epoch = 0
+_weight_cache: dict[int, tuple[tuple, dict[str, torch.Tensor]]] = {}
+
+
+def invalidate_weight_cache() -> None:
+    """Parameters were rewritten through raw pointers (optimizer step / checkpoint load): operand copies are stale."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def prepared_weight(w: torch.Tensor) -> dict[str, torch.Tensor]:
+    """hi/lo (+ transposed) tensor-core operand copies of a weight matrix, rebuilt once per optimizer step."""
+    key = w.data_ptr()
+    stamp = (_weights_epoch, w._version, tuple(w.shape))
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    wp = weight_prep(w) if hit is None else weight_prep(w, out=hit[1])
+    _weight_cache[key] = (stamp, wp)
+    return wp
+
+
+def act_grad_mul(dy: torch.Tensor, y: torch.Tensor, act: int) -> torch.Tensor:
+    """dZ = dY * act'(Z) from the stored post-activation Y."""
+    dy = dy.contiguous()
+    if act == 0:
+        return dy
+    y = y.contiguous()
+    dz = torch.empty_like(dy)
+    code = _lib.load().cusrl_b200_act_grad_mul_f32(_ptr(dy, torch.float32, "dy"), _ptr(y, torch.float32, "y"),
+                                                   dz.data_ptr(), dy.numel(), act, _stream())
+    _lib.check(code, "act_grad_mul")
+    return dz
+
+
+# ---- tcgen05 dense-layer entry points (raw; the autograd-facing wrappers above will move onto these) ----
+def weight_prep(w: torch.Tensor, transposed: bool = True, out: dict[str, torch.Tensor] | None = None) -> dict[str, torch.Tensor]:
+    """hi/lo (and transposed hi/lo) operand copies of a weight matrix [N, K]; leading dims padded to 4 floats."""
+    N, K = w.shape
+    ld = (K + 3) // 4 * 4
+    ldt = (N + 3) // 4 * 4
+    if out is None:
+        out = {"hi": torch.zeros(N, ld, device=w.device), "lo": torch.zeros(N, ld, device=w.device)}
+        if transposed:
+            out["hi_t"] = torch.zeros(K, ldt, device=w.device)
+            out["lo_t"] = torch.zeros(K, ldt, device=w.device)
+    transposed = "hi_t" in out
+    code = _lib.load().cusrl_b200_weight_prep_f32(
+        _ptr(w.detach(), torch.float32, "weight"), N, K, out["hi"].data_ptr(), out["lo"].data_ptr(), ld,
+        out["hi_t"].data_ptr() if transposed else None, out["lo_t"].data_ptr() if transposed else None, ldt, _stream())
+    _lib.check(code, "weight_prep")
+    return out
+
+
+def _rows(t: torch.Tensor, name: str) -> tuple[int, int]:
+    """(data_ptr, leading dimension) of a 2-D tensor with unit inner stride."""
     if not t.is_cuda:
         raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
+        raise ValueError(f"cusrl_b200: '{name}' must be a 2-D float32 tensor with a dense last dim")
+    return t.data_ptr(), t.stride(0)
 
 
-def _apply_act(z: torch.Tensor, act: int) -> torch.Tensor:
-    if act == 1:
-        return torch.nn.functional.elu(z)
-    if act == 2:
-        return torch.relu(z)
-    return z
+def tc_linear_fwd(x: torch.Tensor, wp: dict[str, torch.Tensor], bias: torch.Tensor | None, n_out: int, act: int,
+                  precision: int = 3, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Y = act(X W^T + b) on tcgen05 (cusrl_b200_linear_fwd_tf32)."""
+    M, K = x.shape
+    xp, ldx = _rows(x, "x")
+    y = torch.empty(M, n_out, device=x.device) if out is None else out
+    yp, ldy = _rows(y, "y")
+    code = _lib.load().cusrl_b200_linear_fwd_tf32(
+        xp, ldx, wp["hi"].data_ptr(), wp["lo"].data_ptr(), wp["hi"].stride(0), _ptr(bias, torch.float32, "bias"),
+        yp, ldy, M, n_out, K, act, precision, _stream())
+    _lib.check(code, "linear_fwd")
+    return y
 
 
-def linear_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, act: int) -> torch.Tensor:
-    """Y = act(X W^T + b) (reference nn/module/mlp.py:77-90: nn.Linear + activation)."""
-    _require_cuda(x, "x")
-    return _apply_act(torch.nn.functional.linear(x, w, b), act)
+def tc_linear_dgrad(dy: torch.Tensor, wp: dict[str, torch.Tensor], x_act: torch.Tensor | None, k_in: int, act: int,
+                    precision: int = 3, out: torch.Tensor | None = None) -> torch.Tensor:
+    """dX = (dY W) * act'(x_act) on tcgen05 (cusrl_b200_linear_dgrad_tf32)."""
+    M, N = dy.shape
+    dyp, lddy = _rows(dy, "dy")
+    dx = torch.empty(M, k_in, device=dy.device) if out is None else out
+    dxp, lddx = _rows(dx, "dx")
+    xa, ldxa = (None, 0) if x_act is None else _rows(x_act, "x_act")
+    code = _lib.load().cusrl_b200_linear_dgrad_tf32(
+        dyp, lddy, wp["hi_t"].data_ptr(), wp["lo_t"].data_ptr(), wp["hi_t"].stride(0), xa, ldxa, dxp, lddx,
+        M, N, k_in, act, precision, _stream())
+    _lib.check(code, "linear_dgrad")
+    return dx
 
 
-def act_backward(dy: torch.Tensor, y: torch.Tensor, act: int) -> torch.Tensor:
-    """dZ = dY * act'(Z) expressed through the stored post-activation Y (ELU: y>0 ? 1 : y+1)."""
-    _require_cuda(dy, "dy")
-    if act == 1:
-        return dy * torch.where(y > 0, torch.ones_like(y), y + 1.0)
-    if act == 2:
-        return dy * (y > 0).to(dy.dtype)
-    return dy
+def tc_linear_wgrad(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: torch.Tensor | None, precision: int = 3,
+                    accumulate: bool = False) -> None:
+    """dW (+)= dZ^T X and db (+)= colsum(dZ) on tcgen05 (cusrl_b200_linear_wgrad_tf32)."""
+    M, N = dz.shape
+    K = x.shape[1]
+    dzp, lddz = _rows(dz, "dz")
+    xp, ldx = _rows(x, "x")
+    if not dw.is_contiguous() or dw.shape != (N, K):
+        raise ValueError("tc_linear_wgrad: dw must be a contiguous [N, K] tensor")
+    lib = _lib.load()
+    ws = _get_scratch(dz.device, "wgrad", lib.cusrl_b200_wgrad_workspace_bytes(M, N, K))
+    code = lib.cusrl_b200_linear_wgrad_tf32(dzp, lddz, xp, ldx, dw.data_ptr(), K, _ptr(db, torch.float32, "db"), M, N, K,
+                                            precision, int(accumulate), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(code, "linear_wgrad", launches=4 if db is not None else 2)
 
 
-def linear_dgrad(dz: torch.Tensor, w: torch.Tensor, y_prev: torch.Tensor | None, act: int) -> torch.Tensor:
-    """dX = dZ W, multiplied by act'(previous layer output) when y_prev is given."""
-    _require_cuda(dz, "dz")
-    dx = dz @ w
-    return dx if y_prev is None else act_backward(dx, y_prev, act)
+def head_fwd(h: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None) -> torch.Tensor:
+    """Y = H W^T + b for a small-N fp32 head (cusrl_b200_head_fwd_f32)."""
+    M, K = h.shape
+    No = w.shape[0]
+    hp, ldh = _rows(h, "h")
+    y = torch.empty(M, No, device=h.device)
+    code = _lib.load().cusrl_b200_head_fwd_f32(hp, ldh, _ptr(w.detach(), torch.float32, "weight"),
+                                               _ptr(None if b is None else b.detach(), torch.float32, "bias"),
+                                               y.data_ptr(), M, K, No, _stream())
+    _lib.check(code, "head_fwd")
+    return y
 
 
-def linear_wgrad(dz: torch.Tensor, x: torch.Tensor, out_w: torch.Tensor | None = None,
-                 out_b: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
-    """dW = dZ^T X, db = column sums of dZ; accumulated into out_w / out_b when given."""
-    _require_cuda(dz, "dz")
-    if out_w is not None:
-        out_w.addmm_(dz.t(), x)
-        if out_b is not None:
-            out_b.add_(dz.sum(dim=0))
-        return out_w, out_b
-    return dz.t() @ x, dz.sum(dim=0)
+def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: torch.Tensor, db: torch.Tensor | None,
+             need_dh: bool = True, accumulate: bool = False) -> torch.Tensor | None:
+    """dH = (dY W) * act'(H); dW (+)= dY^T H; db (+)= colsum(dY) (cusrl_b200_head_bwd_f32)."""
+    M, K = h.shape
+    No = w.shape[0]
+    hp, ldh = _rows(h, "h")
+    dh = torch.empty(M, K, device=h.device) if need_dh else None
+    lib = _lib.load()
+    scratch = _get_scratch(h.device, "headbwd", lib.cusrl_b200_head_bwd_scratch_bytes(K, No))
+    code = lib.cusrl_b200_head_bwd_f32(
+        _ptr(dy, torch.float32, "dy"), hp, ldh, _ptr(w.detach(), torch.float32, "weight"), act,
+        None if dh is None else dh.data_ptr(), K, _ptr(dw, torch.float32, "dw"), _ptr(db, torch.float32, "db"),
+        M, K, No, int(accumulate), scratch.data_ptr(), scratch.numel(), _stream())
+    _lib.check(code, "head_bwd", launches=2)
+    return dh

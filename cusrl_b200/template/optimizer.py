@@ -114,6 +114,7 @@ class FlatAdam:
             self.arena.flat, self.arena.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
             g["betas"], g["eps"], g["weight_decay"], coef=self.clip_coef if self._clip_pending else None)
         self._clip_pending = False
+        ops.invalidate_weight_cache()  # the Adam kernel rewrote the parameters through raw pointers
 
     def state_dict(self) -> dict[str, Any]:
         return {
@@ -127,6 +128,7 @@ class FlatAdam:
         self.step_count = int(state["step"])
         self.exp_avg.copy_(state["exp_avg"])
         self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        ops.invalidate_weight_cache()
         for g, saved in zip(self.param_groups, state.get("param_groups", [])):
             g.update({k: v for k, v in saved.items() if k not in ("params", "param_names")})
 

@@ -141,6 +141,8 @@ int cusrl_b200_ppo_loss_f32(const float* mean, const float* std, const float* ac
                             float* entropy, float* logp_ratio, float* prob_ratio, float* losses,
                             float* metrics, float* d_mean, float* d_std_surr, float* d_std_ent,
                             float* d_value, void* scratch, size_t scratch_bytes, void* stream);
+/* dz[i] = dy[i] * act'(z_i) computed from the stored post-activation y (act: 0 identity, 1 ELU, 2 ReLU). */
+int cusrl_b200_act_grad_mul_f32(const float* dy, const float* y, float* dz, int64_t n, int act, void* stream);
 /* x[i] *= *scale_dev (in place, n floats); used to apply an upstream autograd scalar. */
 int cusrl_b200_scale_f32(float* x, int64_t n, const float* scale_dev, void* stream);
 
@@ -167,6 +169,52 @@ int cusrl_b200_clip_coef_f32(const double* sumsq_dev, float max_norm, float* nor
 int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                              int64_t n, const float* coef_dev, float lr, float beta1, float beta2,
                              float eps, float weight_decay, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  dense layers of the MLP actor/critic on tcgen05 tensor cores (TMA-fed, TMEM accumulators) --
+ *     replaces nn.Linear + activation in Mlp.forward (nn/module/mlp.py:77-90) and its autograd.
+ *   precision: 1 = single-pass TF32, 3 = 3xTF32 error-compensated (fp32-equivalent accuracy; the
+ *              reference runs these layers as fp32 SGEMM).
+ *   act:       0 = identity, 1 = ELU(alpha=1), 2 = ReLU.
+ *   weight_prep:  hi = W & ~0x1fff (TF32-representable), lo = W - hi, written with leading dimension
+ *                 ld (>= K); optionally the transposed copies hi_t/lo_t [K, ldt] used by the data
+ *                 gradient.  Run once per optimizer step per layer.
+ *   linear_fwd:   Y[M,N]  = act(X[M,K] @ W[N,K]^T + bias[N])       W given as (W_hi, W_lo) with ldw
+ *   linear_dgrad: dX[M,K] = (dY[M,N] @ W[N,K]) * act'(Xact[M,K])   W given as transposed copies
+ *                 (WT_hi, WT_lo) [K, ldwt]; Xact = the layer input (= post-activation output of the layer
+ *                 below); Xact==NULL: no activation factor.
+ *   Leading dimensions are in ELEMENTS and must be multiples of 4 (16-byte rows for TMA); N must be a
+ *   multiple of 4; ragged K / M edges are zero-filled by TMA.  All pointers 16-byte aligned. */
+int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld,
+                               float* hi_t, float* lo_t, int64_t ldt, void* stream);
+int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, const float* W_lo,
+                               int64_t ldw, const float* bias, float* Y, int64_t ldy, int64_t M,
+                               int64_t N, int64_t K, int act, int precision, void* stream);
+int cusrl_b200_linear_dgrad_tf32(const float* dY, int64_t lddy, const float* WT_hi, const float* WT_lo,
+                                 int64_t ldwt, const float* Xact, int64_t ldxa, float* dX, int64_t lddx,
+                                 int64_t M, int64_t N, int64_t K, int act, int precision, void* stream);
+
+/*   linear_wgrad: dW[N,K] (+)= dZ[M,N]^T @ X[M,K];  db[N] (+)= column sums of dZ (db may be NULL).
+ *                 Split-K over CTAs with a deterministic second-stage reduction through `workspace`
+ *                 (cusrl_b200_wgrad_workspace_bytes).  accumulate != 0 adds to the existing dW / db
+ *                 (flat gradient arena semantics), 0 overwrites.  lddz, ldx multiples of 4. */
+size_t cusrl_b200_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, float* dW,
+                                 int64_t lddw, float* db, int64_t M, int64_t N, int64_t K, int precision,
+                                 int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Small-N output heads (actor mean_head, critic value_head; reference LinearFp32 / nn.Linear in
+ * nn/module/distribution.py:56 and nn/module/critic.py:87-88), exact fp32 SIMT kernels, HBM-bound:
+ *   head_fwd: Y[M,No] = H[M,K] @ W[No,K]^T + bias[No]
+ *   head_bwd: dH[M,K] = (dY[M,No] @ W) * act'(H)   (dH may be NULL);
+ *             dW[No,K] (+)= dY^T @ H;  db[No] (+)= column sums of dY (db may be NULL)
+ *   K multiple of 128, No <= 16, No*K <= 2048.  W, dY, Y dense; ldh / lddh multiples of 4. */
+int cusrl_b200_head_fwd_f32(const float* H, int64_t ldh, const float* W, const float* bias, float* Y,
+                            int64_t M, int64_t K, int64_t No, void* stream);
+size_t cusrl_b200_head_bwd_scratch_bytes(int64_t K, int64_t No);
+int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const float* W, int act, float* dH,
+                            int64_t lddh, float* dW, float* db, int64_t M, int64_t K, int64_t No,
+                            int accumulate, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

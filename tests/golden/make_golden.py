@@ -213,7 +213,7 @@ def make_iteration():
     from cusrl.template.environment import EnvironmentSpec
 
     obs_dim, act_dim, N, T = 19, 5, 16, 6
-    hidden = (32, 16, 8)
+    hidden = (64, 32, 128)  # latent 128: the B200 head kernels need a latent width that is a multiple of 128
     torch.manual_seed(7)
     factory = cusrl.preset.ppo.PpoAgentFactory(
         num_steps_per_update=T, actor_hidden_dims=hidden, critic_hidden_dims=hidden, activation_fn="ELU", lr=1e-3,

@@ -1,0 +1,127 @@
+"""GPU: tcgen05 dense-layer kernels (K6) and the SIMT heads against fp64 references.
+
+Tolerances: 3xTF32 must be fp32-equivalent (max error within a small factor of cuBLAS fp32 SGEMM's own error on the
+same inputs); single-pass TF32 must be within TF32's 2^-10 input rounding."""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from cusrl_b200 import build
+
+    build.build()
+    from cusrl_b200 import ops as _ops
+
+    return _ops
+
+
+def _act(z, act):
+    return torch.nn.functional.elu(z) if act == 1 else (torch.relu(z) if act == 2 else z)
+
+
+def _padded(M, K, g):
+    return torch.randn(M, (K + 3) // 4 * 4, generator=g).to(DEV)[:, :K]
+
+
+@pytest.mark.parametrize("M,K,N,act", [(128, 32, 128, 0), (300, 235, 512, 1), (1000, 512, 256, 1), (1000, 256, 128, 1),
+                                       (777, 64, 16, 0), (4096, 19, 64, 2), (1, 128, 128, 1)])
+@pytest.mark.parametrize("precision", [3, 1])
+def test_linear_fwd(ops, M, K, N, act, precision):
+    g = torch.Generator().manual_seed(M + K + N)
+    x = _padded(M, K, g)
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    y = ops.tc_linear_fwd(x, ops.weight_prep(w), b, N, act, precision)
+    ref = _act(torch.nn.functional.linear(x.double(), w.double(), b.double()), act)
+    err = (y.double() - ref).abs().max().item()
+    f32 = (_act(torch.nn.functional.linear(x, w, b), act).double() - ref).abs().max().item()
+    bound = max(8 * f32, 2e-6 * ref.abs().max().item()) if precision == 3 else 4e-3 * max(ref.abs().max().item(), 1.0)
+    assert err <= bound, (err, f32)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 128, 256, 1), (777, 256, 512, 1), (500, 16, 128, 2), (333, 64, 20, 0)])
+def test_linear_dgrad(ops, M, N, K, act):
+    g = torch.Generator().manual_seed(M + N)
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / N**0.5).to(DEV)
+    xa = torch.randn(M, (K + 3) // 4 * 4, generator=g).to(DEV)[:, :K]
+    dx = ops.tc_linear_dgrad(dy, ops.weight_prep(w), xa if act else None, K, act, 3,
+                             out=torch.empty(M, (K + 3) // 4 * 4, device=DEV)[:, :K])
+    ref = dy.double() @ w.double()
+    if act == 1:
+        ref = ref * torch.where(xa > 0, torch.ones_like(xa), xa + 1).double()
+    elif act == 2:
+        ref = ref * (xa > 0).double()
+    f32 = ((dy @ w).double() - dy.double() @ w.double()).abs().max().item()
+    assert (dx.double() - ref).abs().max().item() <= max(8 * f32, 2e-6 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 128), (4096, 512, 235), (5000, 256, 512), (5000, 128, 256), (3000, 16, 128),
+                                   (100, 64, 19)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_linear_wgrad(ops, M, N, K, accumulate):
+    g = torch.Generator().manual_seed(M + N + K)
+    dz = torch.randn(M, N, generator=g).to(DEV)
+    x = _padded(M, K, g)
+    base_w, base_b = torch.randn(N, K, generator=g).to(DEV), torch.randn(N, generator=g).to(DEV)
+    dw, db = base_w.clone(), base_b.clone()
+    ops.tc_linear_wgrad(dz, x, dw, db, 3, accumulate=accumulate)
+    ref_w, ref_b = dz.double().t() @ x.double(), dz.double().sum(0)
+    if accumulate:
+        ref_w, ref_b = ref_w + base_w.double(), ref_b + base_b.double()
+    f32 = ((dz.t() @ x).double() - dz.double().t() @ x.double()).abs().max().item()
+    assert (dw.double() - ref_w).abs().max().item() <= max(8 * f32, 3e-6 * ref_w.abs().max().item())
+    assert (db.double() - ref_b).abs().max().item() <= 1e-5 * max(ref_b.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("M,K,No", [(1000, 128, 12), (5000, 128, 1), (257, 256, 8), (64, 128, 5)])
+def test_heads(ops, M, K, No):
+    g = torch.Generator().manual_seed(M + No)
+    h = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(No, K, generator=g) / K**0.5).to(DEV)
+    b = torch.randn(No, generator=g).to(DEV)
+    y = ops.head_fwd(h, w, b)
+    assert torch.allclose(y.double(), torch.nn.functional.linear(h.double(), w.double(), b.double()), rtol=1e-5, atol=1e-5)
+    dy = torch.randn(M, No, generator=g).to(DEV)
+    dw, db = torch.zeros(No, K, device=DEV), torch.zeros(No, device=DEV)
+    dh = ops.head_bwd(dy, h, w, 1, dw, db)
+    dh_ref = (dy.double() @ w.double()) * torch.where(h > 0, torch.ones_like(h), h + 1).double()
+    assert torch.allclose(dh.double(), dh_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dw.double(), dy.double().t() @ h.double(), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(db.double(), dy.double().sum(0), rtol=1e-5, atol=1e-4)
+
+
+def test_network_node_matches_torch_autograd(ops):
+    """The fused trunk+head autograd node against plain torch autograd of the same network (fp64 reference)."""
+    from cusrl_b200.nn import functional as F
+
+    g = torch.Generator().manual_seed(0)
+    B, dims, No = 2048, (235, 512, 256, 128), 12
+    x = _padded(B, dims[0], g)
+    ws = [(torch.randn(o, i, generator=g) / i**0.5).to(DEV).requires_grad_(True) for i, o in zip(dims[:-1], dims[1:])]
+    bs = [torch.randn(o, generator=g).mul(0.1).to(DEV).requires_grad_(True) for o in dims[1:]]
+    hw = (torch.randn(No, dims[-1], generator=g) / dims[-1]**0.5).to(DEV).requires_grad_(True)
+    hb = torch.zeros(No, device=DEV, requires_grad=True)
+    out, latent = F.mlp_head_forward(x, ws, bs, "ELU", hw, hb)
+    gout = torch.randn(B, No, generator=g).to(DEV)
+    out.backward(gout)
+    got = [p.grad.clone() for p in ws + bs + [hw, hb]]
+    params64 = [p.detach().double().requires_grad_(True) for p in ws + bs + [hw, hb]]
+    w64, b64, hw64, hb64 = params64[:3], params64[3:6], params64[6], params64[7]
+    h = x.double()
+    for w, b in zip(w64, b64):
+        h = torch.nn.functional.elu(torch.nn.functional.linear(h, w, b))
+    ref_out = torch.nn.functional.linear(h, hw64, hb64)
+    ref_out.backward(gout.double())
+    assert torch.allclose(out.double(), ref_out, rtol=1e-5, atol=2e-5)
+    assert torch.allclose(latent.double(), h, rtol=1e-5, atol=2e-5)
+    for a, r in zip(got, params64):
+        scale = r.grad.abs().max().item()
+        assert (a.double() - r.grad).abs().max().item() <= 2e-5 * scale + 1e-6

@@ -89,7 +89,7 @@ def test_gae_all_vector_widths(ops, vec, threads):
         adv, ret = ops.gae(reward.to(DEV), done.to(DEV), value.to(DEV), nv.to(DEV), 0.99, 0.95)
         assert torch.equal(adv.cpu(), ref_adv) and torch.equal(ret.cpu(), ref_ret)
     finally:
-        lib.cusrl_b200_gae_set_config(1, 128)
+        lib.cusrl_b200_gae_set_config(1, 64)
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])

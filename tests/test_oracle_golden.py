@@ -124,7 +124,7 @@ def _iteration_setup(golden):
     g = golden("iteration")
     params = {k[len("param0/"):]: g.t(k) for k in g.keys() if k.startswith("param0/")}
     buf = {k[len("buffer/"):]: g.t(k) for k in g.keys() if k.startswith("buffer/")}
-    cfg = O.PpoConfig(obs_dim=19, act_dim=5, hidden=(32, 16, 8), num_steps=6)
+    cfg = O.PpoConfig(obs_dim=19, act_dim=5, hidden=(64, 32, 128), num_steps=6)
     return g, cfg, params, buf
 
 

@@ -106,7 +106,7 @@ def main():
             m, b = timer([lambda d=d: ops.gae_fused(d["reward"], d["term"], d["trunc"], d["value"], d["boot"], 0.99, 0.95,
                                                     advantage=d["adv"], ret=d["ret"]) for d in sets])
             report("gae_fused(18B/elt)", 18 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
-        lib.cusrl_b200_gae_set_config(1, 128)
+        lib.cusrl_b200_gae_set_config(1, 64)
     if want("next_value"):
         m, b = timer([lambda d=d: ops.next_value(d["value"], d["term"], d["trunc"], d["boot"], out=d["nv"]) for d in sets])
         report("next_value", 10 * E, m, b, peak, which)
