@@ -5,12 +5,16 @@
 // * forward   : A = X,  B = W        epilogue  y = act(d + bias)                      (nn.Linear + ELU/ReLU)
 // * data grad : A = dZ, B = W^T copy epilogue  dx = d * act'(y_prev)                  (autograd of the layer below)
 //
-// Persistent, warp-specialised CTA (one per SM):
-//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled tiles -> shared memory ring, mbarrier tx
-//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue       : tcgen05.ld -> registers -> bias/activation -> 128-bit global stores
-//   warps 8-11  splitter (3xTF32 only): rewrites the A tile in place as hi = A & ~0x1fff and writes lo = A - hi
+// Persistent, warp-specialised CTAs (one per SM) launched as 2-CTA clusters:
+//   warp 0       TMA producer  : cp.async.bulk.tensor 128B-swizzled tiles -> shared-memory ring, mbarrier tx.  The two
+//                                CTAs of a cluster work on two M tiles that share the same weight tile: each loads its
+//                                own A tile and HALF of the B tile, multicast to both CTAs, so every weight byte leaves
+//                                L2 once per cluster (the weights are re-read for every M tile: L2 bandwidth, not HBM,
+//                                is what bounds the main loop otherwise)
+//   warp 1       MMA issuer    : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
+//   warp 2       TMEM allocator
+//   warps 4-11   epilogue      : tcgen05.ld -> registers -> bias/activation -> 128-bit global stores
+//   warps 12-15  splitter (3xTF32 only): rewrites the A tile in place as hi = A & ~0x1fff and writes lo = A - hi
 // Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Precision.  The reference computes these layers with fp32 SGEMM.  PASSES = 3 is the error-compensated
@@ -27,7 +31,7 @@ using namespace tc;
 constexpr int BM = 128;           // rows per CTA tile (UMMA M)
 constexpr int BK = 32;            // fp32 per k-block = 128 bytes = one SWIZZLE_128B span
 constexpr int UMMA_K = 8;         // tf32 elements per tcgen05.mma
-constexpr int kGemmThreads = 384;
+constexpr int kGemmThreads = 512;
 constexpr int kSmemBudget = 220 * 1024;
 
 enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1 };
@@ -40,6 +44,7 @@ struct GemmParams {
   int64_t ldaux;
   int M, N, K, act;
   int num_m_tiles, num_n_tiles;
+  int num_items;  // work items of a cluster: (pair of M tiles) x (N tile)
 };
 
 template <int BN, int PASSES>
@@ -65,11 +70,12 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
 }
 
 template <int BN, int PASSES, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   using Cfg = GemmCfg<BN, PASSES>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int HALF_B_BYTES = Cfg::B_BYTES / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
@@ -77,16 +83,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto sB = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * (PASSES == 3 ? 2 : 1); };
   auto sBlo = [&](int s) { return sB(s) + Cfg::B_BYTES; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = bars;                  // TMA bytes landed
+  uint64_t* full = bars;                  // TMA bytes landed (own A + both halves of B)
   uint64_t* split = bars + STAGES;        // A tile split into hi/lo (3xTF32)
-  uint64_t* empty = bars + 2 * STAGES;    // MMAs reading the stage retired
+  uint64_t* empty = bars + 2 * STAGES;    // MMAs of BOTH CTAs reading the stage retired
   uint64_t* tfull = bars + 3 * STAGES;    // accumulator complete
   uint64_t* tempty = tfull + 2;           // accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
   const int num_k_blocks = (p.K + BK - 1) / BK;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -97,33 +104,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&split[s], 4);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);  // one tcgen05.commit from each CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (N tile, pair of M tiles); this CTA takes M tile 2*pair + rank (possibly past the end: TMA zero-fills,
+  // the epilogue skips the rows, and the CTA still loads and multicasts its half of B for its peer)
+  auto item_m0 = [&](int item) { return ((item / p.num_n_tiles) * 2 + (int)rank) * BM; };
+  auto item_n0 = [&](int item) { return (item % p.num_n_tiles) * BN; };
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const int m0 = item_m0(item), n0 = item_n0(item);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES * (PASSES == 3 ? 2 : 1));
           tma_load_2d(sA(s), &tmA, kb * BK, m0, &full[s]);
-          tma_load_2d(sB(s), &tmB, kb * BK, n0, &full[s]);
-          if (PASSES == 3) tma_load_2d(sBlo(s), &tmBlo, kb * BK, n0, &full[s]);
+          tma_load_2d_mc(sB(s) + rank * HALF_B_BYTES, &tmB, kb * BK, n0 + (int)rank * (BN / 2), &full[s], (uint16_t)3);
+          if (PASSES == 3)
+            tma_load_2d_mc(sBlo(s) + rank * HALF_B_BYTES, &tmBlo, kb * BK, n0 + (int)rank * (BN / 2), &full[s], (uint16_t)3);
           if (++s == STAGES) s = 0, ph ^= 1;
         }
       }
@@ -135,7 +149,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
         const int a = local & 1;
         const uint32_t aph = (local >> 1) & 1;
         mbar_wait(&tempty[a], aph ^ 1);
@@ -164,54 +178,62 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mma_tf32_ss(d_tmem, da, db, idesc, acc);
             }
           }
-          mma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+          // the stage may be refilled (by either CTA's multicast) only when both CTAs are done reading it
+          mma_commit_mc(&empty[s], (uint16_t)3);
           if (++s == STAGES) s = 0, ph ^= 1;
         }
         mma_commit(&tfull[a]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================================== epilogue ==========================================
-    const int ew = warp - 4;  // TMEM lane quarter this warp may access (warp id % 4)
+    const int ew = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;   // which half of the tile's columns
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
       const int a = local & 1;
       const uint32_t aph = (local >> 1) & 1;
-      const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      const int m0 = item_m0(item), n0 = item_n0(item);
       const int row = m0 + ew * 32 + lane;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
         const int col0 = n0 + c0;
-        if (row < p.M && col0 < p.N) {
+        const bool live = row < p.M && col0 < p.N;
+        // operands of the epilogue arithmetic are fetched while the TMEM load is in flight
+        float4 e[8];
+        if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            e[q] = (p.bias && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * q))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const float* arow = (p.aux && live) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            e[q] = (arow && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(arow + 4 * q))
+                                                : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        tmem_ld_wait();
+        if (live) {
           float* orow = p.out + (int64_t)row * p.ldo + col0;
-          const float* arow = (EPI == EPI_ACT_GRAD && p.aux) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {  // N is a multiple of 4 (checked on the host)
-              float v[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) v[q] = __uint_as_float(r[j + q]);
+          for (int q = 0; q < 8; ++q) {
+            if (col0 + 4 * q < p.N) {  // N is a multiple of 4 (checked on the host)
+              float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                     __uint_as_float(r[4 * q + 3]));
               if (EPI == EPI_BIAS_ACT) {
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                  v[0] += b.x, v[1] += b.y, v[2] += b.z, v[3] += b.w;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = act_fwd(v[q], p.act);
-              } else if (arow) {
-                const float4 y = __ldg(reinterpret_cast<const float4*>(arow + j));
-                v[0] *= act_grad_from_output(y.x, p.act);
-                v[1] *= act_grad_from_output(y.y, p.act);
-                v[2] *= act_grad_from_output(y.z, p.act);
-                v[3] *= act_grad_from_output(y.w, p.act);
+                v.x = act_fwd(v.x + e[q].x, p.act), v.y = act_fwd(v.y + e[q].y, p.act);
+                v.z = act_fwd(v.z + e[q].z, p.act), v.w = act_fwd(v.w + e[q].w, p.act);
+              } else if (p.aux) {
+                v.x *= act_grad_from_output(e[q].x, p.act), v.y *= act_grad_from_output(e[q].y, p.act);
+                v.z *= act_grad_from_output(e[q].z, p.act), v.w *= act_grad_from_output(e[q].w, p.act);
               }
-              *reinterpret_cast<float4*>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(orow + 4 * q) = v;
             }
           }
         }
@@ -220,12 +242,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
     }
-  } else if (PASSES == 3 && warp >= 8) {
+  } else if (PASSES == 3 && warp >= 12) {
     // ===================================== splitter (3xTF32) =================================
-    const int t = threadIdx.x - 256;  // 0..127
+    const int t = threadIdx.x - 384;  // 0..127
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&full[s], ph);
         uint4* hi = reinterpret_cast<uint4*>(sA(s));
@@ -250,6 +272,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();  // do not exit while the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -332,9 +355,9 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     }
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, p);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = p.num_items < max_clusters ? p.num_items : max_clusters;
+  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, p);  // cluster dims (2,1,1) are compiled in
   return check_launch("gemm_tf32_kernel");
 }
 
@@ -356,13 +379,15 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
   const int bn = N > 128 ? 256 : 128;
   CUtensorMap tA, tB, tBlo;
   if (int e = encode_tmap_2d_f32(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return e;
-  if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn)) return e;
-  if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn)) return e;
+  // each CTA of a cluster loads (and multicasts) one half of the B tile: box = bn/2 rows
+  if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
+  if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
   GemmParams p{};
   p.out = out, p.ldo = ldo, p.bias = bias, p.aux = aux, p.ldaux = ldaux;
   p.M = (int)M, p.N = (int)N, p.K = (int)K, p.act = act;
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = (int)((N + bn - 1) / bn);
+  p.num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
 #define CUSRL_GEMM_CASE(BN_, P_, E_) \
   if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, p, s);
