@@ -14,13 +14,20 @@
 //   warp 1       MMA issuer    : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
 //   warp 2       TMEM allocator
 //   warps 4-11   epilogue      : tcgen05.ld -> registers -> bias/activation -> 128-bit global stores
-//   warps 12-15  splitter (3xTF32 only): rewrites the A tile in place as hi = A & ~0x1fff and writes lo = A - hi
+//   warps 12-15  splitter (3xTF32 only): writes lo = A - trunc_tf32(A) next to the A tile (A itself is untouched)
 // Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Precision.  The reference computes these layers with fp32 SGEMM.  PASSES = 3 is the error-compensated
 // "3xTF32" scheme: x = hi + lo with hi, lo both TF32-representable, D = Ahi*Bhi + Ahi*Blo + Alo*Bhi (fp32
-// accumulate), which restores ~fp32 accuracy at one third of the TF32 tensor rate.  hi parts are masked
-// explicitly so the result does not depend on whether the tensor core truncates or rounds its inputs.
+// accumulate), which restores ~fp32 accuracy at one third of the TF32 tensor rate.  The tensor core truncates its
+// fp32 inputs to TF32 (measured, tools/tf32_rounding_probe.py), so the raw fp32 activation tile IS the hi operand
+// and lo = x - (x & ~0x1fff) is exact; weights are pre-split once per optimizer step.
+//
+// What bounds it (ncu + A/B experiments, round 1): shared-memory bandwidth.  Every tf32 MMA re-reads 4 KB of A and
+// 8 KB of B from shared memory per 128 cycles (96 B/clk) on top of the TMA writes and the splitter traffic;
+// deeper pipelines (16-float k-blocks, 4 stages) and fewer bytes into the SM (in-kernel weight split) did not help,
+// more shared-memory traffic made it proportionally slower.  cta_group::2 (each CTA supplies half of B) is the
+// next step.
 // PASSES = 1 is plain single-pass TF32.
 #include "tc_common.cuh"
 
@@ -157,25 +164,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full[s], ph);
-          if (PASSES == 3) mbar_wait(&split[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
           const uint32_t alo_addr = smem_u32(sAlo(s)), blo_addr = smem_u32(sBlo(s));
+          // The tensor core TRUNCATES fp32 inputs to TF32 (measured: tools/tf32_rounding_probe.py), so the raw fp32 A
+          // tile is the "hi" operand as it lands; the two passes that do not need A_lo are issued immediately and
+          // the splitter is off the critical path.  K-major SWIZZLE_128B operands: 8-row groups are 1024 B apart
+          // (SBO); advancing K by 8 tf32 = +32 B.
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major SWIZZLE_128B operands: 8-row groups are 1024 B apart (SBO); advancing K by 8 tf32 = +32 B
             const uint32_t off = (uint32_t)k * UMMA_K * 4;
             const uint64_t da = make_smem_desc_sw128(a_addr + off, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + off, 16, 1024);
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (PASSES == 3) {
-              const uint64_t dalo = make_smem_desc_sw128(alo_addr + off, 16, 1024);
-              const uint64_t dblo = make_smem_desc_sw128(blo_addr + off, 16, 1024);
-              mma_tf32_ss(d_tmem, dalo, db, idesc, acc);   // small terms first
-              mma_tf32_ss(d_tmem, da, dblo, idesc, 1u);
-              mma_tf32_ss(d_tmem, da, db, idesc, 1u);
-            } else {
-              mma_tf32_ss(d_tmem, da, db, idesc, acc);
+            mma_tf32_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (PASSES == 3) mma_tf32_ss(d_tmem, da, make_smem_desc_sw128(blo_addr + off, 16, 1024), idesc, 1u);
+          }
+          if (PASSES == 3) {
+            mbar_wait(&split[s], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t off = (uint32_t)k * UMMA_K * 4;
+              mma_tf32_ss(d_tmem, make_smem_desc_sw128(alo_addr + off, 16, 1024), make_smem_desc_sw128(b_addr + off, 16, 1024),
+                          idesc, 1u);
             }
           }
           // the stage may be refilled (by either CTA's multicast) only when both CTAs are done reading it
@@ -250,17 +261,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&full[s], ph);
-        uint4* hi = reinterpret_cast<uint4*>(sA(s));
+        const uint4* hi = reinterpret_cast<const uint4*>(sA(s));
         float4* lo = reinterpret_cast<float4*>(sAlo(s));
 #pragma unroll
         for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
           const int idx = t + i * 128;  // elementwise at identical offsets: the swizzled layout is preserved
-          uint4 x = hi[idx];
-          uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
-          float4 l = make_float4(__uint_as_float(x.x) - __uint_as_float(h.x), __uint_as_float(x.y) - __uint_as_float(h.y),
-                                 __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
-          hi[idx] = h;
-          lo[idx] = l;
+          const uint4 x = hi[idx];
+          lo[idx] = make_float4(__uint_as_float(x.x) - __uint_as_float(x.x & 0xffffe000u),
+                                __uint_as_float(x.y) - __uint_as_float(x.y & 0xffffe000u),
+                                __uint_as_float(x.z) - __uint_as_float(x.z & 0xffffe000u),
+                                __uint_as_float(x.w) - __uint_as_float(x.w & 0xffffe000u));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -324,7 +334,7 @@ static EncodeTiledFn get_encoder() {
 }
 
 int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                       uint32_t box_inner, uint32_t box_outer, bool swizzle_32b_atom) {
+                       uint32_t box_inner, uint32_t box_outer, int swizzle) {
   EncodeTiledFn enc = get_encoder();
   CUSRL_REQUIRE(enc != nullptr, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[2] = {inner, outer};
@@ -332,7 +342,9 @@ int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint6
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == TMAP_SW128_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                : (swizzle == TMAP_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CUSRL_REQUIRE(r == CUDA_SUCCESS, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

@@ -47,7 +47,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
   constexpr int CHUNK_BYTES = WG_BKB * 128;  // 4096
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // stage layout: [A hi | B hi | A lo | B lo]  (hi parts are the raw TMA destinations, masked in place for 3x)
+  // stage layout: [A | B | A lo | B lo]  (A, B are the raw TMA destinations = the hi operands: the MMA truncates)
   auto sA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
   auto sB = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
   auto sLo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
@@ -111,25 +111,27 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
-        if (PASSES == 3) mbar_wait(&split[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
         const uint32_t alo_addr = smem_u32(sLo(s)), blo_addr = alo_addr + Cfg::A_BYTES;
+        // hi x hi first (raw fp32 tiles: the tensor core truncates to TF32), the two lo passes once the splitter is done.
+        // One MMA consumes 8 batch rows = two 4-row swizzle atoms (2 x 512 B) of every 32-feature chunk.
 #pragma unroll
         for (int k = 0; k < WG_BKB / 8; ++k) {
-          // one MMA consumes 8 batch rows = two 4-row swizzle atoms (2 x 512 B) of every 32-feature chunk
           const uint32_t off = (uint32_t)k * 1024;
-          const uint64_t da = make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1);
-          const uint64_t db = make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1);
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          if (PASSES == 3) {
-            const uint64_t dalo = make_smem_desc_sw128(alo_addr + off, CHUNK_BYTES, 512, 1);
-            const uint64_t dblo = make_smem_desc_sw128(blo_addr + off, CHUNK_BYTES, 512, 1);
-            mma_tf32_ss(tmem_base, dalo, db, idesc, acc);
-            mma_tf32_ss(tmem_base, da, dblo, idesc, 1u);
-            mma_tf32_ss(tmem_base, da, db, idesc, 1u);
-          } else {
-            mma_tf32_ss(tmem_base, da, db, idesc, acc);
+          mma_tf32_ss(tmem_base, make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1),
+                      make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        if (PASSES == 3) {
+          mbar_wait(&split[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < WG_BKB / 8; ++k) {
+            const uint32_t off = (uint32_t)k * 1024;
+            const uint64_t da = make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1);
+            const uint64_t db = make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1);
+            mma_tf32_ss(tmem_base, make_smem_desc_sw128(alo_addr + off, CHUNK_BYTES, 512, 1), db, idesc, 1u);
+            mma_tf32_ss(tmem_base, da, make_smem_desc_sw128(blo_addr + off, CHUNK_BYTES, 512, 1), idesc, 1u);
           }
         }
         mma_commit(&empty[s]);
@@ -164,22 +166,22 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
     }
     tc_fence_before();
   } else if (PASSES == 3 && warp >= 8) {
-    // splitter: both operand tiles, hi masked in place, lo written to the mirror buffer at identical offsets
+    // splitter: lo = x - trunc_tf32(x) of both operand tiles, written to the mirror buffer at identical offsets
     const int t = threadIdx.x - 256;  // 0..255
     constexpr int VECS = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;
     int s = 0;
     uint32_t ph = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full[s], ph);
-      uint4* hi = reinterpret_cast<uint4*>(sA(s));
+      const uint4* hi = reinterpret_cast<const uint4*>(sA(s));
       float4* lo = reinterpret_cast<float4*>(sLo(s));
 #pragma unroll 4
       for (int idx = t; idx < VECS; idx += 256) {
         const uint4 x = hi[idx];
-        const uint4 h = make_uint4(x.x & 0xffffe000u, x.y & 0xffffe000u, x.z & 0xffffe000u, x.w & 0xffffe000u);
-        hi[idx] = h;
-        lo[idx] = make_float4(__uint_as_float(x.x) - __uint_as_float(h.x), __uint_as_float(x.y) - __uint_as_float(h.y),
-                              __uint_as_float(x.z) - __uint_as_float(h.z), __uint_as_float(x.w) - __uint_as_float(h.w));
+        lo[idx] = make_float4(__uint_as_float(x.x) - __uint_as_float(x.x & 0xffffe000u),
+                              __uint_as_float(x.y) - __uint_as_float(x.y & 0xffffe000u),
+                              __uint_as_float(x.z) - __uint_as_float(x.z & 0xffffe000u),
+                              __uint_as_float(x.w) - __uint_as_float(x.w & 0xffffe000u));
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -235,13 +237,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     __syncthreads();
   }
 }
+// one warp per output column: lanes stride over the block partials (fixed order -> deterministic)
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ db,
                                     int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= N) return;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * N + c];
-  db[c] = accumulate ? db[c] + (float)acc : (float)acc;
+  for (int b = lane; b < nblocks; b += 32) acc += partial[(int64_t)b * N + c];
+  acc = warp_sum(acc);
+  if (lane == 0) db[c] = accumulate ? db[c] + (float)acc : (float)acc;
 }
 
 template <int BN, int PASSES>
@@ -310,8 +314,8 @@ int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, 
   int64_t ldp;
   wgrad_plan(M, N, K, &bn, &mt, &nt, &splits, &rps, &ldp);
   CUtensorMap tDZ, tX;
-  if (int e = encode_tmap_2d_f32(&tDZ, dZ, (uint64_t)N, (uint64_t)M, (uint64_t)lddz, WG_CHUNK, WG_BKB, true)) return e;
-  if (int e = encode_tmap_2d_f32(&tX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, WG_CHUNK, WG_BKB, true)) return e;
+  if (int e = encode_tmap_2d_f32(&tDZ, dZ, (uint64_t)N, (uint64_t)M, (uint64_t)lddz, WG_CHUNK, WG_BKB, TMAP_SW128_ATOM32)) return e;
+  if (int e = encode_tmap_2d_f32(&tX, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx, WG_CHUNK, WG_BKB, TMAP_SW128_ATOM32)) return e;
   WgradParams p{};
   p.partial = (float*)workspace, p.ldp = ldp, p.M = (int)M, p.N = (int)N, p.K = (int)K;
   p.num_m_tiles = mt, p.num_n_tiles = nt, p.splits = splits, p.rows_per_split = rps;
@@ -334,7 +338,7 @@ int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, 
     nb = (int)((M + rows_per_block - 1) / rows_per_block);
     colsum_partial_kernel<<<nb, 256, 0, s>>>(dZ, lddz, (int)M, (int)N, rows_per_block, cs);
     if (int e3 = check_launch("colsum_partial_kernel")) return e3;
-    colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(cs, nb, (int)N, db, accumulate);
+    colsum_final_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s>>>(cs, nb, (int)N, db, accumulate);
     if (int e4 = check_launch("colsum_final_kernel")) return e4;
   }
   return 0;

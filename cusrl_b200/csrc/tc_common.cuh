@@ -134,7 +134,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 format, cf. cute::UMMA::SmemDescriptor): start address, leading /
 // stride byte offsets (all >> 4), version = 1, layout type 2 = SWIZZLE_128B.
-// layout_type: 2 = SWIZZLE_128B (16-byte chunks, 8-row atoms; K-major operands),
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks, 8-row atoms of 128 B rows; K-major operands, 32 tf32 per row),
+//              4 = SWIZZLE_64B  (16-byte chunks, 8-row atoms of 64 B rows; K-major operands, 16 tf32 per row),
 //              1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atoms; the only layout for MN-major tf32 operands).
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                          uint32_t layout_type = 2) {
@@ -157,9 +158,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 #endif  // __CUDACC__
 
 // ---- host: TMA descriptor encoding through the driver entry point (no link-time libcuda dependency) ----
-// swizzle_32b_atom = false: CU_TENSOR_MAP_SWIZZLE_128B; true: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+enum TmapSwizzle { TMAP_SW128 = 0, TMAP_SW128_ATOM32 = 1, TMAP_SW64 = 2 };
 int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                       uint32_t box_inner, uint32_t box_outer, bool swizzle_32b_atom = false);
+                       uint32_t box_inner, uint32_t box_outer, int swizzle = TMAP_SW128);
 
 }  // namespace tc
 }  // namespace cusrl_b200
