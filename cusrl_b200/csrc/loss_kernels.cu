@@ -412,3 +412,111 @@ int cusrl_b200_policy_stats_f32(const float* mean_old, const float* std_old, con
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// K5: Random Network Distillation arithmetic (hook/auxiliary/rnd.py:68-81).  The two small MLPs run on the K6 GEMMs;
+// these kernels fuse everything after them.
+// ================================================================================================
+namespace cusrl_b200 {
+
+// rnd_reward[m] = scale * mean_d (target[m,d] - pred[m,d])^2 ;  reward[m, 0..Dr) += rnd_reward[m]   (rnd.py:72-74)
+__global__ void __launch_bounds__(256) rnd_reward_kernel(const float* __restrict__ target, const float* __restrict__ pred,
+                                                         int64_t M, int D, float scale, float* __restrict__ reward, int Dr,
+                                                         float* __restrict__ rnd_reward, double* __restrict__ partials) {
+  __shared__ double smem[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += stride) {
+    float s = 0.f;
+    if ((D & 3) == 0) {
+      for (int d = 0; d < D; d += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(target + m * D + d));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pred + m * D + d));
+        const float a = t.x - q.x, b = t.y - q.y, c = t.z - q.z, e = t.w - q.w;
+        s += (a * a + b * b) + (c * c + e * e);
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const float a = target[m * D + d] - pred[m * D + d];
+        s += a * a;
+      }
+    }
+    const float r = scale * (s / (float)D);
+    if (rnd_reward) rnd_reward[m] = r;
+    for (int k = 0; k < Dr; ++k) reward[m * Dr + k] += r;  // broadcast add over the reward dim (torch add_ broadcasting)
+    acc += r;
+  }
+  double v[1] = {(double)acc};
+  block_sum<1>(v, smem);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+}
+
+// loss = mean over M*D of (pred - target)^2 ;  d_pred = 2 (pred - target) / (M*D)     (nn.MSELoss, rnd.py:80)
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n,
+                                                  float inv_n, float* __restrict__ d_pred, double* __restrict__ partials) {
+  __shared__ double smem[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float e = pred[i] - target[i];
+    acc += e * e;
+    if (d_pred) d_pred[i] = 2.f * e * inv_n;
+  }
+  double v[1] = {(double)acc};
+  block_sum<1>(v, smem);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double scale, float* __restrict__ out) {
+  __shared__ double smem[32];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += partials[i];
+  block_sum<1>(v, smem);
+  if (threadIdx.x == 0) *out = (float)(v[0] * scale);
+}
+
+}  // namespace cusrl_b200
+
+extern "C" {
+
+size_t cusrl_b200_rnd_scratch_bytes(void) { return (size_t)kLossMaxBlocks * sizeof(double); }
+
+int cusrl_b200_rnd_reward_f32(const float* target, const float* pred, int64_t M, int64_t D, float reward_scale, float* reward,
+                              int64_t Dr, float* rnd_reward, float* mean_out, void* scratch, size_t scratch_bytes, void* stream) {
+  CUSRL_REQUIRE(target && pred && reward && scratch, CUSRL_B200_EINVAL, "rnd_reward: null pointer");
+  CUSRL_REQUIRE(M > 0 && D > 0 && Dr > 0, CUSRL_B200_EINVAL, "rnd_reward: M, D, Dr must be positive");
+  CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_rnd_scratch_bytes(), CUSRL_B200_ESCRATCH, "rnd_reward: scratch too small");
+  CUSRL_REQUIRE((D & 3) || (aligned_to(target, 16) && aligned_to(pred, 16)), CUSRL_B200_EALIGN, "rnd_reward: alignment");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t blocks = (M + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kLossMaxBlocks) cap = kLossMaxBlocks;
+  if (blocks > cap) blocks = cap;
+  rnd_reward_kernel<<<(unsigned)blocks, 256, 0, s>>>(target, pred, M, (int)D, reward_scale, reward, (int)Dr, rnd_reward,
+                                                     (double*)scratch);
+  if (int e = check_launch("rnd_reward_kernel")) return e;
+  if (mean_out) {
+    sum_partials_kernel<<<1, 256, 0, s>>>((const double*)scratch, (int)blocks, 1.0 / (double)M, mean_out);
+    return check_launch("sum_partials_kernel");
+  }
+  return 0;
+}
+
+int cusrl_b200_mse_f32(const float* pred, const float* target, int64_t M, int64_t D, float* loss, float* d_pred, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+  CUSRL_REQUIRE(pred && target && loss && scratch, CUSRL_B200_EINVAL, "mse: null pointer");
+  CUSRL_REQUIRE(M > 0 && D > 0, CUSRL_B200_EINVAL, "mse: M, D must be positive");
+  CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_rnd_scratch_bytes(), CUSRL_B200_ESCRATCH, "mse: scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = M * D;
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kLossMaxBlocks) cap = kLossMaxBlocks;
+  if (blocks > cap) blocks = cap;
+  mse_kernel<<<(unsigned)blocks, 256, 0, s>>>(pred, target, n, 1.f / (float)n, d_pred, (double*)scratch);
+  if (int e = check_launch("mse_kernel")) return e;
+  sum_partials_kernel<<<1, 256, 0, s>>>((const double*)scratch, (int)blocks, 1.0 / (double)n, loss);
+  return check_launch("sum_partials_kernel");
+}
+
+}  // extern "C"

@@ -1,3 +1,4 @@
+from .auxiliary import RandomNetworkDistillation
 from .on_policy import (
     AdaptiveLRSchedule,
     AdvantageNormalization,
@@ -22,6 +23,7 @@ __all__ = [
     "OnPolicyPreparation",
     "OnPolicyStatistics",
     "PpoSurrogateLoss",
+    "RandomNetworkDistillation",
     "ValueComputation",
     "ValueLoss",
 ]

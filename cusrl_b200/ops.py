@@ -511,3 +511,36 @@ def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: t
         M, K, No, int(accumulate), scratch.data_ptr(), scratch.numel(), _stream())
     _lib.check(code, "head_bwd", launches=2)
     return dh
+
+
+# ---------------------------------------------------------------------------------------------- K5
+def rnd_reward_(target: torch.Tensor, pred: torch.Tensor, reward: torch.Tensor, reward_scale: float
+                ) -> tuple[torch.Tensor, torch.Tensor]:
+    """reward += scale * mean_d (target - pred)^2 (in place); returns (rnd_reward [.., 1], its mean) (rnd.py:68-75)."""
+    D = target.shape[-1]
+    M = target.numel() // D
+    Dr = reward.shape[-1]
+    lib = _lib.load()
+    scratch = _get_scratch(target.device, "rnd", lib.cusrl_b200_rnd_scratch_bytes())
+    rnd = torch.empty(*target.shape[:-1], 1, device=target.device)
+    mean = torch.empty(1, device=target.device)
+    code = lib.cusrl_b200_rnd_reward_f32(_ptr(target, torch.float32, "target"), _ptr(pred, torch.float32, "prediction"), M, D,
+                                         float(reward_scale), _ptr(reward, torch.float32, "reward"), Dr, rnd.data_ptr(),
+                                         mean.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream())
+    _lib.check(code, "rnd_reward", launches=2)
+    return rnd, mean
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """(mean squared error [1], d loss / d pred) in one pass (nn.MSELoss forward + backward)."""
+    D = pred.shape[-1]
+    M = pred.numel() // D
+    lib = _lib.load()
+    scratch = _get_scratch(pred.device, "rnd", lib.cusrl_b200_rnd_scratch_bytes())
+    loss = torch.empty(1, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    code = lib.cusrl_b200_mse_f32(_ptr(pred, torch.float32, "prediction"), _ptr(target, torch.float32, "target"), M, D,
+                                  loss.data_ptr(), None if grad is None else grad.data_ptr(), scratch.data_ptr(),
+                                  scratch.numel(), _stream())
+    _lib.check(code, "mse", launches=2)
+    return loss, grad

@@ -216,6 +216,20 @@ int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const 
                             int64_t lddh, float* dW, float* db, int64_t M, int64_t K, int64_t No,
                             int accumulate, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K5  Random Network Distillation arithmetic -- replaces the tensor code of RandomNetworkDistillation
+ *     (hook/auxiliary/rnd.py:68-81); the two small MLPs run on the K6 dense-layer kernels.
+ *   rnd_reward: r[m] = reward_scale * mean_d (target[m,d] - pred[m,d])^2;  reward[m, 0..Dr) += r[m]
+ *               (rnd.py:72-74); rnd_reward [M] and mean_out (mean of r, the recorded metric) optional.
+ *   mse:        loss = mean_{M*D} (pred - target)^2 (nn.MSELoss, rnd.py:80); d_pred = dloss/dpred (optional).
+ *   scratch: cusrl_b200_rnd_scratch_bytes() bytes, 8-byte aligned. */
+size_t cusrl_b200_rnd_scratch_bytes(void);
+int cusrl_b200_rnd_reward_f32(const float* target, const float* pred, int64_t M, int64_t D, float reward_scale,
+                              float* reward, int64_t Dr, float* rnd_reward, float* mean_out, void* scratch,
+                              size_t scratch_bytes, void* stream);
+int cusrl_b200_mse_f32(const float* pred, const float* target, int64_t M, int64_t D, float* loss, float* d_pred,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

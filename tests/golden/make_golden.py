@@ -283,7 +283,38 @@ def make_iteration():
     save("iteration", **out)
 
 
+def make_rnd():
+    """RandomNetworkDistillation.pre_update / objective of the reference (hook/auxiliary/rnd.py:68-81)."""
+    from cusrl.hook.auxiliary.rnd import RandomNetworkDistillation
+
+    torch.manual_seed(21)
+    T, N, D = 6, 16, 19
+    hook = RandomNetworkDistillation(cusrl.Mlp.Factory([64, 64]), output_dim=16, reward_scale=0.1)
+    recorded = {}
+    hook.agent = SimpleNamespace(state_dim=D, setup_module=lambda m: m, record=lambda **kw: recorded.update(kw))
+    hook.init()
+    g = torch.Generator().manual_seed(22)
+    buffer = Buffer(T, N, device="cpu")
+    buffer["next_observation"] = torch.randn(T, N, D, generator=g)
+    reward0 = torch.randn(T, N, 1, generator=g)
+    buffer["reward"] = reward0.clone()
+    hook.pre_update(buffer)
+    out = {"next_observation": buffer["next_observation"], "reward_before": reward0, "reward_after": buffer["reward"],
+           "rnd_reward": recorded["rnd_reward"]}
+    for net in ("target", "predictor"):
+        for k, v in getattr(hook, net).state_dict().items():
+            out[f"{net}/{k}"] = v
+    batch = {"next_observation": buffer["next_observation"].flatten(0, 1)[:40]}
+    loss = hook.objective({}, batch)["rnd_loss"]
+    loss.backward()
+    out["rnd_loss"] = loss
+    for k, p in hook.predictor.named_parameters():
+        out[f"grad/{k}"] = p.grad
+    save("rnd", **out)
+
+
 if __name__ == "__main__":
+    make_rnd()
     make_gae()
     make_advnorm()
     make_next_value()
