@@ -7,8 +7,8 @@ library of hand-written CUDA kernels (``include/cusrl_b200.h``).  See DESIGN.md 
 from . import distributed, hook, nn, ops, preset
 from .environment import EnvironmentSpec, SyntheticEnvironment
 from .hook import *  # noqa: F401,F403
-from .nn import Actor, Mlp, NormalDist, Value
-from .preset import PpoAgentFactory, anymal_c_rough_ppo, ppo_hook_suite
+from .nn import Actor, Mlp, NormalDist, Rnn, Value
+from .preset import PpoAgentFactory, RecurrentPpoAgentFactory, anymal_c_rough_ppo, ppo_hook_suite
 from .runtime import CONFIG, device
 from .sampler import AutoMiniBatchSampler, MiniBatchSampler, TemporalMiniBatchSampler
 from .template import ActorCritic, ActorCriticFactory, AdamFactory, Buffer, FlatAdam, Hook, HookComposite, HookList, Sampler

@@ -61,6 +61,8 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_rnd_scratch_bytes": (c_size_t, []),
     "cusrl_b200_rnd_reward_f32": (c_int, [P, P, c_int64, c_int64, c_float, P, c_int64, P, P, P, c_size_t, P]),
     "cusrl_b200_mse_f32": (c_int, [P, P, c_int64, c_int64, P, P, P, c_size_t, P]),
+    "cusrl_b200_lstm_cell_fwd_f32": (c_int, [P, c_int64, P, P, P, P, P, P, P, P, c_int64, c_int64, P]),
+    "cusrl_b200_lstm_cell_bwd_f32": (c_int, [P, c_int64, P, P, P, P, P, P, P, P, c_int64, c_int64, P]),
     "cusrl_b200_grad_sumsq_f32": (c_int, [P, c_int64, P, P]),
     "cusrl_b200_clip_coef_f32": (c_int, [P, c_float, P, P, P]),
     "cusrl_b200_adam_step_f32": (c_int, [P, P, P, P, c_int64, P] + [c_float] * 5 + [c_int64, P]),

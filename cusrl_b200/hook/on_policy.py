@@ -127,7 +127,13 @@ class ValueComputation(Hook):
         if self.bootstrap_truncated_states:
             # value.py:74-80 evaluates the critic on next_state[truncated] (data-dependent size -> host sync);
             # evaluating every next state keeps the stream free of syncs and selects the same entries in-kernel
-            trunc_value = critic.evaluate(next_state, memory=buffer.get("next_critic_memory")).contiguous()
+            next_memory = buffer.get("next_critic_memory")
+            if next_memory is not None:  # recurrent critic: every (t, n) is an independent single step with its own memory
+                flat_mem = {k: v.flatten(0, 1) for k, v in next_memory.items()}
+                trunc_value = critic.evaluate(next_state.flatten(0, 1), memory=flat_mem).reshape(*next_state.shape[:2], -1)
+            else:
+                trunc_value = critic.evaluate(next_state)
+            trunc_value = trunc_value.contiguous()
         ops.next_value(value, buffer["terminated"], buffer["truncated"], boot.contiguous(), self.termination_value,
                        trunc_value=trunc_value, out=next_value)
 

@@ -19,7 +19,7 @@ import torch
 
 from .. import ops
 
-__all__ = ["ACTIVATIONS", "mlp_forward", "mlp_head_forward"]
+__all__ = ["ACTIVATIONS", "linear_head", "mlp_forward", "mlp_head_forward"]
 
 ACTIVATIONS = {"Identity": 0, "ELU": 1, "ReLU": 2}
 
@@ -41,9 +41,11 @@ def _rows_ok(x: torch.Tensor) -> torch.Tensor:
     return padded[:, :width]
 
 
-def _wgrad(dz, inp, weight, bias, grads, slot):
-    """Weight / bias gradient of one layer: accumulate into the flat arena when the parameter has one."""
+def _wgrad(dz, inp, weight, bias, grads, slot, bias_slot=None):
+    """Weight / bias gradient of one layer: accumulate into the flat arena when the parameter has one, otherwise hand
+    fresh tensors to autograd through ``grads[slot]`` / ``grads[bias_slot]`` (default: the adjacent slot)."""
     precision = ops.GEMM_PRECISION
+    bias_slot = slot + 1 if bias_slot is None else bias_slot
     w_grad, b_grad = weight.grad, (bias.grad if bias is not None else None)
     if w_grad is not None and (bias is None or b_grad is not None) and w_grad.is_contiguous():
         ops.tc_linear_wgrad(dz, inp, w_grad, b_grad, precision, accumulate=True)
@@ -51,7 +53,7 @@ def _wgrad(dz, inp, weight, bias, grads, slot):
         dw = torch.empty_like(weight)
         db = torch.empty_like(bias) if bias is not None else None
         ops.tc_linear_wgrad(dz, inp, dw, db, precision, accumulate=False)
-        grads[slot], grads[slot + 1] = dw, db
+        grads[slot], grads[bias_slot] = dw, db
 
 
 class _MlpHeadFunction(torch.autograd.Function):
@@ -131,3 +133,50 @@ def mlp_head_forward(x: torch.Tensor, weights, biases, activation: str, head_wei
     params = [t for pair in zip(weights, biases) for t in pair] + [head_weight, head_bias]
     out, latent = _MlpHeadFunction.apply(x2, _act_code(activation), True, True, *params)
     return out.reshape(*lead, out.shape[-1]), latent.reshape(*lead, latent.shape[-1])
+
+
+_SIMT_HEADS = {(no, 1) for no in range(1, 17)} | {(no, 2) for no in (1, 2, 4, 6, 8)}
+
+
+class _HeadFunction(torch.autograd.Function):
+    """y = x W^T + b for an output head fed by a non-MLP backbone (e.g. the LSTM): the fp32 SIMT head when its shape is
+    instantiated (csrc/head_kernels.cu), otherwise the tcgen05 dense-layer kernels (needs out_features % 4 == 0)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _rows_ok(x)
+        No, K = weight.shape
+        simt = K % 128 == 0 and (No, K // 128) in _SIMT_HEADS
+        if simt:
+            y = ops.head_fwd(x, weight, bias)
+        else:
+            y = ops.tc_linear_fwd(x, ops.prepared_weight(weight), bias, No, 0, ops.GEMM_PRECISION)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.simt = simt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        grads: list[torch.Tensor | None] = [None, None]
+        need_dx = ctx.needs_input_grad[0]
+        if ctx.simt:
+            w_grad, b_grad = weight.grad, (bias.grad if bias is not None else None)
+            arena = w_grad is not None and (bias is None or b_grad is not None)
+            dw = w_grad if arena else torch.empty_like(weight)
+            db = b_grad if arena else (torch.empty_like(bias) if bias is not None else None)
+            dx = ops.head_bwd(dy, x, weight, 0, dw, db, need_dh=need_dx, accumulate=arena)
+            if not arena:
+                grads = [dw, db]
+        else:
+            _wgrad(dy, x, weight, bias, grads, 0)
+            dx = ops.tc_linear_dgrad(dy, ops.prepared_weight(weight), None, weight.shape[1], 0, ops.GEMM_PRECISION) if need_dx else None
+        return dx, grads[0], grads[1]
+
+
+def linear_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """Output head on arbitrary leading dims (mean_head / value_head behind a recurrent backbone)."""
+    x2, lead = _flatten(x)
+    y = _HeadFunction.apply(x2, weight, bias)
+    return y.reshape(*lead, y.shape[-1])

@@ -192,7 +192,10 @@ class Actor(Module):
         """backbone + mean head as ONE autograd node (trunk GEMMs on tcgen05, fp32 SIMT head)."""
         head = self.distribution.mean_head
         if self.backbone.is_recurrent:
-            raise NotImplementedError("recurrent backbones are handled by cusrl_b200.nn.recurrent")
+            # LSTM backbone (K7) + head; rollout calls are single-step (the reference passes sequential=False there)
+            latent, memory = self.backbone(observation, memory, done=done, sequential=observation.dim() >= 3)
+            self.intermediate_repr["backbone.output"] = latent
+            return F.linear_head(latent, head.weight, head.bias), memory
         lins = self.backbone.linears()
         if not self.backbone.ends_with_activation:
             raise ValueError("Actor expects an activation-terminated Mlp backbone (reference preset/ppo.py:137-140)")
@@ -257,7 +260,9 @@ class Value(Module):
 
     def forward(self, state: Tensor, *, memory=None, done: Tensor | None = None, **kw):
         if self.backbone.is_recurrent:
-            raise NotImplementedError("recurrent backbones are handled by cusrl_b200.nn.recurrent")
+            latent, memory = self.backbone(state, memory, done=done, sequential=state.dim() >= 3)
+            self.intermediate_repr["backbone.output"] = latent
+            return F.linear_head(latent, self.value_head.weight, self.value_head.bias), memory
         lins = self.backbone.linears()
         if not self.backbone.ends_with_activation:
             raise ValueError("Value expects an activation-terminated Mlp backbone (reference preset/ppo.py:143-147)")

@@ -544,3 +544,29 @@ def mse_loss(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True) -
                                   scratch.numel(), _stream())
     _lib.check(code, "mse", launches=2)
     return loss, grad
+
+
+# ---------------------------------------------------------------------------------------------- K7
+def lstm_cell_fwd(xp: torch.Tensor, hp: torch.Tensor, c_in: torch.Tensor, done: torch.Tensor | None, gates: torch.Tensor,
+                  c_out: torch.Tensor, h_out: torch.Tensor, c_next: torch.Tensor | None, h_next: torch.Tensor | None) -> None:
+    """One LSTM step for all rows (cusrl_b200_lstm_cell_fwd_f32); xp may be a row-strided slice."""
+    Nb, H = c_in.shape
+    xpp, ldxp = _rows(xp, "xp")
+    code = _lib.load().cusrl_b200_lstm_cell_fwd_f32(
+        xpp, ldxp, _ptr(hp, torch.float32, "hp"), _ptr(c_in, torch.float32, "c_in"), None if done is None else _flag_ptr(done, "done"),
+        _ptr(gates, torch.float32, "gates"), _ptr(c_out, torch.float32, "c_out"), _ptr(h_out, torch.float32, "h_out"),
+        _ptr(c_next, torch.float32, "c_next"), _ptr(h_next, torch.float32, "h_next"), Nb, H, _stream())
+    _lib.check(code, "lstm_cell_fwd")
+
+
+def lstm_cell_bwd(dh_above: torch.Tensor, dh_rec: torch.Tensor | None, dc_rec: torch.Tensor | None, done: torch.Tensor | None,
+                  gates: torch.Tensor, c: torch.Tensor, c_in: torch.Tensor, dgates: torch.Tensor, dc_prev: torch.Tensor) -> None:
+    """BPTT of one LSTM step (cusrl_b200_lstm_cell_bwd_f32)."""
+    Nb, H = c.shape
+    dhp, lddh = _rows(dh_above, "dh_above")
+    code = _lib.load().cusrl_b200_lstm_cell_bwd_f32(
+        dhp, lddh, _ptr(dh_rec, torch.float32, "dh_rec"), _ptr(dc_rec, torch.float32, "dc_rec"),
+        None if done is None else _flag_ptr(done, "done"), _ptr(gates, torch.float32, "gates"), _ptr(c, torch.float32, "c"),
+        _ptr(c_in, torch.float32, "c_in"), _ptr(dgates, torch.float32, "dgates"), _ptr(dc_prev, torch.float32, "dc_prev"),
+        Nb, H, _stream())
+    _lib.check(code, "lstm_cell_bwd")

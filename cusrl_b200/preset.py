@@ -9,14 +9,18 @@ from dataclasses import dataclass, field
 import torch
 
 from . import hook as H
-from .nn import Actor, Mlp, NormalDist, Value
+from .nn import Actor, Mlp, NormalDist, Rnn, Value
 from .sampler import AutoMiniBatchSampler
 from .template import ActorCritic, ActorCriticFactory, AdamFactory
 
-__all__ = ["PpoAgentFactory", "anymal_c_rough_ppo", "ppo_hook_suite", "PPO_MINIBATCH_FIELDS"]
+__all__ = ["PpoAgentFactory", "RecurrentPpoAgentFactory", "anymal_c_rough_ppo", "ppo_hook_suite", "PPO_MINIBATCH_FIELDS",
+           "RECURRENT_PPO_MINIBATCH_FIELDS"]
 
 # leaves the PPO objective consumes: everything else in the buffer is not gathered
 PPO_MINIBATCH_FIELDS = ("observation", "state", "action", "action_logp", "advantage", "return", "value", "done")
+
+
+RECURRENT_PPO_MINIBATCH_FIELDS = PPO_MINIBATCH_FIELDS + ("actor_memory", "critic_memory")
 
 
 def ppo_hook_suite(
@@ -118,3 +122,25 @@ def anymal_c_rough_ppo(**overrides) -> PpoAgentFactory:
                   entropy_loss_weight=0.005, desired_kl_divergence=0.015)
     kwargs.update(overrides)
     return PpoAgentFactory(**kwargs)
+
+
+@dataclass(kw_only=True)
+class RecurrentPpoAgentFactory(PpoAgentFactory):
+    """The reference's ``RecurrentPpoAgentFactory`` (preset/ppo.py:185-298): LSTM 2 x 256 actor and critic."""
+
+    rnn_type: str = "LSTM"
+    actor_num_layers: int = 2
+    actor_hidden_size: int = 256
+    critic_num_layers: int = 2
+    critic_hidden_size: int = 256
+
+    def to_underlying(self) -> ActorCriticFactory:
+        base = super().to_underlying()
+        base.actor_factory = Actor.Factory(
+            backbone_factory=Rnn.Factory(self.rnn_type, num_layers=self.actor_num_layers, hidden_size=self.actor_hidden_size),
+            distribution_factory=NormalDist.Factory(init_std=self.init_distribution_std))
+        base.critic_factory = Value.Factory(
+            backbone_factory=Rnn.Factory(self.rnn_type, num_layers=self.critic_num_layers, hidden_size=self.critic_hidden_size))
+        base.sampler = AutoMiniBatchSampler(num_epochs=self.sampler_epochs, num_mini_batches=self.sampler_mini_batches,
+                                            fields=RECURRENT_PPO_MINIBATCH_FIELDS, memory_first_step_only=True)
+        return base

@@ -26,6 +26,7 @@ class MiniBatchSampler(Sampler):
     """Shuffled minibatches of individual transitions from a full buffer."""
 
     temporal = False
+    memory_first_step_only = False  # temporal sampler: gather only step 0 of `*memory` leaves (a [1, Nmb, .] batch leaf)
 
     def __init__(self, num_epochs: int = 1, num_mini_batches: int | Sequence[int] = 1, shuffle: bool = True,
                  fields: Sequence[str] | None = None):
@@ -99,25 +100,30 @@ class MiniBatchSampler(Sampler):
     def _gather(self, buffer: Buffer, keys: list[str], idx: torch.Tensor) -> dict[str, torch.Tensor]:
         T, N = buffer.capacity, buffer.get_parallelism()
         out: dict[str, torch.Tensor] = {}
-        pairs = []
+        groups: dict[int, tuple[torch.Tensor, list]] = {}
         if self.temporal:
             n_mb = idx.numel()
-            rows = (torch.arange(T, device=idx.device).unsqueeze(1) * N + idx.unsqueeze(0)).reshape(-1)
-            lead: tuple[int, ...] = (T, n_mb)
-        else:
-            rows, lead = idx, (idx.numel(),)
+            all_rows = (torch.arange(T, device=idx.device).unsqueeze(1) * N + idx.unsqueeze(0)).reshape(-1)
         for key in keys:
             leaf = buffer.storage[key]
             back = buffer.backing(key)
+            if not self.temporal:
+                rows, lead = idx, (idx.numel(),)
+            elif self.memory_first_step_only and key.split(".")[0].endswith("memory"):
+                # only step 0 of a stored recurrent memory is ever consumed (reference recurrent.py:202-212)
+                rows, lead = idx, (1, n_mb)
+            else:
+                rows, lead = all_rows, (T, n_mb)
             dst, view = self._dst_for(key, leaf, lead)
             # backing rows are dense [T*N, padded]: pass the padded payload so the row copies are 16-byte vectors
             src2 = back.reshape(T * N, -1)
             dst2 = dst.reshape(rows.numel(), -1)
-            pairs.append((src2 if src2.shape[1] == dst2.shape[1] else src2[:, : min(src2.shape[1], dst2.shape[1])], dst2))
+            pair = (src2 if src2.shape[1] == dst2.shape[1] else src2[:, : min(src2.shape[1], dst2.shape[1])], dst2)
+            groups.setdefault(id(rows), (rows, []))[1].append(pair)
             out[key] = view
-        # at most CUSRL_B200_MAX_GATHER_FIELDS (24) fields per launch
-        for i in range(0, len(pairs), 24):
-            ops.gather_rows(pairs[i : i + 24], rows)
+        for rows, pairs in groups.values():
+            for i in range(0, len(pairs), 24):  # at most CUSRL_B200_MAX_GATHER_FIELDS (24) fields per launch
+                ops.gather_rows(pairs[i : i + 24], rows)
         return out
 
     def __call__(self, buffer: Buffer):
@@ -148,8 +154,9 @@ class AutoMiniBatchSampler(Sampler):
     """Temporal iff any top-level field name ends with ``memory`` (:117-140)."""
 
     def __init__(self, num_epochs: int = 1, num_mini_batches: int | Sequence[int] = 1, shuffle: bool = True,
-                 fields: Sequence[str] | None = None):
+                 fields: Sequence[str] | None = None, memory_first_step_only: bool = False):
         self.num_epochs, self.num_mini_batches, self.shuffle, self.fields = num_epochs, num_mini_batches, shuffle, fields
+        self.memory_first_step_only = memory_first_step_only
         self._impl: MiniBatchSampler | None = None
 
     def _resolve(self, buffer: Buffer) -> MiniBatchSampler:
@@ -157,6 +164,7 @@ class AutoMiniBatchSampler(Sampler):
         cls = TemporalMiniBatchSampler if is_temporal else MiniBatchSampler
         if not isinstance(self._impl, cls) or type(self._impl) is not cls:
             self._impl = cls(self.num_epochs, self.num_mini_batches, self.shuffle, self.fields)
+            self._impl.memory_first_step_only = self.memory_first_step_only
         return self._impl
 
     def indices(self, buffer: Buffer):

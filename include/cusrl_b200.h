@@ -230,6 +230,23 @@ int cusrl_b200_rnd_reward_f32(const float* target, const float* pred, int64_t M,
 int cusrl_b200_mse_f32(const float* pred, const float* target, int64_t M, int64_t D, float* loss, float* d_pred,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K7  LSTM cell arithmetic -- with the K6 GEMMs replaces nn.LSTM forward/backward as used by Rnn._forward_sequence
+ *     (nn/module/rnn.py:62-97,264-299; episode segmentation of nn/utils/recurrent.py:160-272 expressed as an
+ *     in-line reset of the state where done, the equivalence pinned by cusrl_test/nn/module/test_rnn.py:145-164).
+ *   cell_fwd: gates = xp + hp (biases already included), torch gate order (i,f,g,o);
+ *             c_t = f*c_in + i*g; h_t = o*tanh(c_t); gates (activated), c_t, h_t stored;
+ *             c_next/h_next = c_t/h_t * (1 - done)  = the state entering step t+1 (NULL at the last step).
+ *   cell_bwd: dh = dh_above + (1-done)*dh_rec; dc = (1-done)*dc_rec + dh*o*(1-tanh(c_t)^2);
+ *             dgates = pre-activation gate gradients; dc_prev = dc*f (masked by the previous step's done THERE).
+ *   All [Nb, H] / [Nb, 4H] dense except xp (row pitch ldxp) and dh_above (row pitch lddh); H % 4 == 0. */
+int cusrl_b200_lstm_cell_fwd_f32(const float* xp, int64_t ldxp, const float* hp, const float* c_in, const uint8_t* done,
+                                 float* gates, float* c_out, float* h_out, float* c_next, float* h_next, int64_t Nb,
+                                 int64_t H, void* stream);
+int cusrl_b200_lstm_cell_bwd_f32(const float* dh_above, int64_t lddh, const float* dh_rec, const float* dc_rec,
+                                 const uint8_t* done, const float* gates, const float* c, const float* c_in, float* dgates,
+                                 float* dc_prev, int64_t Nb, int64_t H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -313,7 +313,30 @@ def make_rnd():
     save("rnd", **out)
 
 
+def make_lstm():
+    """Reference Rnn (LSTM) forward on a done-segmented sequence + gradients (nn/module/rnn.py:264-299)."""
+    torch.manual_seed(31)
+    T, N, I, H, L = 7, 12, 19, 32, 2
+    rnn = cusrl.Rnn.Factory("LSTM", hidden_size=H, num_layers=L)(I)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(T, N, I, generator=g)
+    done = torch.rand(T, N, 1, generator=g) < 0.2
+    memory = {"hidden": torch.randn(N, L * H, generator=g) * 0.5, "cell": torch.randn(N, L * H, generator=g) * 0.5}
+    out, _ = rnn(x, memory={k: v.clone() for k, v in memory.items()}, done=done)
+    gout = torch.randn(T, N, H, generator=g)
+    (out * gout).sum().backward()
+    res = {"x": x, "done": done, "hidden0": memory["hidden"], "cell0": memory["cell"], "out": out, "gout": gout}
+    for k, p_ in rnn.named_parameters():
+        res[f"param/{k}"] = p_.detach()
+        res[f"grad/{k}"] = p_.grad
+    # single-step (rollout) call without done: returns the next memory
+    step_out, step_mem = rnn(x[0], memory={k: v.clone() for k, v in memory.items()}, sequential=False)
+    res.update(step_out=step_out, step_hidden=step_mem["hidden"], step_cell=step_mem["cell"])
+    save("lstm", **res)
+
+
 if __name__ == "__main__":
+    make_lstm()
     make_rnd()
     make_gae()
     make_advnorm()
