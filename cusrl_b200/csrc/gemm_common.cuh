@@ -1,0 +1,115 @@
+// Shared definitions of the K-major tcgen05 dense-layer kernels (gemm_tf32.cu: 1-SM MMA + TMA multicast;
+// gemm2sm_tf32.cu: cta_group::2 MMA).
+#pragma once
+#include "tc_common.cuh"
+
+namespace cusrl_b200 {
+
+using namespace tc;
+
+constexpr int BM = 128;           // rows per CTA tile (UMMA M)
+constexpr int BK = 32;            // fp32 per k-block = 128 bytes = one SWIZZLE_128B span
+constexpr int UMMA_K = 8;         // tf32 elements per tcgen05.mma
+constexpr int kGemmThreads = 512;
+constexpr int kEpiWarpBytes = 32 * 32 * 4;          // one 32-row x 32-column fp32 chunk per epilogue warp
+constexpr int kEpiStageBytes = 8 * kEpiWarpBytes;    // 8 epilogue warps
+constexpr int kSmemBudget = 192 * 1024;              // pipeline stages (the epilogue staging and barriers come on top)
+
+enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1 };
+
+struct GemmParams {
+  float* out;
+  int64_t ldo;
+  const float* bias;   // EPI_BIAS_ACT (may be null)
+  const float* aux;    // EPI_ACT_GRAD: post-activation output of the layer below (may be null: plain copy)
+  int64_t ldaux;
+  int M, N, K, act;
+  int num_m_tiles, num_n_tiles;
+  int num_items;  // work items of a cluster: (pair of M tiles) x (N tile)
+};
+
+// expm1(z) for z <= 0 in ~11 instructions, both branches evaluated and selected (no divergence): libdevice's expm1f costs
+// ~25 instructions per element and made the 8 epilogue warps the bottleneck of the whole GEMM (measured).
+// |z| < 1/8: degree-6 Taylor polynomial (truncation < 4e-8 relative); otherwise ex2.approx(z log2 e) - 1, whose
+// 2-ulp error in the exponential is < 2.4e-7 absolute on a result of magnitude > 0.117.
+__device__ __forceinline__ float expm1_neg(float z) {
+  float poly = fmaf(z, 1.f / 720.f, 1.f / 120.f);
+  poly = fmaf(poly, z, 1.f / 24.f);
+  poly = fmaf(poly, z, 1.f / 6.f);
+  poly = fmaf(poly, z, 0.5f);
+  poly = fmaf(poly, z, 1.f);
+  poly *= z;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 1.4426950408889634f));
+  const float big = e - 1.f;
+  return z > -0.125f ? poly : big;
+}
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return z > 0.f ? z : expm1_neg(z);  // ELU(alpha=1), torch.nn.functional.elu
+  if (act == 2) return fmaxf(z, 0.f);
+  return z;
+}
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  if (act == 1) return y > 0.f ? 1.f : y + 1.f;  // d/dz ELU(z) = exp(z) = y + 1 for z <= 0
+  if (act == 2) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+
+// One 32-row x 32-column chunk of the epilogue, executed by one warp (lane = accumulator row within the chunk):
+// TMEM -> registers -> bias + activation (forward) or x act'(aux) (data gradient) -> shared-memory staging in the
+// SWIZZLE_128B pattern -> ONE bulk tensor store, which writes full 128-byte lines and clips rows >= M / columns >= N.
+// The bias / aux operands are fetched while the TMEM load is in flight, and the wait for the previous chunk's bulk
+// store (it must have finished READING the staging buffer) comes after the arithmetic, so the two overlap.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const CUtensorMap* tmOut, uint8_t* stg, uint32_t taddr,
+                                               int row0, int col0, int lane) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  float4 e[8];
+  const int row = row0 + lane;
+  if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      e[q] = (p.bias && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * q))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    // row-per-lane 16-byte loads: the 8 loads of a lane cover one 128-byte line, L1 serves 7 of them
+    const float* arow = (p.aux && row < p.M) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      e[q] = (arow && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(arow + 4 * q)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  tmem_ld_wait();
+  float4 v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                       __uint_as_float(r[4 * q + 3]));
+    if (EPI == EPI_BIAS_ACT) {
+      v[q].x = act_fwd(v[q].x + e[q].x, p.act), v[q].y = act_fwd(v[q].y + e[q].y, p.act);
+      v[q].z = act_fwd(v[q].z + e[q].z, p.act), v[q].w = act_fwd(v[q].w + e[q].w, p.act);
+    } else if (p.aux) {
+      v[q].x *= act_grad_from_output(e[q].x, p.act), v[q].y *= act_grad_from_output(e[q].y, p.act);
+      v[q].z *= act_grad_from_output(e[q].z, p.act), v[q].w *= act_grad_from_output(e[q].w, p.act);
+    }
+  }
+  if (lane == 0) tma_store_wait_read();  // the previous chunk's store has finished reading the staging buffer
+  __syncwarp();
+  float4* srow = reinterpret_cast<float4*>(stg + lane * 128);
+  const int sw = lane & 7;  // SWIZZLE_128B: 16-byte unit q of row r lives at unit q ^ (r % 8)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) srow[q ^ sw] = v[q];
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmOut, stg, col0, row0);
+    tma_store_commit();
+  }
+}
+
+// host-side launchers of the cta_group::2 variant (gemm2sm_tf32.cu); returns CUSRL_B200_EUNSUPPORTED for unknown combos
+int launch_gemm_2sm(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
+                    const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s);
+
+}  // namespace cusrl_b200

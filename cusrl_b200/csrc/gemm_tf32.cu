@@ -29,30 +29,9 @@
 // more shared-memory traffic made it proportionally slower.  cta_group::2 (each CTA supplies half of B) is the
 // next step.
 // PASSES = 1 is plain single-pass TF32.
-#include "tc_common.cuh"
+#include "gemm_common.cuh"
 
 namespace cusrl_b200 {
-
-using namespace tc;
-
-constexpr int BM = 128;           // rows per CTA tile (UMMA M)
-constexpr int BK = 32;            // fp32 per k-block = 128 bytes = one SWIZZLE_128B span
-constexpr int UMMA_K = 8;         // tf32 elements per tcgen05.mma
-constexpr int kGemmThreads = 512;
-constexpr int kSmemBudget = 220 * 1024;
-
-enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1 };
-
-struct GemmParams {
-  float* out;
-  int64_t ldo;
-  const float* bias;   // EPI_BIAS_ACT (may be null)
-  const float* aux;    // EPI_ACT_GRAD: post-activation output of the layer below (may be null: plain copy)
-  int64_t ldaux;
-  int M, N, K, act;
-  int num_m_tiles, num_n_tiles;
-  int num_items;  // work items of a cluster: (pair of M tiles) x (N tile)
-};
 
 template <int BN, int PASSES>
 struct GemmCfg {
@@ -60,26 +39,16 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
   static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 6 ? 6 : (kSmemBudget / STAGE_BYTES);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiStageBytes + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
   static_assert(STAGES >= 2, "tile does not fit in shared memory");
 };
-
-__device__ __forceinline__ float act_fwd(float z, int act) {
-  if (act == 1) return z > 0.f ? z : expm1f(z);  // ELU(alpha=1), same as torch.nn.functional.elu
-  if (act == 2) return fmaxf(z, 0.f);
-  return z;
-}
-__device__ __forceinline__ float act_grad_from_output(float y, int act) {
-  if (act == 1) return y > 0.f ? 1.f : y + 1.f;  // d/dz ELU(z) = exp(z) = y + 1 for z <= 0
-  if (act == 2) return y > 0.f ? 1.f : 0.f;
-  return 1.f;
-}
 
 template <int BN, int PASSES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
+                 const GemmParams p) {
   using Cfg = GemmCfg<BN, PASSES>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF_B_BYTES = Cfg::B_BYTES / 2;
@@ -89,7 +58,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto sAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
   auto sB = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * (PASSES == 3 ? 2 : 1); };
   auto sBlo = [&](int s) { return sB(s) + Cfg::B_BYTES; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 8 epilogue warps x one 32x32 fp32 chunk (SWIZZLE_128B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes);
   uint64_t* full = bars;                  // TMA bytes landed (own A + both halves of B)
   uint64_t* split = bars + STAGES;        // A tile split into hi/lo (3xTF32)
   uint64_t* empty = bars + 2 * STAGES;    // MMAs of BOTH CTAs reading the stage retired
@@ -106,6 +76,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -200,59 +171,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================================== epilogue ==========================================
     const int ew = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
     const int half = (warp - 4) >> 2;   // which half of the tile's columns
+    uint8_t* stg = epi_stage + (warp - 4) * kEpiWarpBytes;
     int local = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
       const int a = local & 1;
       const uint32_t aph = (local >> 1) & 1;
-      const int m0 = item_m0(item), n0 = item_n0(item);
-      const int row = m0 + ew * 32 + lane;
+      const int row0 = item_m0(item) + ew * 32, n0 = item_n0(item);
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(ew * 32) << 16);
+      if (row0 < p.M) {
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, r);
-        const int col0 = n0 + c0;
-        const bool live = row < p.M && col0 < p.N;
-        // operands of the epilogue arithmetic are fetched while the TMEM load is in flight
-        float4 e[8];
-        if (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            e[q] = (p.bias && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * q))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          const float* arow = (p.aux && live) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            e[q] = (arow && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(arow + 4 * q))
-                                                : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-        tmem_ld_wait();
-        if (live) {
-          float* orow = p.out + (int64_t)row * p.ldo + col0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (col0 + 4 * q < p.N) {  // N is a multiple of 4 (checked on the host)
-              float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                     __uint_as_float(r[4 * q + 3]));
-              if (EPI == EPI_BIAS_ACT) {
-                v.x = act_fwd(v.x + e[q].x, p.act), v.y = act_fwd(v.y + e[q].y, p.act);
-                v.z = act_fwd(v.z + e[q].z, p.act), v.w = act_fwd(v.w + e[q].w, p.act);
-              } else if (p.aux) {
-                v.x *= act_grad_from_output(e[q].x, p.act), v.y *= act_grad_from_output(e[q].y, p.act);
-                v.z *= act_grad_from_output(e[q].z, p.act), v.w *= act_grad_from_output(e[q].w, p.act);
-              }
-              *reinterpret_cast<float4*>(orow + 4 * q) = v;
-            }
-          }
-        }
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32)
+          if (n0 + c0 < p.N) epilogue_chunk<EPI>(p, &tmOut, stg, taddr + (uint32_t)c0, row0, n0 + c0, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
     }
+    if (lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
   } else if (PASSES == 3 && warp >= 12) {
     // ===================================== splitter (3xTF32) =================================
     const int t = threadIdx.x - 384;  // 0..127
@@ -353,9 +290,11 @@ int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint6
 
 }  // namespace tc
 
+static int g_gemm_two_sm = 0;  // 1: cta_group::2 kernels (gemm2sm_tf32.cu), 0: 1-SM MMA + TMA multicast (this file)
+
 template <int BN, int PASSES, int EPI>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo, const GemmParams& p,
-                       cudaStream_t s) {
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo, const CUtensorMap& tOut,
+                       const GemmParams& p, cudaStream_t s) {
   using Cfg = GemmCfg<BN, PASSES>;
   auto kern = gemm_tf32_kernel<BN, PASSES, EPI>;
   static bool configured = false;
@@ -369,7 +308,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   }
   const int max_clusters = sm_count() / 2;
   const int clusters = p.num_items < max_clusters ? p.num_items : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, p);  // cluster dims (2,1,1) are compiled in
+  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, tOut, p);  // cluster dims (2,1,1) are compiled in
   return check_launch("gemm_tf32_kernel");
 }
 
@@ -394,6 +333,9 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
   // each CTA of a cluster loads (and multicasts) one half of the B tile: box = bn/2 rows
   if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
   if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
+  // epilogue: 32 x 32 fp32 chunks staged in shared memory and written by bulk tensor stores
+  CUtensorMap tOut;
+  if (int e = encode_tmap_2d_f32(&tOut, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 32, 32)) return e;
   GemmParams p{};
   p.out = out, p.ldo = ldo, p.bias = bias, p.aux = aux, p.ldaux = ldaux;
   p.M = (int)M, p.N = (int)N, p.K = (int)K, p.act = act;
@@ -401,8 +343,9 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
   p.num_n_tiles = (int)((N + bn - 1) / bn);
   p.num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_gemm_two_sm) return launch_gemm_2sm(bn, precision, epi, tA, tB, tBlo, tOut, p, s);
 #define CUSRL_GEMM_CASE(BN_, P_, E_) \
-  if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, p, s);
+  if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, tOut, p, s);
   CUSRL_GEMM_CASE(256, 3, EPI_BIAS_ACT)
   CUSRL_GEMM_CASE(128, 3, EPI_BIAS_ACT)
   CUSRL_GEMM_CASE(256, 1, EPI_BIAS_ACT)
@@ -421,6 +364,11 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
 using namespace cusrl_b200;
 
 extern "C" {
+
+int cusrl_b200_gemm_set_config(int two_sm) {
+  g_gemm_two_sm = two_sm ? 1 : 0;
+  return 0;
+}
 
 int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld, float* hi_t,
                                float* lo_t, int64_t ldt, void* stream) {

@@ -185,6 +185,9 @@ int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, fl
  *                 below); Xact==NULL: no activation factor.
  *   Leading dimensions are in ELEMENTS and must be multiples of 4 (16-byte rows for TMA); N must be a
  *   multiple of 4; ragged K / M edges are zero-filled by TMA.  All pointers 16-byte aligned. */
+/* Tuning knob (process-wide): 1 = cta_group::2 (CTA-pair MMA) forward / data-gradient kernels (default),
+ * 0 = 1-SM MMA with TMA-multicast weight tiles. */
+int cusrl_b200_gemm_set_config(int two_sm);
 int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld,
                                float* hi_t, float* lo_t, int64_t ldt, void* stream);
 int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, const float* W_lo,

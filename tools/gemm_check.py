@@ -81,6 +81,9 @@ def speed(M, K, N, precision, reps=20):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "all"
     if mode in ("all", "small"):
+        from cusrl_b200 import _lib
+        if len(sys.argv) > 2:
+            _lib.load().cusrl_b200_gemm_set_config(int(sys.argv[2]))
         check(128, 32, 128, 0, 1, with_bias=False)
         check(128, 32, 128, 0, 3, with_bias=False)
         check(256, 64, 256, 0, 1)
@@ -92,6 +95,9 @@ if __name__ == "__main__":
         check_dgrad(777, 256, 512, 1, 3)
         check_dgrad(512, 256, 512, 1, 1)
     if mode in ("all", "speed"):
+        from cusrl_b200 import _lib
+        if len(sys.argv) > 2:
+            _lib.load().cusrl_b200_gemm_set_config(int(sys.argv[2]))
         for p in (3, 1):
             speed(393216, 235, 512, p)
             speed(393216, 512, 256, p)
