@@ -49,7 +49,8 @@ gemm2sm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* bfull = bars + STAGES;        // leader: B halves (1xTF32: A tiles too) of both CTAs landed
   uint64_t* split = bars + 2 * STAGES;    // leader: A_lo written by the splitters of both CTAs    (3xTF32)
   uint64_t* empty = bars + 3 * STAGES;    // local : MMAs reading the stage retired (multicast commit)
-  uint64_t* tfull = bars + 4 * STAGES;    // local : accumulator complete (multicast commit)
+  uint64_t* apeer = bars + 4 * STAGES;    // leader: the PEER's A tile landed (relayed by the peer's warp 3)      (3xTF32)
+  uint64_t* tfull = bars + 5 * STAGES;    // local : accumulator complete (multicast commit)
   uint64_t* tempty = tfull + 2;           // leader: accumulator drained by the epilogues of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -70,6 +71,7 @@ gemm2sm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&bfull[s], 1);
       mbar_init(&split[s], 8);    // 4 splitter warps x 2 CTAs
       mbar_init(&empty[s], 1);
+      mbar_init(&apeer[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -127,7 +129,10 @@ gemm2sm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait_cluster(&bfull[s], ph);
-          if (PASSES == 3) mbar_wait_cluster(&split[s], ph);  // also implies both A tiles have landed
+          if (PASSES == 3) {
+            mbar_wait(&afull[s], ph);
+            mbar_wait_cluster(&apeer[s], ph);
+          }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
           const uint32_t alo_addr = smem_u32(sAlo(s)), blo_addr = smem_u32(sBlo(s));
@@ -137,15 +142,37 @@ gemm2sm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t da = make_smem_desc_sw128(a_addr + off, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + off, 16, 1024);
             mma_tf32_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (PASSES == 3) {
-              mma_tf32_ss_2sm(d_tmem, da, make_smem_desc_sw128(blo_addr + off, 16, 1024), idesc, 1u);
-              mma_tf32_ss_2sm(d_tmem, make_smem_desc_sw128(alo_addr + off, 16, 1024), db, idesc, 1u);
+            if (PASSES == 3) mma_tf32_ss_2sm(d_tmem, da, make_smem_desc_sw128(blo_addr + off, 16, 1024), idesc, 1u);
+          }
+          if (PASSES == 3) {
+            // the raw fp32 A tiles are the "hi" operands as they land (the tensor core truncates to TF32); only the
+            // third pass needs the splitters of both CTAs
+            mbar_wait_cluster(&split[s], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t off = (uint32_t)k * UMMA_K * 4;
+              mma_tf32_ss_2sm(d_tmem, make_smem_desc_sw128(alo_addr + off, 16, 1024), make_smem_desc_sw128(b_addr + off, 16, 1024),
+                              idesc, 1u);
             }
           }
           mma_commit_2sm_mc(&empty[s], (uint16_t)3);
           if (++s == STAGES) s = 0, ph ^= 1;
         }
         mma_commit_2sm_mc(&tfull[a], (uint16_t)3);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== peer: relay "my A tile landed" to the leader ======
+    if (PASSES == 3 && !leader && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&afull[s], ph);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&apeer[s]), 0));
+          if (++s == STAGES) s = 0, ph ^= 1;
+        }
       }
     }
   } else if (warp >= 4 && warp < 12) {

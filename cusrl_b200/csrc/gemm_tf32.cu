@@ -13,7 +13,7 @@
 //                                is what bounds the main loop otherwise)
 //   warp 1       MMA issuer    : one elected thread issues tcgen05.mma.kind::tf32, accumulators in TMEM
 //   warp 2       TMEM allocator
-//   warps 4-11   epilogue      : tcgen05.ld -> registers -> bias/activation -> 128-bit global stores
+//   warps 4-11   epilogue      : tcgen05.ld -> registers -> bias/activation -> swizzled staging -> bulk tensor store
 //   warps 12-15  splitter (3xTF32 only): writes lo = A - trunc_tf32(A) next to the A tile (A itself is untouched)
 // Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
 //
@@ -23,18 +23,32 @@
 // fp32 inputs to TF32 (measured, tools/tf32_rounding_probe.py), so the raw fp32 activation tile IS the hi operand
 // and lo = x - (x & ~0x1fff) is exact; weights are pre-split once per optimizer step.
 //
-// What bounds it (ncu + A/B experiments, round 1): shared-memory bandwidth.  Every tf32 MMA re-reads 4 KB of A and
-// 8 KB of B from shared memory per 128 cycles (96 B/clk) on top of the TMA writes and the splitter traffic;
-// deeper pipelines (16-float k-blocks, 4 stages) and fewer bytes into the SM (in-kernel weight split) did not help,
-// more shared-memory traffic made it proportionally slower.  cta_group::2 (each CTA supplies half of B) is the
-// next step.
+// What bounds it (round 1, A/B experiments with parts of the kernel disabled, M = 393216, K = 512, N = 256):
+//   * 1xTF32: 227 us; main loop alone (epilogue off) 162 us  = HBM (1.2 GB at ~5.3 TB/s);
+//   * 3xTF32: 437 us; main loop alone 377 us = 1.12 us per 32-deep k-block against 0.78 us of MMA time.  Per k-block
+//     a CTA INGESTS 16 KB of A + 64 KB of W hi/lo (~85-95 GB/s per SM, the L2 -> SM port) and its shared memory serves
+//     80 KB of TMA writes + 32 KB of splitter traffic + 144 KB of MMA operand reads (12 MMAs x 12 KB), i.e. 256 KB per
+//     1536 MMA cycles = 167 B/clk against 128 B/clk: the SM's own data paths, not HBM and not the tensor pipe
+//     (58 % busy under ncu), set the pace.  Tried and measured without gain: 4 stages of 16-float k-blocks, an
+//     in-kernel weight split (fewer bytes in, more shared-memory traffic), cta_group::2 (gemm2sm_tf32.cu; the peer's
+//     half of B still crosses the SM boundary).  What DID matter was the epilogue: libdevice expm1f (-25 %) and
+//     row-per-thread 16-byte global stores.
 // PASSES = 1 is plain single-pass TF32.
 #include "gemm_common.cuh"
 
 namespace cusrl_b200 {
 
+// k-block depth.  16-float (SWIZZLE_64B) k-blocks give the 3xTF32 kernel 4 pipeline stages instead of 2 in the same
+// shared memory; measured on B200 it changes nothing (474/426/165 us vs 485/437/153 us for the three Anymal-C layers),
+// so the pipeline is not latency-bound and the simpler 32-float blocks stay.  Return 16 for PASSES == 3 to re-test.
+template <int PASSES>
+constexpr int gemm_bk() { return 32; }
+
 template <int BN, int PASSES>
 struct GemmCfg {
+  static constexpr int BK = gemm_bk<PASSES>();
+  static constexpr uint32_t LAYOUT = BK == 32 ? 2u : 4u;   // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr uint32_t SBO = 8 * BK * 4;               // stride between 8-row groups
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (PASSES == 3 ? 2 : 1);
@@ -50,6 +64,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN, PASSES>;
+  constexpr int BK = Cfg::BK;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF_B_BYTES = Cfg::B_BYTES / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -145,10 +160,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t off = (uint32_t)k * UMMA_K * 4;
-            const uint64_t da = make_smem_desc_sw128(a_addr + off, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + off, 16, 1024);
+            const uint64_t da = make_smem_desc_sw128(a_addr + off, 16, Cfg::SBO, Cfg::LAYOUT);
+            const uint64_t db = make_smem_desc_sw128(b_addr + off, 16, Cfg::SBO, Cfg::LAYOUT);
             mma_tf32_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (PASSES == 3) mma_tf32_ss(d_tmem, da, make_smem_desc_sw128(blo_addr + off, 16, 1024), idesc, 1u);
+            if (PASSES == 3) mma_tf32_ss(d_tmem, da, make_smem_desc_sw128(blo_addr + off, 16, Cfg::SBO, Cfg::LAYOUT), idesc, 1u);
           }
           if (PASSES == 3) {
             mbar_wait(&split[s], ph);
@@ -156,7 +171,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t off = (uint32_t)k * UMMA_K * 4;
-              mma_tf32_ss(d_tmem, make_smem_desc_sw128(alo_addr + off, 16, 1024), make_smem_desc_sw128(b_addr + off, 16, 1024),
+              mma_tf32_ss(d_tmem, make_smem_desc_sw128(alo_addr + off, 16, Cfg::SBO, Cfg::LAYOUT), make_smem_desc_sw128(b_addr + off, 16, Cfg::SBO, Cfg::LAYOUT),
                           idesc, 1u);
             }
           }
@@ -329,10 +344,13 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
                 CUSRL_B200_EALIGN, "linear: pointers must be 16-byte aligned");
   const int bn = N > 128 ? 256 : 128;
   CUtensorMap tA, tB, tBlo;
-  if (int e = encode_tmap_2d_f32(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return e;
+  const bool deep = gemm_bk<3>() == 16 && precision == 3 && !g_gemm_two_sm;  // 16-float k-blocks, SWIZZLE_64B
+  const uint32_t bk = deep ? 16 : 32;
+  const int sw = deep ? TMAP_SW64 : TMAP_SW128;
+  if (int e = encode_tmap_2d_f32(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, bk, BM, sw)) return e;
   // each CTA of a cluster loads (and multicasts) one half of the B tile: box = bn/2 rows
-  if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
-  if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn / 2)) return e;
+  if (int e = encode_tmap_2d_f32(&tB, Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, (uint32_t)bn / 2, sw)) return e;
+  if (int e = encode_tmap_2d_f32(&tBlo, Blo ? Blo : Bhi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, (uint32_t)bn / 2, sw)) return e;
   // epilogue: 32 x 32 fp32 chunks staged in shared memory and written by bulk tensor stores
   CUtensorMap tOut;
   if (int e = encode_tmap_2d_f32(&tOut, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 32, 32)) return e;

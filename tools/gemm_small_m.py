@@ -3,7 +3,8 @@ import sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from cusrl_b200 import ops
+from cusrl_b200 import ops, _lib
+_lib.load().cusrl_b200_gemm_set_config(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 dev = "cuda"
 def t(M, K, N, p, reps=20):
     x = torch.randn(M, (K + 3) // 4 * 4, device=dev)[:, :K]
@@ -20,7 +21,7 @@ def t(M, K, N, p, reps=20):
         ops.tc_linear_fwd(x, wp, b, N, 1, p, out=y)
     e.record(); torch.cuda.synchronize()
     return a.elapsed_time(e) / reps * 1e3
-for M in (18944, 37888, 75776, 151552, 393216):
+for M in (75776, 393216):
     for p in (3, 1):
         for (K, N) in ((235, 512), (512, 256), (256, 128)):
             us = t(M, K, N, p)
