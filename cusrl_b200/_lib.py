@@ -75,9 +75,11 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_head_fwd_f32": (c_int, [P, c_int64, P, P, P, c_int64, c_int64, c_int64, P]),
     "cusrl_b200_head_bwd_scratch_bytes": (c_size_t, [c_int64, c_int64]),
     "cusrl_b200_head_bwd_f32": (
-        c_int, [P, P, c_int64, P, c_int, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+        c_int, [P, P, c_int64, P, c_int, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int, P, c_int, P, c_size_t, P]),
     "cusrl_b200_linear_dgrad_tf32": (
-        c_int, [P, c_int64, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
+        c_int, [P, c_int64, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, c_int, P,
+                c_size_t, P]),
+    "cusrl_b200_dgrad_workspace_bytes": (c_size_t, [c_int64]),
 }
 
 

@@ -26,6 +26,7 @@ struct GemmParams {
   int M, N, K, act;
   int num_m_tiles, num_n_tiles;
   int num_items;  // work items of a cluster: (pair of M tiles) x (N tile)
+  float* colsum;  // EPI_ACT_GRAD, optional: [gridDim.x][4][N] column sums of the output (bias gradient partials)
 };
 
 // expm1(z) for z <= 0 in ~11 instructions, both branches evaluated and selected (no divergence): libdevice's expm1f costs
@@ -106,9 +107,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const CUtens
     tma_store_2d(tmOut, stg, col0, row0);
     tma_store_commit();
   }
+  if (EPI == EPI_ACT_GRAD && p.colsum) {
+    // bias gradient of the layer below = column sums of this output: lane c adds up column c of the staged chunk (rows
+    // >= M hold exact zeros: their accumulators are products of zero-filled A rows) in a fixed order and accumulates
+    // into the slot owned by this (CTA, row quarter, column) -- one owner per slot, so plain read-modify-write.
+    const float* col = reinterpret_cast<const float*>(stg) + (lane & 3);
+    const int unit = lane >> 2;
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) sum += col[r * 32 + ((unit ^ (r & 7)) << 2)];
+    if (col0 + lane < p.N) {
+      float* slot = p.colsum + ((int64_t)blockIdx.x * 4 + ((threadIdx.x >> 5) & 3)) * p.N + col0 + lane;
+      *slot += sum;
+    }
+  }
 }
 
 // host-side launchers of the cta_group::2 variant (gemm2sm_tf32.cu); returns CUSRL_B200_EUNSUPPORTED for unknown combos
+// grid size the launchers use for `num_items` work items (2 CTAs per cluster)
+int gemm_grid_ctas(int num_items);
 int launch_gemm_2sm(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
                     const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s);
 

@@ -307,6 +307,11 @@ int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint6
 
 static int g_gemm_two_sm = 0;  // 1: cta_group::2 kernels (gemm2sm_tf32.cu), 0: 1-SM MMA + TMA multicast (this file)
 
+int gemm_grid_ctas(int num_items) {
+  const int max_clusters = sm_count() / 2;
+  return 2 * (num_items < max_clusters ? num_items : max_clusters);
+}
+
 template <int BN, int PASSES, int EPI>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo, const CUtensorMap& tOut,
                        const GemmParams& p, cudaStream_t s) {
@@ -321,16 +326,20 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     }
     configured = true;
   }
-  const int max_clusters = sm_count() / 2;
-  const int clusters = p.num_items < max_clusters ? p.num_items : max_clusters;
-  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, tOut, p);  // cluster dims (2,1,1) are compiled in
+  kern<<<gemm_grid_ctas(p.num_items), kGemmThreads, Cfg::SMEM_BYTES, s>>>(tA, tB, tBlo, tOut, p);  // cluster dims (2,1,1) are compiled in
   return check_launch("gemm_tf32_kernel");
 }
+
+static int gemm_dispatch(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
+                         const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s);
+// db (+)= sum over `nblocks` partial rows, fixed order (gemm_wgrad_tf32.cu)
+int colsum_finalize(const float* partial, int nblocks, int N, float* db, int accumulate, cudaStream_t s);
 
 // Shared implementation of forward (EPI_BIAS_ACT) and data-gradient (EPI_ACT_GRAD) calls.
 static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const float* Blo, int64_t ldb, float* out, int64_t ldo,
                        const float* bias, const float* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int act,
-                       int precision, int epi, void* stream) {
+                       int precision, int epi, void* stream, float* colsum_db = nullptr, int colsum_accumulate = 0,
+                       void* workspace = nullptr, size_t workspace_bytes = 0) {
   CUSRL_REQUIRE(A && Bhi && out, CUSRL_B200_EINVAL, "linear: null pointer");
   CUSRL_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N <= 65536 && K <= 65536, CUSRL_B200_EINVAL,
                 "linear: bad problem size");
@@ -361,6 +370,22 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
   p.num_n_tiles = (int)((N + bn - 1) / bn);
   p.num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
+  const int ctas = gemm_grid_ctas(p.num_items);
+  if (colsum_db) {
+    const size_t need = (size_t)ctas * 4 * (size_t)N * sizeof(float);
+    CUSRL_REQUIRE(workspace && workspace_bytes >= need && aligned_to(workspace, 16), CUSRL_B200_ESCRATCH,
+                  "linear_dgrad: workspace too small for the bias-gradient partials");
+    cudaError_t me = cudaMemsetAsync(workspace, 0, need, s);
+    CUSRL_REQUIRE(me == cudaSuccess, (int)me, "linear_dgrad: cudaMemsetAsync: %s", cudaGetErrorString(me));
+    p.colsum = (float*)workspace;
+  }
+  int rc = gemm_dispatch(bn, precision, epi, tA, tB, tBlo, tOut, p, s);
+  if (rc || !colsum_db) return rc;
+  return colsum_finalize((const float*)workspace, ctas * 4, (int)N, colsum_db, colsum_accumulate, s);
+}
+
+static int gemm_dispatch(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
+                         const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s) {
   if (g_gemm_two_sm) return launch_gemm_2sm(bn, precision, epi, tA, tB, tBlo, tOut, p, s);
 #define CUSRL_GEMM_CASE(BN_, P_, E_) \
   if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, tOut, p, s);
@@ -407,12 +432,18 @@ int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, c
   return gemm_kmajor(X, ldx, W_hi, W_lo, ldw, Y, ldy, bias, nullptr, 0, M, N, K, act, precision, EPI_BIAS_ACT, stream);
 }
 
+size_t cusrl_b200_dgrad_workspace_bytes(int64_t K) {
+  if (K <= 0) return 0;
+  return (size_t)sm_count() * 4 * (size_t)K * sizeof(float);
+}
+
 int cusrl_b200_linear_dgrad_tf32(const float* dY, int64_t lddy, const float* WT_hi, const float* WT_lo, int64_t ldwt,
                                  const float* Xact, int64_t ldxa, float* dX, int64_t lddx, int64_t M, int64_t N, int64_t K,
-                                 int act, int precision, void* stream) {
+                                 int act, int precision, float* db_below, int accumulate, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   // dX[M,K] = dY[M,N] @ W[N,K]: as a K-major GEMM the reduction runs over N and B is the transposed copy WT[K,N]
   return gemm_kmajor(dY, lddy, WT_hi, WT_lo, ldwt, dX, lddx, nullptr, Xact, ldxa, M, /*N=*/K, /*K=*/N, act, precision,
-                     EPI_ACT_GRAD, stream);
+                     EPI_ACT_GRAD, stream, db_below, accumulate, workspace, workspace_bytes);
 }
 
 }  // extern "C"

@@ -248,6 +248,11 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nbloc
   if (lane == 0) db[c] = accumulate ? db[c] + (float)acc : (float)acc;
 }
 
+int colsum_finalize(const float* partial, int nblocks, int N, float* db, int accumulate, cudaStream_t s) {
+  colsum_final_kernel<<<(unsigned)(((int64_t)N * 32 + 255) / 256), 256, 0, s>>>(partial, nblocks, N, db, accumulate);
+  return check_launch("colsum_final_kernel");
+}
+
 template <int BN, int PASSES>
 static int launch_wgrad(const CUtensorMap& tDZ, const CUtensorMap& tX, const WgradParams& p, cudaStream_t s) {
   using Cfg = WgradCfg<BN, PASSES>;
@@ -338,8 +343,7 @@ int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, 
     nb = (int)((M + rows_per_block - 1) / rows_per_block);
     colsum_partial_kernel<<<nb, 256, 0, s>>>(dZ, lddz, (int)M, (int)N, rows_per_block, cs);
     if (int e3 = check_launch("colsum_partial_kernel")) return e3;
-    colsum_final_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s>>>(cs, nb, (int)N, db, accumulate);
-    if (int e4 = check_launch("colsum_final_kernel")) return e4;
+    if (int e4 = colsum_finalize(cs, nb, (int)N, db, accumulate, s)) return e4;
   }
   return 0;
 }

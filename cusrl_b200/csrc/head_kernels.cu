@@ -4,6 +4,7 @@
 //   forward : Y[M,No] = H[M,K] @ W[No,K]^T + b
 //   backward: dH[M,K] = (dY[M,No] @ W) * act'(H)      (act' of the trunk's last layer, from its output H)
 //             dW[No,K] (+)= dY^T @ H ;  db[No] (+)= column sums of dY
+//             dbH[K]   (+)= column sums of dH        (optional: the bias gradient of the trunk's last layer)
 #include "common.cuh"
 
 namespace cusrl_b200 {
@@ -59,13 +60,15 @@ template <int NO, int KV>
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ H,
                                                                 int64_t ldh, const float* __restrict__ W, int act,
                                                                 float* __restrict__ dH, int64_t lddh, int M,
-                                                                float* __restrict__ partial /*[blocks][NO*K + NO]*/) {
+                                                                float* __restrict__ partial /*[blocks][NO*K + NO + K]*/) {
   constexpr int K = 128 * KV;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float4 w[NO][KV], gw[NO][KV];
+  float4 w[NO][KV], gw[NO][KV], gd[KV];
   float gb[NO];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) gd[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int o = 0; o < NO; ++o) {
     gb[o] = 0.f;
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
         d.x *= head_act_grad(h[v].x, act), d.y *= head_act_grad(h[v].y, act);
         d.z *= head_act_grad(h[v].z, act), d.w *= head_act_grad(h[v].w, act);
         *reinterpret_cast<float4*>(dH + (int64_t)row * lddh + 128 * v + 4 * lane) = d;
+        gd[v].x += d.x, gd[v].y += d.y, gd[v].z += d.z, gd[v].w += d.w;
       }
     }
 #pragma unroll
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
   }
   // block reduction of the weight-gradient partials through shared memory (fixed order over warps)
   __shared__ float red[kHeadThreads / 32][NO * K > 2048 ? 1 : NO * K];  // only instantiated with NO*K <= 2048
-  float* out = partial + (int64_t)blockIdx.x * (NO * K + NO);
+  float* out = partial + (int64_t)blockIdx.x * (NO * K + NO + K);
 #pragma unroll
   for (int o = 0; o < NO; ++o)
 #pragma unroll
@@ -125,17 +129,31 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
     for (int q = 0; q < kHeadThreads / 32; ++q) s += redb[q][threadIdx.x];
     out[NO * K + threadIdx.x] = s;
   }
+  // column sums of dH (re-using the reduction buffer)
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < KV; ++v) *reinterpret_cast<float4*>(&red[wib][128 * v + 4 * lane]) = gd[v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kHeadThreads / 32; ++q) s += red[q][i];
+    out[NO * K + NO + i] = s;
+  }
 }
 
 __global__ void head_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int NO, int K, float* __restrict__ dW,
-                                      float* __restrict__ db, int accumulate) {
-  const int total = NO * K + NO;
+                                      float* __restrict__ db, int accumulate, float* __restrict__ dbH, int accumulate_dbh) {
+  const int total = NO * K + NO + K;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const bool trunk = i >= NO * K + NO;
+  float* dst = i < NO * K ? dW + i : (trunk ? (dbH ? dbH + (i - NO * K - NO) : nullptr) : (db ? db + (i - NO * K) : nullptr));
+  if (!dst) return;
   double acc = 0.0;
   for (int b = 0; b < nblocks; ++b) acc += partial[(int64_t)b * total + i];
-  float* dst = i < NO * K ? dW + i : (db ? db + (i - NO * K) : nullptr);
-  if (dst) *dst = accumulate ? *dst + (float)acc : (float)acc;
+  const int add = trunk ? accumulate_dbh : accumulate;
+  *dst = add ? *dst + (float)acc : (float)acc;
 }
 
 template <typename F>
@@ -206,12 +224,12 @@ int cusrl_b200_head_fwd_f32(const float* H, int64_t ldh, const float* W, const f
 }
 
 size_t cusrl_b200_head_bwd_scratch_bytes(int64_t K, int64_t No) {
-  return (size_t)kHeadMaxBlocks * (size_t)(No * K + No) * sizeof(float);
+  return (size_t)kHeadMaxBlocks * (size_t)(No * K + No + K) * sizeof(float);
 }
 
 int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const float* W, int act, float* dH,
                             int64_t lddh, float* dW, float* db, int64_t M, int64_t K, int64_t No, int accumulate,
-                            void* scratch, size_t scratch_bytes, void* stream) {
+                            float* dbH, int accumulate_dbh, void* scratch, size_t scratch_bytes, void* stream) {
   CUSRL_REQUIRE(dY && H && W && dW && scratch, CUSRL_B200_EINVAL, "head_bwd: null pointer");
   CUSRL_REQUIRE(M > 0 && K > 0 && No > 0 && M < (1ll << 31), CUSRL_B200_EINVAL, "head_bwd: bad sizes");
   CUSRL_REQUIRE((K % 128) == 0 && No <= kHeadMaxNo && No * K <= 2048, CUSRL_B200_EUNSUPPORTED,
@@ -220,13 +238,14 @@ int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const 
                     aligned_to(W, 16) && (!dH || aligned_to(dH, 16)),
                 CUSRL_B200_EALIGN, "head_bwd: alignment");
   CUSRL_REQUIRE(act >= 0 && act <= 2, CUSRL_B200_EINVAL, "head_bwd: unknown activation code");
+  CUSRL_REQUIRE(!dbH || dH, CUSRL_B200_EINVAL, "head_bwd: dbH (column sums of dH) needs dH");
   CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_head_bwd_scratch_bytes(K, No), CUSRL_B200_ESCRATCH, "head_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
   HeadBwd f{dY, H, W, ldh, lddh, act, (int)M, dH, (float*)scratch, head_grid(M), s};
   if (int e = head_dispatch((int)No, (int)K, f)) return e;
-  const int total = (int)(No * K + No);
+  const int total = (int)(No * K + No + K);
   head_bwd_final_kernel<<<(total + 255) / 256, 256, 0, s>>>((const float*)scratch, (int)f.grid, (int)No, (int)K, dW, db,
-                                                            accumulate);
+                                                            accumulate, dbH, accumulate_dbh);
   return check_launch("head_bwd_final_kernel");
 }
 

@@ -41,19 +41,36 @@ def _rows_ok(x: torch.Tensor) -> torch.Tensor:
     return padded[:, :width]
 
 
-def _wgrad(dz, inp, weight, bias, grads, slot, bias_slot=None):
+def _in_arena(weight, bias) -> bool:
+    """Both parameters of a layer accumulate straight into existing (flat-arena) gradient tensors."""
+    return weight.grad is not None and weight.grad.is_contiguous() and (bias is None or bias.grad is not None)
+
+
+def _wgrad(dz, inp, weight, bias, grads, slot, bias_slot=None, bias_done=False):
     """Weight / bias gradient of one layer: accumulate into the flat arena when the parameter has one, otherwise hand
-    fresh tensors to autograd through ``grads[slot]`` / ``grads[bias_slot]`` (default: the adjacent slot)."""
+    fresh tensors to autograd through ``grads[slot]`` / ``grads[bias_slot]`` (default: the adjacent slot).
+    ``bias_done``: the bias gradient was already produced by the kernel that produced ``dz`` (its column sums)."""
     precision = ops.GEMM_PRECISION
     bias_slot = slot + 1 if bias_slot is None else bias_slot
-    w_grad, b_grad = weight.grad, (bias.grad if bias is not None else None)
-    if w_grad is not None and (bias is None or b_grad is not None) and w_grad.is_contiguous():
-        ops.tc_linear_wgrad(dz, inp, w_grad, b_grad, precision, accumulate=True)
+    if _in_arena(weight, bias):
+        ops.tc_linear_wgrad(dz, inp, weight.grad, None if (bias is None or bias_done) else bias.grad, precision, accumulate=True)
     else:
         dw = torch.empty_like(weight)
-        db = torch.empty_like(bias) if bias is not None else None
+        db = torch.empty_like(bias) if (bias is not None and not bias_done) else None
         ops.tc_linear_wgrad(dz, inp, dw, db, precision, accumulate=False)
-        grads[slot], grads[bias_slot] = dw, db
+        grads[slot] = dw
+        if not bias_done:
+            grads[bias_slot] = db
+
+
+def _bias_target(weight, bias, grads, bias_slot):
+    """(tensor, accumulate) the producer of a layer's dZ should add that layer's bias gradient to, or (None, False)."""
+    if bias is None or not bias.requires_grad or not weight.requires_grad:
+        return None, False
+    if _in_arena(weight, bias):
+        return bias.grad, True
+    grads[bias_slot] = torch.empty_like(bias)
+    return grads[bias_slot], False
 
 
 class _MlpHeadFunction(torch.autograd.Function):
@@ -97,18 +114,27 @@ class _MlpHeadFunction(torch.autograd.Function):
             arena = hw_grad is not None and (head_b is None or hb_grad is not None)
             dw = hw_grad if arena else torch.empty_like(head_w)
             db = hb_grad if arena else (torch.empty_like(head_b) if head_b is not None else None)
-            # dZ of the last trunk layer = (dOut W_head) * act'(latent), fused in the head kernel
-            dz = ops.head_bwd(grad_out.contiguous(), acts[-1], head_w, last_code, dw, db, need_dh=True, accumulate=arena)
+            # dZ of the last trunk layer = (dOut W_head) * act'(latent), fused in the head kernel together with its
+            # column sums (= that layer's bias gradient)
+            db_trunk, acc_trunk = _bias_target(weights[n - 1], biases[n - 1], grads, 2 * n - 1)
+            dz = ops.head_bwd(grad_out.contiguous(), acts[-1], head_w, last_code, dw, db, need_dh=True, accumulate=arena,
+                              db_trunk=db_trunk, accumulate_trunk=acc_trunk)
+            bias_done = db_trunk is not None
             if not arena:
                 grads[2 * n], grads[2 * n + 1] = dw, db
         else:
             dz = ops.act_grad_mul(grad_out, acts[-1], last_code)
+            bias_done = False
         for i in range(n - 1, -1, -1):
             inp = acts[i - 1] if i > 0 else x
             if weights[i].requires_grad:
-                _wgrad(dz, inp, weights[i], biases[i], grads, 2 * i)
+                _wgrad(dz, inp, weights[i], biases[i], grads, 2 * i, bias_done=bias_done)
             if i > 0:
-                dz = ops.tc_linear_dgrad(dz, ops.prepared_weight(weights[i]), acts[i - 1], weights[i].shape[1], act_code, precision)
+                # the data-gradient epilogue also emits the bias gradient of layer i-1 (column sums of its output)
+                db_below, acc_below = _bias_target(weights[i - 1], biases[i - 1], grads, 2 * i - 1)
+                dz = ops.tc_linear_dgrad(dz, ops.prepared_weight(weights[i]), acts[i - 1], weights[i].shape[1], act_code, precision,
+                                         db_below=db_below, accumulate=acc_below)
+                bias_done = db_below is not None
             elif x_req:
                 dz = ops.tc_linear_dgrad(dz, ops.prepared_weight(weights[0]), None, weights[0].shape[1], 0, precision)
         return (dz if x_req else None, None, None, None, *grads)

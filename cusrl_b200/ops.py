@@ -453,17 +453,25 @@ def tc_linear_fwd(x: torch.Tensor, wp: dict[str, torch.Tensor], bias: torch.Tens
 
 
 def tc_linear_dgrad(dy: torch.Tensor, wp: dict[str, torch.Tensor], x_act: torch.Tensor | None, k_in: int, act: int,
-                    precision: int = 3, out: torch.Tensor | None = None) -> torch.Tensor:
-    """dX = (dY W) * act'(x_act) on tcgen05 (cusrl_b200_linear_dgrad_tf32)."""
+                    precision: int = 3, out: torch.Tensor | None = None, db_below: torch.Tensor | None = None,
+                    accumulate: bool = False) -> torch.Tensor:
+    """dX = (dY W) * act'(x_act) on tcgen05 (cusrl_b200_linear_dgrad_tf32); `db_below` (+)= column sums of dX, the bias
+    gradient of the layer below, produced by the same kernel's epilogue."""
     M, N = dy.shape
     dyp, lddy = _rows(dy, "dy")
     dx = torch.empty(M, k_in, device=dy.device) if out is None else out
     dxp, lddx = _rows(dx, "dx")
     xa, ldxa = (None, 0) if x_act is None else _rows(x_act, "x_act")
-    code = _lib.load().cusrl_b200_linear_dgrad_tf32(
+    lib = _lib.load()
+    if db_below is not None:
+        ws = _get_scratch(dy.device, "dgrad", lib.cusrl_b200_dgrad_workspace_bytes(k_in))
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    else:
+        ws_ptr, ws_bytes = None, 0
+    code = lib.cusrl_b200_linear_dgrad_tf32(
         dyp, lddy, wp["hi_t"].data_ptr(), wp["lo_t"].data_ptr(), wp["hi_t"].stride(0), xa, ldxa, dxp, lddx,
-        M, N, k_in, act, precision, _stream())
-    _lib.check(code, "linear_dgrad")
+        M, N, k_in, act, precision, _ptr(db_below, torch.float32, "db_below"), int(accumulate), ws_ptr, ws_bytes, _stream())
+    _lib.check(code, "linear_dgrad", launches=1 if db_below is None else 2)
     return dx
 
 
@@ -497,8 +505,9 @@ def head_fwd(h: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None) -> torch.
 
 
 def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: torch.Tensor, db: torch.Tensor | None,
-             need_dh: bool = True, accumulate: bool = False) -> torch.Tensor | None:
-    """dH = (dY W) * act'(H); dW (+)= dY^T H; db (+)= colsum(dY) (cusrl_b200_head_bwd_f32)."""
+             need_dh: bool = True, accumulate: bool = False, db_trunk: torch.Tensor | None = None,
+             accumulate_trunk: bool = False) -> torch.Tensor | None:
+    """dH = (dY W) * act'(H); dW (+)= dY^T H; db (+)= colsum(dY); db_trunk (+)= colsum(dH) (cusrl_b200_head_bwd_f32)."""
     M, K = h.shape
     No = w.shape[0]
     hp, ldh = _rows(h, "h")
@@ -508,7 +517,8 @@ def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: t
     code = lib.cusrl_b200_head_bwd_f32(
         _ptr(dy, torch.float32, "dy"), hp, ldh, _ptr(w.detach(), torch.float32, "weight"), act,
         None if dh is None else dh.data_ptr(), K, _ptr(dw, torch.float32, "dw"), _ptr(db, torch.float32, "db"),
-        M, K, No, int(accumulate), scratch.data_ptr(), scratch.numel(), _stream())
+        M, K, No, int(accumulate), _ptr(db_trunk, torch.float32, "db_trunk"), int(accumulate_trunk),
+        scratch.data_ptr(), scratch.numel(), _stream())
     _lib.check(code, "head_bwd", launches=2)
     return dh
 

@@ -185,8 +185,12 @@ int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, fl
  *                 below); Xact==NULL: no activation factor.
  *   Leading dimensions are in ELEMENTS and must be multiples of 4 (16-byte rows for TMA); N must be a
  *   multiple of 4; ragged K / M edges are zero-filled by TMA.  All pointers 16-byte aligned. */
-/* Tuning knob (process-wide): 1 = cta_group::2 (CTA-pair MMA) forward / data-gradient kernels (default),
- * 0 = 1-SM MMA with TMA-multicast weight tiles. */
+/*                 db_below (optional): the bias gradient of the layer BELOW, i.e. the column sums of dX
+ *                 (dX is that layer's dZ), produced by the epilogue while the tile is on chip and reduced
+ *                 in a fixed order through `workspace` (cusrl_b200_dgrad_workspace_bytes(K));
+ *                 accumulate != 0 adds to the existing db_below.  NULL: not computed, workspace unused.
+ * Tuning knob (process-wide): 0 = 1-SM MMA with TMA-multicast weight tiles (default),
+ * 1 = cta_group::2 (CTA-pair MMA) forward / data-gradient kernels (measured slower, kept for A/B runs). */
 int cusrl_b200_gemm_set_config(int two_sm);
 int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld,
                                float* hi_t, float* lo_t, int64_t ldt, void* stream);
@@ -195,7 +199,9 @@ int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, c
                                int64_t N, int64_t K, int act, int precision, void* stream);
 int cusrl_b200_linear_dgrad_tf32(const float* dY, int64_t lddy, const float* WT_hi, const float* WT_lo,
                                  int64_t ldwt, const float* Xact, int64_t ldxa, float* dX, int64_t lddx,
-                                 int64_t M, int64_t N, int64_t K, int act, int precision, void* stream);
+                                 int64_t M, int64_t N, int64_t K, int act, int precision, float* db_below,
+                                 int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+size_t cusrl_b200_dgrad_workspace_bytes(int64_t K);
 
 /*   linear_wgrad: dW[N,K] (+)= dZ[M,N]^T @ X[M,K];  db[N] (+)= column sums of dZ (db may be NULL).
  *                 Split-K over CTAs with a deterministic second-stage reduction through `workspace`
@@ -210,14 +216,16 @@ int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, 
  * nn/module/distribution.py:56 and nn/module/critic.py:87-88), exact fp32 SIMT kernels, HBM-bound:
  *   head_fwd: Y[M,No] = H[M,K] @ W[No,K]^T + bias[No]
  *   head_bwd: dH[M,K] = (dY[M,No] @ W) * act'(H)   (dH may be NULL);
- *             dW[No,K] (+)= dY^T @ H;  db[No] (+)= column sums of dY (db may be NULL)
+ *             dW[No,K] (+)= dY^T @ H;  db[No] (+)= column sums of dY (db may be NULL);
+ *             dbH[K] (+)= column sums of dH = bias gradient of the trunk's last layer (optional, needs dH)
  *   K multiple of 128, No <= 16, No*K <= 2048.  W, dY, Y dense; ldh / lddh multiples of 4. */
 int cusrl_b200_head_fwd_f32(const float* H, int64_t ldh, const float* W, const float* bias, float* Y,
                             int64_t M, int64_t K, int64_t No, void* stream);
 size_t cusrl_b200_head_bwd_scratch_bytes(int64_t K, int64_t No);
 int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const float* W, int act, float* dH,
                             int64_t lddh, float* dW, float* db, int64_t M, int64_t K, int64_t No,
-                            int accumulate, void* scratch, size_t scratch_bytes, void* stream);
+                            int accumulate, float* dbH, int accumulate_dbh, void* scratch, size_t scratch_bytes,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  Random Network Distillation arithmetic -- replaces the tensor code of RandomNetworkDistillation

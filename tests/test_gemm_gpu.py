@@ -63,6 +63,43 @@ def test_linear_dgrad(ops, M, N, K, act):
     assert (dx.double() - ref).abs().max().item() <= max(8 * f32, 2e-6 * ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,act", [(1000, 128, 256, 1), (40000, 256, 512, 1), (333, 64, 20, 0), (70000, 128, 132, 2)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_linear_dgrad_emits_bias_gradient_of_layer_below(ops, M, N, K, act, accumulate):
+    """db_below (+)= column sums of dX, produced by the data-gradient epilogue (ragged M / K edges, multi-item CTAs)."""
+    g = torch.Generator().manual_seed(M + N + 1)
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / N**0.5).to(DEV)
+    xa = torch.randn(M, (K + 3) // 4 * 4, generator=g).to(DEV)[:, :K]
+    base = torch.randn(K, generator=g).to(DEV)
+    db = base.clone()
+    dx = ops.tc_linear_dgrad(dy, ops.weight_prep(w), xa if act else None, K, act, 3, db_below=db, accumulate=accumulate)
+    ref = dx.double().sum(0) + (base.double() if accumulate else 0.0)   # column sums of what the kernel itself wrote
+    assert (db.double() - ref).abs().max().item() <= 2e-6 * max(dx.double().abs().sum(0).max().item(), 1.0)
+    # and the run-to-run result is bitwise reproducible (fixed-order reduction)
+    db2 = base.clone()
+    ops.tc_linear_dgrad(dy, ops.weight_prep(w), xa if act else None, K, act, 3, db_below=db2, accumulate=accumulate)
+    assert torch.equal(db, db2)
+
+
+def test_two_sm_variant_matches_default(ops):
+    """The cta_group::2 kernels (kept behind cusrl_b200_gemm_set_config for A/B measurements) compute the same thing."""
+    from cusrl_b200 import _lib
+    g = torch.Generator().manual_seed(7)
+    x = _padded(3000, 235, g)
+    w = (torch.randn(512, 235, generator=g) / 15.0).to(DEV)
+    b = torch.randn(512, generator=g).to(DEV)
+    wp = ops.weight_prep(w)
+    y0 = ops.tc_linear_fwd(x, wp, b, 512, 1, 3)
+    try:
+        _lib.load().cusrl_b200_gemm_set_config(1)
+        y1 = ops.tc_linear_fwd(x, wp, b, 512, 1, 3)
+    finally:
+        _lib.load().cusrl_b200_gemm_set_config(0)
+    torch.cuda.synchronize()
+    assert torch.allclose(y0, y1, rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 128, 128), (4096, 512, 235), (5000, 256, 512), (5000, 128, 256), (3000, 16, 128),
                                    (100, 64, 19)])
 @pytest.mark.parametrize("accumulate", [False, True])
@@ -91,9 +128,11 @@ def test_heads(ops, M, K, No):
     assert torch.allclose(y.double(), torch.nn.functional.linear(h.double(), w.double(), b.double()), rtol=1e-5, atol=1e-5)
     dy = torch.randn(M, No, generator=g).to(DEV)
     dw, db = torch.zeros(No, K, device=DEV), torch.zeros(No, device=DEV)
-    dh = ops.head_bwd(dy, h, w, 1, dw, db)
+    dbt = torch.ones(K, device=DEV)
+    dh = ops.head_bwd(dy, h, w, 1, dw, db, db_trunk=dbt, accumulate_trunk=True)
     dh_ref = (dy.double() @ w.double()) * torch.where(h > 0, torch.ones_like(h), h + 1).double()
     assert torch.allclose(dh.double(), dh_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dbt.double(), 1.0 + dh_ref.sum(0), rtol=1e-5, atol=1e-4)
     assert torch.allclose(dw.double(), dy.double().t() @ h.double(), rtol=1e-5, atol=1e-4)
     assert torch.allclose(db.double(), dy.double().sum(0), rtol=1e-5, atol=1e-4)
 
