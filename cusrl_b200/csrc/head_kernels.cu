@@ -19,43 +19,74 @@ __device__ __forceinline__ float head_act_grad(float y, int act) {
   return 1.f;
 }
 
-// K = 128 * KV: lane l owns columns {128*v + 4*l .. +3}
+// Both kernels stream [M, K] rows once and are HBM-bound only if enough loads are in flight: a warp works on 8 rows per
+// iteration and issues all their loads before the arithmetic (one row per iteration left the SM with ~8 KB in flight
+// and the kernels at ~1.5 TB/s).
+constexpr int kHeadRows = 8;  // rows per warp iteration
+
+// forward: 8 lanes per row (lane `sub` owns the float4 columns {q*8 + sub}), 4 rows side by side, 2 row batches per
+// iteration; W lives in shared memory (the 8 sub-lanes read one 128-byte line, broadcast over the 4 row groups), so
+// the cross-lane reduction is 3 shuffle steps per output instead of 5.
 template <int NO, int KV>
 __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const float* __restrict__ H, int64_t ldh,
                                                                 const float* __restrict__ W, const float* __restrict__ b,
                                                                 float* __restrict__ Y, int M) {
-  const int lane = threadIdx.x & 31;
+  constexpr int K = 128 * KV, Q = 4 * KV;
+  __shared__ float4 sW[NO][K / 4];
+  for (int i = threadIdx.x; i < NO * (K / 4); i += blockDim.x)
+    sW[i / (K / 4)][i % (K / 4)] = __ldg(reinterpret_cast<const float4*>(W) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, rg = lane >> 3;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float4 w[NO][KV];
+  const float b_lo = (b && sub < NO) ? __ldg(b + sub) : 0.f;
+  const float b_hi = (b && sub + 8 < NO) ? __ldg(b + sub + 8) : 0.f;
+  for (int64_t base = (int64_t)warp * kHeadRows; base < M; base += (int64_t)nwarps * kHeadRows) {
+    float4 h[2][Q];
 #pragma unroll
-  for (int o = 0; o < NO; ++o)
+    for (int rb = 0; rb < 2; ++rb) {
+      const int64_t row = base + rb * 4 + rg;
 #pragma unroll
-    for (int v = 0; v < KV; ++v) w[o][v] = __ldg(reinterpret_cast<const float4*>(W + o * (128 * KV) + 128 * v + 4 * lane));
-  const float bias = (b && lane < NO) ? __ldg(b + lane) : 0.f;
-  for (int row = warp; row < M; row += nwarps) {
-    float4 h[KV];
-#pragma unroll
-    for (int v = 0; v < KV; ++v) h[v] = ldg_stream4(H + (int64_t)row * ldh + 128 * v + 4 * lane);
-    float acc[NO];
+      for (int q = 0; q < Q; ++q)
+        h[rb][q] = row < M ? ldg_stream4(H + row * ldh + (q * 8 + sub) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float acc[2][NO];
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int v = 0; v < KV; ++v) a += h[v].x * w[o][v].x + h[v].y * w[o][v].y + h[v].z * w[o][v].z + h[v].w * w[o][v].w;
-      acc[o] = a;
+      for (int q = 0; q < Q; ++q) {
+        const float4 w = sW[o][q * 8 + sub];
+        a0 += h[0][q].x * w.x + h[0][q].y * w.y + h[0][q].z * w.z + h[0][q].w * w.w;
+        a1 += h[1][q].x * w.x + h[1][q].y * w.y + h[1][q].z * w.z + h[1][q].w * w.w;
+      }
+      acc[0][o] = a0, acc[1][o] = a1;
     }
-    // butterfly: afterwards every lane holds every sum; lane o writes output o
-    float mine = 0.f;
 #pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      const float s = warp_sum(acc[o]);
-      if (lane == o) mine = s;
+    for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        acc[0][o] += __shfl_xor_sync(0xffffffffu, acc[0][o], off);
+        acc[1][o] += __shfl_xor_sync(0xffffffffu, acc[1][o], off);
+      }
+    // every sub-lane now holds every sum of its row; sub-lane s writes outputs s and s + 8
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      const int64_t row = base + rb * 4 + rg;
+      float lo = 0.f, hi = 0.f;
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+        if ((o & 7) == sub) (o < 8 ? lo : hi) = acc[rb][o];
+      if (row < M) {
+        if (sub < NO) Y[row * NO + sub] = lo + b_lo;
+        if (sub + 8 < NO) Y[row * NO + sub + 8] = hi + b_hi;
+      }
     }
-    if (lane < NO) Y[(int64_t)row * NO + lane] = mine + bias;
   }
 }
 
+// backward: lane l owns columns {128*v + 4*l .. +3} of every row its warp handles (W and the dW accumulators stay in
+// registers); the NO upstream gradients of a row are loaded by lanes 0..NO-1 and broadcast by shuffle.
 template <int NO, int KV>
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ H,
                                                                 int64_t ldh, const float* __restrict__ W, int act,
@@ -66,42 +97,66 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   float4 w[NO][KV], gw[NO][KV], gd[KV];
-  float gb[NO];
+  float gb = 0.f;  // lane o: column sum of dY[:, o]
 #pragma unroll
   for (int v = 0; v < KV; ++v) gd[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int o = 0; o < NO; ++o) {
-    gb[o] = 0.f;
 #pragma unroll
     for (int v = 0; v < KV; ++v) {
       w[o][v] = __ldg(reinterpret_cast<const float4*>(W + o * K + 128 * v + 4 * lane));
       gw[o][v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  for (int row = warp; row < M; row += nwarps) {
-    float g[NO];
+  // software pipeline: the loads of the next 8 rows are issued before the arithmetic on the current 8
+  float4 h[kHeadRows][KV], hn[kHeadRows][KV];
+  float gl[kHeadRows], gn[kHeadRows];
+  auto load_rows = [&](int64_t base, float4 (&hh)[kHeadRows][KV], float (&gg)[kHeadRows]) {
 #pragma unroll
-    for (int o = 0; o < NO; ++o) g[o] = __ldg(dY + (int64_t)row * NO + o);  // same address in every lane: broadcast
-    float4 h[KV];
+    for (int r = 0; r < kHeadRows; ++r) {
+      const int64_t row = base + r;  // rows >= M contribute zeros and are not stored
 #pragma unroll
-    for (int v = 0; v < KV; ++v) h[v] = ldg_stream4(H + (int64_t)row * ldh + 128 * v + 4 * lane);
+      for (int v = 0; v < KV; ++v)
+        hh[r][v] = row < M ? ldg_stream4(H + row * ldh + 128 * v + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gg[r] = (row < M && lane < NO) ? __ldg(dY + row * NO + lane) : 0.f;
+    }
+  };
+  const int64_t stride = (int64_t)nwarps * kHeadRows;
+  load_rows((int64_t)warp * kHeadRows, h, gl);
+  for (int64_t base = (int64_t)warp * kHeadRows; base < M; base += stride) {
+    load_rows(base + stride, hn, gn);
 #pragma unroll
-    for (int v = 0; v < KV; ++v) {
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < kHeadRows; ++r) {
+      const int64_t row = base + r;
+      float4 d[KV];
+#pragma unroll
+      for (int v = 0; v < KV; ++v) d[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int o = 0; o < NO; ++o) {
-        d.x += g[o] * w[o][v].x, d.y += g[o] * w[o][v].y, d.z += g[o] * w[o][v].z, d.w += g[o] * w[o][v].w;
-        gw[o][v].x += g[o] * h[v].x, gw[o][v].y += g[o] * h[v].y, gw[o][v].z += g[o] * h[v].z, gw[o][v].w += g[o] * h[v].w;
+        const float g = __shfl_sync(0xffffffffu, gl[r], o);
+#pragma unroll
+        for (int v = 0; v < KV; ++v) {
+          d[v].x += g * w[o][v].x, d[v].y += g * w[o][v].y, d[v].z += g * w[o][v].z, d[v].w += g * w[o][v].w;
+          gw[o][v].x += g * h[r][v].x, gw[o][v].y += g * h[r][v].y, gw[o][v].z += g * h[r][v].z, gw[o][v].w += g * h[r][v].w;
+        }
       }
-      if (dH) {
-        d.x *= head_act_grad(h[v].x, act), d.y *= head_act_grad(h[v].y, act);
-        d.z *= head_act_grad(h[v].z, act), d.w *= head_act_grad(h[v].w, act);
-        *reinterpret_cast<float4*>(dH + (int64_t)row * lddh + 128 * v + 4 * lane) = d;
-        gd[v].x += d.x, gd[v].y += d.y, gd[v].z += d.z, gd[v].w += d.w;
+      if (dH && row < M) {
+#pragma unroll
+        for (int v = 0; v < KV; ++v) {
+          d[v].x *= head_act_grad(h[r][v].x, act), d[v].y *= head_act_grad(h[r][v].y, act);
+          d[v].z *= head_act_grad(h[r][v].z, act), d[v].w *= head_act_grad(h[r][v].w, act);
+          *reinterpret_cast<float4*>(dH + row * lddh + 128 * v + 4 * lane) = d[v];
+          gd[v].x += d[v].x, gd[v].y += d[v].y, gd[v].z += d[v].z, gd[v].w += d[v].w;
+        }
       }
+      gb += gl[r];
     }
 #pragma unroll
-    for (int o = 0; o < NO; ++o) gb[o] += g[o];
+    for (int r = 0; r < kHeadRows; ++r) {
+      gl[r] = gn[r];
+#pragma unroll
+      for (int v = 0; v < KV; ++v) h[r][v] = hn[r][v];
+    }
   }
   // block reduction of the weight-gradient partials through shared memory (fixed order over warps)
   __shared__ float red[kHeadThreads / 32][NO * K > 2048 ? 1 : NO * K];  // only instantiated with NO*K <= 2048
@@ -117,11 +172,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
     for (int q = 0; q < kHeadThreads / 32; ++q) s += red[q][i];
     out[i] = s;
   }
-  // bias gradient: every lane of a warp accumulated the same rows -> take lane 0 of each warp
+  // bias gradient: lane o of every warp holds its warp's share of column o
   __shared__ float redb[kHeadThreads / 32][NO];
-  if (lane == 0)
-#pragma unroll
-    for (int o = 0; o < NO; ++o) redb[wib][o] = gb[o];
+  if (lane < NO) redb[wib][lane] = gb;
   __syncthreads();
   if (threadIdx.x < NO) {
     float s = 0.f;
@@ -198,10 +251,11 @@ struct HeadBwd {
   }
 };
 
-static unsigned head_grid(int64_t M) {
-  int64_t blocks = (M + (kHeadThreads / 32) - 1) / (kHeadThreads / 32);
-  int64_t cap = (int64_t)sm_count() * 4;
-  if (cap > kHeadMaxBlocks) cap = kHeadMaxBlocks;
+static unsigned head_grid(int64_t M, int blocks_per_sm, int64_t max_blocks) {
+  const int64_t rows_per_block = (kHeadThreads / 32) * kHeadRows;
+  int64_t blocks = (M + rows_per_block - 1) / rows_per_block;
+  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  if (cap > max_blocks) cap = max_blocks;
   return (unsigned)(blocks < cap ? blocks : cap);
 }
 
@@ -219,7 +273,7 @@ int cusrl_b200_head_fwd_f32(const float* H, int64_t ldh, const float* W, const f
                 "head_fwd: latent dim must be a multiple of 128 and outputs <= %d", kHeadMaxNo);
   CUSRL_REQUIRE((ldh % 4) == 0 && ldh >= K && aligned_to(H, 16) && aligned_to(W, 16), CUSRL_B200_EALIGN,
                 "head_fwd: H and W must be 16-byte aligned with ldh a multiple of 4");
-  HeadFwd f{H, W, bias, ldh, Y, (int)M, head_grid(M), (cudaStream_t)stream};
+  HeadFwd f{H, W, bias, ldh, Y, (int)M, head_grid(M, 6, 1 << 20), (cudaStream_t)stream};
   return head_dispatch((int)No, (int)K, f);
 }
 
@@ -241,7 +295,7 @@ int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const 
   CUSRL_REQUIRE(!dbH || dH, CUSRL_B200_EINVAL, "head_bwd: dbH (column sums of dH) needs dH");
   CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_head_bwd_scratch_bytes(K, No), CUSRL_B200_ESCRATCH, "head_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
-  HeadBwd f{dY, H, W, ldh, lddh, act, (int)M, dH, (float*)scratch, head_grid(M), s};
+  HeadBwd f{dY, H, W, ldh, lddh, act, (int)M, dH, (float*)scratch, head_grid(M, 2, kHeadMaxBlocks), s};  // 176 registers: 2 blocks per SM
   if (int e = head_dispatch((int)No, (int)K, f)) return e;
   const int total = (int)(No * K + No + K);
   head_bwd_final_kernel<<<(total + 255) / 256, 256, 0, s>>>((const float*)scratch, (int)f.grid, (int)No, (int)K, dW, db,
