@@ -41,4 +41,4 @@ tot = sum(r[1] for r in rows)
 print(f"total device time {tot/1e3:.1f} ms over {args.iters} iteration(s)")
 print("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|")
 for k, t, n in sorted(rows, key=lambda r: -r[1])[:32]:
-    print(f"| `{k[:90]}` | {n} | {t/1e3:.2f} | {100*t/tot:.1f}% | {t/n:.1f} |")
+    print(f"| `{k[:230]}` | {n} | {t/1e3:.2f} | {100*t/tot:.1f}% | {t/n:.1f} |")
