@@ -6,9 +6,12 @@
 // layout type SWIZZLE_128B_BASE32B -- the only shared-memory layout the tensor core accepts for MN-major tf32
 // operands: 32-byte chunks XOR-ed with (row % 4), atoms of 4 rows x 128 B (LBO = chunk stride, SBO = 4-row group stride).
 //
-// Split-K over CTAs: every CTA owns one 128 x BN output tile and a contiguous slab of batch rows, keeps its fp32
-// accumulator in TMEM for the whole slab and finally writes a partial tile to a workspace; a second kernel adds
-// the partials in a fixed order (deterministic) into the gradient arena.  3xTF32 splits BOTH operands in shared
+// Split-K over CTAs: every CTA owns one 128 x BN output tile and a contiguous slab of batch rows and produces one
+// partial tile in a workspace; a second kernel adds the partials in a fixed order (deterministic) into the gradient
+// arena.  The tensor core's accumulator adder TRUNCATES, so a long accumulation chain drifts (7e-5 relative after
+// 10 k batch rows, measured): the slab is therefore cut into segments of WG_SEG k-blocks that alternate between two
+// TMEM accumulators, and the four epilogue warps fold every finished segment into the CTA's partial tile with
+// round-to-nearest fp32 adds (read-modify-write of 128 KB that stays in L2) while the next segment is running.  3xTF32 splits BOTH operands in shared
 // memory (they are activations / gradients, there is nothing to pre-split).
 #include "tc_common.cuh"
 
@@ -20,6 +23,7 @@ constexpr int WG_BM = 128;        // output features per tile (UMMA M)
 constexpr int WG_BKB = 32;        // batch rows per k-block
 constexpr int WG_CHUNK = 32;      // features per 128-byte swizzle span
 constexpr int WG_THREADS = 512;
+constexpr int WG_SEG = 64;        // k-blocks (= 1024 batch rows) accumulated inside the tensor core before a drain
 
 struct WgradParams {
   float* partial;        // [splits][num_m_tiles*128][ldp]
@@ -55,8 +59,9 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
   uint64_t* full = bars;
   uint64_t* split = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
-  uint64_t* tfull = bars + 3 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* tfull = bars + 3 * STAGES;   // [2] segment accumulator complete
+  uint64_t* tempty = tfull + 2;          // [2] segment accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x % (p.num_m_tiles * p.num_n_tiles);
@@ -78,10 +83,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
       mbar_init(&split[s], 8);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN <= 128 ? 128 : 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,6 +118,12 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
+        const int seg = kb / WG_SEG, a = seg & 1, kin = kb - seg * WG_SEG;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        if (kin == 0) {
+          mbar_wait(&tempty[a], ((seg >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA(s)), b_addr = smem_u32(sB(s));
@@ -119,8 +133,8 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
 #pragma unroll
         for (int k = 0; k < WG_BKB / 8; ++k) {
           const uint32_t off = (uint32_t)k * 1024;
-          mma_tf32_ss(tmem_base, make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1),
-                      make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          mma_tf32_ss(d_tmem, make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1),
+                      make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1), idesc, (kin > 0 || k > 0) ? 1u : 0u);
         }
         if (PASSES == 3) {
           mbar_wait(&split[s], ph);
@@ -130,41 +144,55 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
             const uint32_t off = (uint32_t)k * 1024;
             const uint64_t da = make_smem_desc_sw128(a_addr + off, CHUNK_BYTES, 512, 1);
             const uint64_t db = make_smem_desc_sw128(b_addr + off, CHUNK_BYTES, 512, 1);
-            mma_tf32_ss(tmem_base, make_smem_desc_sw128(alo_addr + off, CHUNK_BYTES, 512, 1), db, idesc, 1u);
-            mma_tf32_ss(tmem_base, da, make_smem_desc_sw128(blo_addr + off, CHUNK_BYTES, 512, 1), idesc, 1u);
+            mma_tf32_ss(d_tmem, make_smem_desc_sw128(alo_addr + off, CHUNK_BYTES, 512, 1), db, idesc, 1u);
+            mma_tf32_ss(d_tmem, da, make_smem_desc_sw128(blo_addr + off, CHUNK_BYTES, 512, 1), idesc, 1u);
           }
         }
         mma_commit(&empty[s]);
+        if (kin == WG_SEG - 1 || kb == num_kb - 1) mma_commit(&tfull[a]);
         if (++s == STAGES) s = 0, ph ^= 1;
       }
-      mma_commit(tfull);
     }
   } else if (warp >= 4 && warp < 8) {
-    // epilogue: one partial tile per CTA
+    // epilogue: fold every finished segment into this CTA's partial tile (the first one overwrites)
     const int ew = warp - 4;
     const int frow = f0 + ew * 32 + lane;  // output feature handled by this thread
     float* prow = p.partial + ((int64_t)sp * p.num_m_tiles * WG_BM + frow) * p.ldp + k0;
-    if (num_kb > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-    }
-    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int num_seg = (num_kb + WG_SEG - 1) / WG_SEG;
+    if (num_seg == 0) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (k0 + c0 + j < p.ldp)
-          *reinterpret_cast<uint4*>(prow + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      for (int c0 = 0; c0 < BN; c0 += 4)
+        if (k0 + c0 < p.ldp) *reinterpret_cast<uint4*>(prow + c0) = make_uint4(0u, 0u, 0u, 0u);
     }
-    tc_fence_before();
+#pragma unroll 1
+    for (int seg = 0; seg < num_seg; ++seg) {
+      const int a = seg & 1;
+      mbar_wait(&tfull[a], (seg >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, r);
+        float4 prev[8];
+        if (seg > 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            prev[j] = (k0 + c0 + 4 * j < p.ldp) ? *reinterpret_cast<const float4*>(prow + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+          if (seg > 0) v.x += prev[j].x, v.y += prev[j].y, v.z += prev[j].z, v.w += prev[j].w;
+          if (k0 + c0 + 4 * j < p.ldp) *reinterpret_cast<float4*>(prow + c0 + 4 * j) = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+    }
   } else if (PASSES == 3 && warp >= 8) {
     // splitter: lo = x - trunc_tf32(x) of both operand tiles, written to the mirror buffer at identical offsets
     const int t = threadIdx.x - 256;  // 0..255
@@ -194,7 +222,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN <= 128 ? 128 : 256);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
