@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import ctypes
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -376,7 +378,7 @@ def adam_step_(
 GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))  # 3 = 3xTF32 (fp32-equivalent), 1 = TF32
 
 _weights_epoch = 0
-_weight_cache: dict[int, tuple[tuple, dict[str, torch.Tensor]]] = {}
+_weight_cache: dict[int, tuple[tuple, dict[str, torch.Tensor], "weakref.ref"]] = {}
 
 
 def invalidate_weight_cache() -> None:
@@ -390,10 +392,18 @@ def prepared_weight(w: torch.Tensor) -> dict[str, torch.Tensor]:
     key = w.data_ptr()
     stamp = (_weights_epoch, w._version, tuple(w.shape))
     hit = _weight_cache.get(key)
-    if hit is not None and hit[0] == stamp:
+    # An entry is only trusted while the tensor object it was built from is alive: once that tensor is freed the
+    # allocator may hand its address (with an equal version counter) to a different matrix.
+    alive = hit is not None and hit[2]() is not None
+    if alive and hit[0] == stamp:
         return hit[1]
-    wp = weight_prep(w) if hit is None else weight_prep(w, out=hit[1])
-    _weight_cache[key] = (stamp, wp)
+    reuse = alive and hit[0][2] == stamp[2]
+    wp = weight_prep(w, out=hit[1]) if reuse else weight_prep(w)
+    owner = hit[2] if reuse else weakref.ref(w)
+    _weight_cache[key] = (stamp, wp, owner)
+    if len(_weight_cache) > 256:  # drop entries of freed tensors (tests create many short-lived matrices)
+        for k in [k for k, v in _weight_cache.items() if v[2]() is None]:
+            del _weight_cache[k]
     return wp
 
 
