@@ -68,18 +68,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const CUtens
   uint32_t r[32];
   tmem_ld_32x32(taddr, r);
   float4 e[8];
-  const int row = row0 + lane;
   if (EPI == EPI_BIAS_ACT) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       e[q] = (p.bias && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * q))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-  } else {
-    // row-per-lane 16-byte loads: the 8 loads of a lane cover one 128-byte line, L1 serves 7 of them
-    const float* arow = (p.aux && row < p.M) ? p.aux + (int64_t)row * p.ldaux + col0 : nullptr;
+  } else if (p.aux) {
+    // coalesced: load i of lane l fetches 16-byte unit (l % 8) of row 4 i + l / 8, i.e. every instruction reads four
+    // full 128-byte lines (row-per-lane loads touch 32 lines per instruction and saturated the L1 pipe, ncu)
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      e[q] = (arow && col0 + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(arow + 4 * q)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3), c = col0 + 4 * (lane & 7);
+      e[i] = (row0 + r < p.M && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.aux + (int64_t)(row0 + r) * p.ldaux + c))
+                                        : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
   }
   tmem_ld_wait();
   float4 v[8];
@@ -90,15 +92,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const CUtens
     if (EPI == EPI_BIAS_ACT) {
       v[q].x = act_fwd(v[q].x + e[q].x, p.act), v[q].y = act_fwd(v[q].y + e[q].y, p.act);
       v[q].z = act_fwd(v[q].z + e[q].z, p.act), v[q].w = act_fwd(v[q].w + e[q].w, p.act);
-    } else if (p.aux) {
-      v[q].x *= act_grad_from_output(e[q].x, p.act), v[q].y *= act_grad_from_output(e[q].y, p.act);
-      v[q].z *= act_grad_from_output(e[q].z, p.act), v[q].w *= act_grad_from_output(e[q].w, p.act);
     }
   }
   if (lane == 0) tma_store_wait_read();  // the previous chunk's store has finished reading the staging buffer
   __syncwarp();
   float4* srow = reinterpret_cast<float4*>(stg + lane * 128);
   const int sw = lane & 7;  // SWIZZLE_128B: 16-byte unit q of row r lives at unit q ^ (r % 8)
+  if (EPI == EPI_ACT_GRAD && p.aux) {
+    // transpose the coalesced aux fragments through the staging buffer: afterwards e[q] is unit q of this lane's row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3);
+      reinterpret_cast<float4*>(stg + r * 128)[(lane & 7) ^ (r & 7)] = e[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) e[q] = srow[q ^ sw];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[q].x *= act_grad_from_output(e[q].x, p.act), v[q].y *= act_grad_from_output(e[q].y, p.act);
+      v[q].z *= act_grad_from_output(e[q].z, p.act), v[q].w *= act_grad_from_output(e[q].w, p.act);
+    }
+  }
 #pragma unroll
   for (int q = 0; q < 8; ++q) srow[q ^ sw] = v[q];
   fence_proxy_async_smem();
