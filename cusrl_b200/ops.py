@@ -39,7 +39,15 @@ def launch_count() -> int:
     return _lib.KERNEL_LAUNCHES
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter is ~30x cheaper than building a
+    torch.cuda.Stream object, and this is called once per kernel launch)."""
+    if _raw_stream is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -1,0 +1,25 @@
+"""cProfile of the host side of PPO iterations at a tiny env count (GPU time negligible -> what remains is host overhead)."""
+import cProfile, pstats, sys, io
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import cusrl_b200 as C
+from bench import RolloutData, run_iteration
+dev = torch.device("cuda", 0)
+envs = 2048
+env = C.SyntheticEnvironment(envs, device=dev, seed=42)
+agent = C.anymal_c_rough_ppo(device=dev).from_environment(env)
+data = RolloutData(24, envs, dev, seed=1000, pinned_host=False)
+for _ in range(3):
+    run_iteration(agent, data)
+torch.cuda.synchronize()
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(5):
+    run_iteration(agent, data)
+torch.cuda.synchronize()
+pr.disable()
+for key in ("tottime", "cumulative"):
+    s = io.StringIO()
+    pstats.Stats(pr, stream=s).sort_stats(key).print_stats(45 if key == "tottime" else 60)
+    print("\n".join(l[:170] for l in s.getvalue().splitlines()[4:]))
