@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-envs", type=int, default=4096, help="environments of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline (oracle port on cuda:0)")
     return ap.parse_args()
 
 
@@ -151,7 +152,7 @@ def time_iterations(agent, data, steps: int, warmup: int, distributed: bool) -> 
 def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
     """Achieved HBM bandwidth of the GAE scan kernel, timed live: a CUDA graph of launches over rotating buffer
     sets whose footprint exceeds L2, CUDA events on the launching stream."""
-    from cusrl_b200 import ops
+    from cusrl_b200 import _lib, ops
 
     E = T * N
     n_sets = max(2, int(300e6 // (21 * E)) + 1)
@@ -190,7 +191,8 @@ def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
     peak = float(peaks["hbm_gbs"])
     return {"kernel": "gae_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
-            "bytes_per_launch": 21 * E, "us_per_launch": round(sec * 1e6, 2)}
+            "bytes_per_launch": 21 * E, "us_per_launch": round(sec * 1e6, 2),
+            "variant": dict(zip(("variant", "warps", "stages", "ctas_per_sm"), _lib._gae_variant_from_env()))}
 
 
 def gemm_roofline(rows: int, peaks: dict, which: str) -> dict:
@@ -232,30 +234,35 @@ def gemm_roofline(rows: int, peaks: dict, which: str) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_iteration_rate(envs: int, T: int, iters: int, warmup: int, threads: int) -> tuple[float, float]:
-    """env-steps/s of the CPU oracle port (the reference's PyTorch-CPU arithmetic restated, oracle/ppo_path.py)
-    on `threads` host threads, for a bounded sample of `envs` environments."""
+def cpu_port_iteration_rate(envs: int, T: int, iters: int, warmup: int, threads: int, device: str = "cpu") -> tuple[float, float]:
+    """env-steps/s of the oracle port (the reference's PyTorch arithmetic restated, oracle/ppo_path.py) on `threads`
+    host threads for a bounded sample of `envs` environments.  With device="cuda" the same eager PyTorch code (fp32
+    SGEMM, TF32 off, ~100 kernel launches per minibatch) runs on the GPU: the "reference's own 1-GPU PyTorch PPO"
+    denominator of BASELINE.json's target, reported as `torch_eager_gpu`."""
     from oracle import ppo_path as O
 
     torch.set_num_threads(threads)
     cfg = O.PpoConfig()
-    g = torch.Generator().manual_seed(0)
-    agent = O.OraclePpo(cfg, O.init_mlp_params_ref(cfg.obs_dim, cfg.act_dim, cfg.hidden, generator=g))
-    obs = torch.randn(T + 1, envs, cfg.obs_dim, generator=g)
-    reward = torch.randn(T, envs, 1, generator=g)
-    term = torch.rand(T, envs, 1, generator=g) < 0.01
-    trunc = torch.rand(T, envs, 1, generator=g) < 0.001
+    g = torch.Generator(device=device).manual_seed(0)
+    params = O.init_mlp_params_ref(cfg.obs_dim, cfg.act_dim, cfg.hidden, generator=torch.Generator().manual_seed(0))
+    agent = O.OraclePpo(cfg, {k: v.to(device) for k, v in params.items()})
+    obs = torch.randn(T + 1, envs, cfg.obs_dim, generator=g, device=device)
+    reward = torch.randn(T, envs, 1, generator=g, device=device)
+    term = torch.rand(T, envs, 1, generator=g, device=device) < 0.01
+    trunc = torch.rand(T, envs, 1, generator=g, device=device) < 0.001
 
     def iteration():
         leaves = {k: [] for k in ("observation", "action", "action_logp", "action_dist.mean", "action_dist.std", "value")}
         for t in range(T):
-            tr = agent.act(obs[t], torch.randn(envs, cfg.act_dim, generator=g))
+            tr = agent.act(obs[t], torch.randn(envs, cfg.act_dim, generator=g, device=device))
             for k in leaves:
                 leaves[k].append(tr[k])
         buf = {k: torch.stack(v) for k, v in leaves.items()}
         buf.update(next_observation=obs[1:], reward=reward.clone(), terminated=term, truncated=trunc, done=term | trunc)
-        perms = [torch.randperm(T * envs, generator=g) for _ in range(cfg.epochs)]
+        perms = [torch.randperm(T * envs, generator=g, device=device) for _ in range(cfg.epochs)]
         agent.update(buf, perms)
+        if device != "cpu":
+            torch.cuda.synchronize()
 
     for _ in range(warmup):
         iteration()
@@ -359,12 +366,24 @@ def main():
             cpu = {"value": round(rate, 1), "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_envs} envs x {T} steps, 1 warm-up + 2 timed iterations ({dt:.2f} s each)",
                    "thread_calibration_env_steps_per_s": calib}
+        eager = None
+        if not args.no_gpu_eager and world == 1:
+            # the same workload (all args.envs environments) through the oracle's eager PyTorch code on this GPU
+            del agent, env
+            torch.cuda.empty_cache()
+            try:
+                rate, dt = cpu_port_iteration_rate(args.envs, T, iters=2, warmup=1, threads=min(host_threads, 16), device="cuda")
+                eager = {"value": round(rate, 1), "unit": "env-steps/s", "kind": "port", "ms_per_step": round(dt * 1e3, 2),
+                         "note": "oracle/ppo_path.py (the reference's arithmetic in eager PyTorch, fp32 SGEMM, TF32 off) on "
+                                 f"cuda:0, {args.envs} envs x {T} steps, 1 warm-up + 2 timed iterations, wall clock + synchronize"}
+            except Exception as error:  # a baseline must never take the bench line down with it
+                eager = {"value": None, "error": f"{type(error).__name__}: {error}"[:300]}
         line = {
             "metric": "ppo_env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "roofline": roof, "roofline_gae": roof_gae, "cpu_baseline": cpu,
+            "clocks": clocks.summary(), "roofline": roof, "roofline_gae": roof_gae, "cpu_baseline": cpu, "torch_eager_gpu": eager,
             "last_metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")},
         }
     if distributed:

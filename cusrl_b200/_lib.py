@@ -41,6 +41,7 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
         [P, P, P, P, P, c_float, P, P, P, c_int64, c_int64, c_int64, c_double, c_double, c_double, P],
     ),
     "cusrl_b200_gae_set_config": (c_int, [c_int, c_int]),
+    "cusrl_b200_gae_set_variant": (c_int, [c_int, c_int, c_int, c_int]),
     "cusrl_b200_advantage_stats_scratch_bytes": (c_size_t, [c_int64]),
     "cusrl_b200_advantage_stats_f32": (c_int, [P, c_int64, c_int64, P, P, c_size_t, P]),
     "cusrl_b200_advantage_normalize_f32": (c_int, [P, c_int64, c_int64, P, c_float, P]),
@@ -110,8 +111,29 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.cusrl_b200_abi_version() != 1:
         raise RuntimeError("libcusrl_b200.so ABI version mismatch; rebuild with `python -m cusrl_b200.build -f`")
+    variant = _gae_variant_from_env()
+    if lib.cusrl_b200_gae_set_variant(*variant) != 0:
+        raise RuntimeError(f"CUSRL_B200_GAE_VARIANT={variant} is not a valid (variant, warps, stages, ctas_per_sm)")
     _lib = lib
     return lib
+
+
+# Kernel variant of the GAE scan installed at load time: (variant, warps, stages, ctas_per_sm) of
+# cusrl_b200_gae_set_variant.  Chosen from the round-1 sweep on a B200 (profiles/); CUSRL_B200_GAE_VARIANT="v,w,s,c"
+# overrides it for experiments.  Both variants are bit-identical.
+GAE_DEFAULT_VARIANT = (0, 0, 2, 2)
+
+
+def _gae_variant_from_env() -> tuple[int, int, int, int]:
+    import os
+
+    raw = os.environ.get("CUSRL_B200_GAE_VARIANT")
+    if not raw:
+        return GAE_DEFAULT_VARIANT
+    parts = tuple(int(x) for x in raw.split(","))
+    if len(parts) != 4:
+        raise RuntimeError("CUSRL_B200_GAE_VARIANT must be 'variant,warps,stages,ctas_per_sm'")
+    return parts  # type: ignore[return-value]
 
 
 KERNEL_LAUNCHES = 0  # launches of cusrl_b200 kernels issued through this binding (bench.py's gpu_launches)

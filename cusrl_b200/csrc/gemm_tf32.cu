@@ -303,6 +303,24 @@ int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return 0;
 }
 
+// Un-swizzled 2D map over a row-major [outer, inner] array of 1-byte or 4-byte elements (HBM-bound staging kernels:
+// rows land in shared memory exactly as they lie in global memory).
+int encode_tmap_2d_plain(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                         uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encoder();
+  CUSRL_REQUIRE(enc != nullptr, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  CUSRL_REQUIRE(elem_bytes == 1 || elem_bytes == 4, CUSRL_B200_EINVAL, "tensor map: element size must be 1 or 4 bytes");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUSRL_REQUIRE(r == CUDA_SUCCESS, CUSRL_B200_EDRIVER, "cuTensorMapEncodeTiled (plain) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace tc
 
 static int g_gemm_two_sm = 0;  // 1: cta_group::2 kernels (gemm2sm_tf32.cu), 0: 1-SM MMA + TMA multicast (this file)

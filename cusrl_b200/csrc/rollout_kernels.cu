@@ -2,6 +2,7 @@
 // All HBM-bound: lanes run along the contiguous env axis N of the time-major [T,N,Dv] leaves
 // (reference layout: template/buffer.py:144), the T-step recurrence lives in registers.
 #include "common.cuh"
+#include "gae_common.cuh"
 
 namespace cusrl_b200 {
 
@@ -65,22 +66,6 @@ struct VecLoad<4> {
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
-};
-
-struct GaeParams {
-  const float* reward;
-  const uint8_t* done;        // !FUSED: done flags; FUSED: terminated
-  const uint8_t* truncated;   // FUSED only
-  const float* value;
-  const float* next_value;    // !FUSED only
-  const float* boot;          // FUSED only, [N*Dv]
-  float* next_value_out;      // FUSED, optional
-  float* advantage;
-  float* ret;                 // optional
-  int64_t T, N, Dv;
-  float gamma, c_adv, c_ret;  // f32(gamma), f32(gamma*lamda), f32(gamma*lamda_value)
-  float termination_value;
-  int two_lambda;
 };
 
 template <int VEC, int U, bool FUSED, typename idx_t>
@@ -165,6 +150,8 @@ __global__ void __launch_bounds__(128, (U * VEC >= 16 ? 4 : 6)) gae_kernel(const
 }
 
 static int g_gae_vec = 1, g_gae_threads = 64;  // tuning knobs, see cusrl_b200_gae_set_config
+static int g_gae_variant = 0;                  // 0: register-resident LDG kernel, 1: TMA-staged kernel (gae_tma.cu)
+static GaeTmaConfig g_gae_tma_cfg = {0, 2, 2};  // see cusrl_b200_gae_set_variant
 
 template <int VEC, bool FUSED, typename idx_t>
 static void launch_gae_u(const GaeParams& p, unsigned grid, int threads, cudaStream_t s) {
@@ -194,6 +181,10 @@ static void launch_gae_u(const GaeParams& p, unsigned grid, int threads, cudaStr
 template <bool FUSED>
 static int launch_gae(const GaeParams& p, cudaStream_t s) {
   const int64_t C = p.N * p.Dv;
+  if (!FUSED && g_gae_variant == 1) {
+    const int rc = launch_gae_tma(p, g_gae_tma_cfg, s);
+    if (rc != CUSRL_B200_EUNSUPPORTED) return rc;  // otherwise: layout not TMA-able, use the LDG kernel below
+  }
   auto ok = [&](int vec) {
     if (p.Dv != 1 || (p.N % vec) != 0) return false;
     const size_t a = 4 * vec;
@@ -361,6 +352,14 @@ int cusrl_b200_gae_set_config(int vec, int threads) {
   if ((vec != 1 && vec != 2 && vec != 4) || threads < 32 || threads > 128 || (threads % 32)) return CUSRL_B200_EINVAL;
   g_gae_vec = vec;
   g_gae_threads = threads;
+  return 0;
+}
+
+int cusrl_b200_gae_set_variant(int variant, int warps, int stages, int ctas_per_sm) {
+  if ((variant != 0 && variant != 1) || warps < 0 || warps > 8 || stages < 1 || stages > 8 || ctas_per_sm < 1 || ctas_per_sm > 8)
+    return CUSRL_B200_EINVAL;
+  g_gae_variant = variant;
+  g_gae_tma_cfg = GaeTmaConfig{warps, stages, ctas_per_sm};
   return 0;
 }
 

@@ -229,5 +229,8 @@ enum TmapSwizzle { TMAP_SW128 = 0, TMAP_SW128_ATOM32 = 1, TMAP_SW64 = 2 };
 int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                        uint32_t box_inner, uint32_t box_outer, int swizzle = TMAP_SW128);
 
+int encode_tmap_2d_plain(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                         uint32_t box_inner, uint32_t box_outer);
+
 }  // namespace tc
 }  // namespace cusrl_b200

@@ -34,6 +34,9 @@ __all__ = [
 _scratch: dict[tuple[int, str], torch.Tensor] = {}
 
 
+GAE_DEFAULT_VARIANT = _lib.GAE_DEFAULT_VARIANT
+
+
 def launch_count() -> int:
     """Number of cusrl_b200 kernel launches issued so far by this process."""
     return _lib.KERNEL_LAUNCHES

@@ -79,6 +79,11 @@ int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, con
 /* Tuning knob for K1 (process-wide): columns per thread (1, 2 or 4) and threads per block
  * (multiple of 32, <= 128).  Results are bit-identical for every setting. */
 int cusrl_b200_gae_set_config(int vec, int threads);
+/* Kernel variant of cusrl_b200_gae_f32 (process-wide): 0 = register-resident scan fed by vector loads, 1 = TMA-staged
+ * scan (column tiles of 32*warps environments x T steps moved by bulk-tensor loads/stores through `stages`
+ * shared-memory stages, grid sized for `ctas_per_sm` resident CTAs; warps = 0 picks the tile width per problem).
+ * Variant 1 needs Dv == 1, N % 16 == 0 and 16-byte aligned leaves, otherwise variant 0 runs.  Bit-identical results. */
+int cusrl_b200_gae_set_variant(int variant, int warps, int stages, int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  advantage statistics + normalisation -- replaces AdvantageNormalization.normalize_,

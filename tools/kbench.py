@@ -98,15 +98,25 @@ def main():
         sets.append(d)
 
     if want("gae"):
-        for vec, threads in ((1, 64), (1, 128), (2, 64), (2, 128), (4, 64), (4, 128)):
+        gae_calls = [lambda d=d: ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95,
+                                         advantage=d["adv"], ret=d["ret"]) for d in sets]
+        lib.cusrl_b200_gae_set_variant(0, 0, 2, 2)
+        for vec, threads in ((1, 32), (1, 64), (1, 96), (1, 128), (2, 64), (4, 64)):
             lib.cusrl_b200_gae_set_config(vec, threads)
-            m, b = timer([lambda d=d: ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95,
-                                              advantage=d["adv"], ret=d["ret"]) for d in sets])
-            report("gae", 21 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
-            m, b = timer([lambda d=d: ops.gae_fused(d["reward"], d["term"], d["trunc"], d["value"], d["boot"], 0.99, 0.95,
-                                                    advantage=d["adv"], ret=d["ret"]) for d in sets])
-            report("gae_fused(18B/elt)", 18 * E, m, b, peak, which, vec=vec, threads=threads, T=T, N=N)
+            m, b = timer(gae_calls)
+            report("gae", 21 * E, m, b, peak, which, variant="ldg", vec=vec, threads=threads, T=T, N=N)
+            if (vec, threads) in ((1, 64), (1, 128)):
+                m, b = timer([lambda d=d: ops.gae_fused(d["reward"], d["term"], d["trunc"], d["value"], d["boot"], 0.99, 0.95,
+                                                        advantage=d["adv"], ret=d["ret"]) for d in sets])
+                report("gae_fused(18B/elt)", 18 * E, m, b, peak, which, variant="ldg", vec=vec, threads=threads, T=T, N=N)
         lib.cusrl_b200_gae_set_config(1, 64)
+        # TMA-staged variant: (warps per tile, stages, resident CTAs per SM the grid is sized for); warps 0 = automatic
+        for warps, stages, ctas in ((0, 2, 1), (0, 2, 2), (0, 2, 3), (0, 2, 4), (7, 1, 2), (7, 2, 1), (8, 1, 2), (8, 2, 1),
+                                    (5, 3, 1), (4, 2, 2), (4, 4, 1), (3, 2, 3), (2, 2, 4), (2, 4, 2), (1, 2, 8), (1, 4, 4), (1, 8, 2)):
+            lib.cusrl_b200_gae_set_variant(1, warps, stages, ctas)
+            m, b = timer(gae_calls)
+            report("gae", 21 * E, m, b, peak, which, variant="tma", warps=warps, stages=stages, ctas_per_sm=ctas, T=T, N=N)
+        lib.cusrl_b200_gae_set_variant(*ops.GAE_DEFAULT_VARIANT)
     if want("next_value"):
         m, b = timer([lambda d=d: ops.next_value(d["value"], d["term"], d["trunc"], d["boot"], out=d["nv"]) for d in sets])
         report("next_value", 10 * E, m, b, peak, which)
