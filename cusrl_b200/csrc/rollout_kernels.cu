@@ -69,7 +69,7 @@ struct VecLoad<4> {
 };
 
 template <int VEC, int U, bool FUSED, typename idx_t>
-__global__ void __launch_bounds__(128, (U * VEC >= 16 ? 4 : 6)) gae_kernel(const GaeParams p) {
+__global__ void __launch_bounds__(128, (U * VEC >= 40 ? 2 : (U * VEC >= 16 ? 4 : 6))) gae_kernel(const GaeParams p) {
   const idx_t C = (idx_t)(p.N * p.Dv);
   const idx_t N = (idx_t)p.N;
   const idx_t c0 = (idx_t)(blockIdx.x * (idx_t)blockDim.x + threadIdx.x) * VEC;
@@ -169,7 +169,9 @@ static void launch_gae_u(const GaeParams& p, unsigned grid, int threads, cudaStr
     else
       gae_kernel<1, 16, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
   } else if constexpr (VEC == 2) {
-    if (p.T <= 12 || p.T == 24)
+    if (p.T > 12 && p.T <= 24 && !FUSED)
+      gae_kernel<2, 24, FUSED, idx_t><<<grid, threads, 0, s>>>(p);  // whole rollout of two columns in registers
+    else if (p.T <= 12 || p.T == 24)
       gae_kernel<2, 12, FUSED, idx_t><<<grid, threads, 0, s>>>(p);
     else
       gae_kernel<2, 8, FUSED, idx_t><<<grid, threads, 0, s>>>(p);

@@ -74,7 +74,7 @@ def test_gae_vs_oracle_bit_exact(ops, T, N, Dv, lamda_value):
     assert torch.equal(ret.cpu(), ref_ret)
 
 
-@pytest.mark.parametrize("vec,threads", [(1, 128), (2, 64), (4, 128), (1, 32)])
+@pytest.mark.parametrize("vec,threads", [(1, 128), (2, 64), (2, 32), (4, 128), (1, 32), (1, 96)])
 def test_gae_all_vector_widths(ops, vec, threads):
     from cusrl_b200 import _lib
 

@@ -101,7 +101,7 @@ def main():
         gae_calls = [lambda d=d: ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95,
                                          advantage=d["adv"], ret=d["ret"]) for d in sets]
         lib.cusrl_b200_gae_set_variant(0, 0, 2, 2)
-        for vec, threads in ((1, 32), (1, 64), (1, 96), (1, 128), (2, 64), (4, 64)):
+        for vec, threads in ((1, 32), (1, 64), (1, 96), (1, 128), (2, 32), (2, 64), (4, 32), (4, 64)):
             lib.cusrl_b200_gae_set_config(vec, threads)
             m, b = timer(gae_calls)
             report("gae", 21 * E, m, b, peak, which, variant="ldg", vec=vec, threads=threads, T=T, N=N)
@@ -117,6 +117,14 @@ def main():
             m, b = timer(gae_calls)
             report("gae", 21 * E, m, b, peak, which, variant="tma", warps=warps, stages=stages, ctas_per_sm=ctas, T=T, N=N)
         lib.cusrl_b200_gae_set_variant(*ops.GAE_DEFAULT_VARIANT)
+    if want("gae") or want("copy"):
+        # context: a device-to-device copy moving the same 33 MB (16.5 MB read + 16.5 MB written) on rotating buffers
+        half = (21 * E // 2 + 15) // 16 * 16
+        srcs = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(S)]
+        dsts = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(S)]
+        m, b = timer([lambda a=a, c=c: c.copy_(a) for a, c in zip(srcs, dsts)])
+        report("torch_copy_same_bytes", 2 * half, m, b, peak, which)
+        del srcs, dsts
     if want("next_value"):
         m, b = timer([lambda d=d: ops.next_value(d["value"], d["term"], d["trunc"], d["boot"], out=d["nv"]) for d in sets])
         report("next_value", 10 * E, m, b, peak, which)
