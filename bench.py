@@ -54,6 +54,16 @@ def measured_peaks() -> tuple[dict, str]:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(key: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel at exactly this problem size, from
+    the committed `ncu --set full` captures (profiles/ncu_traffic.json names the capture each figure comes from)."""
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    if not f.exists():
+        return None
+    entry = json.loads(f.read_text()).get(key)
+    return None if entry is None else entry["dram_bytes"]
+
+
 class ClockSampler:
     """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
 
@@ -190,7 +200,8 @@ def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
     achieved = 21 * E / sec / 1e9
     peak = float(peaks["hbm_gbs"])
     return {"kernel": "gae_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+            "frac": round(achieved / peak, 4),
+            "traffic": ncu_traffic(f"gae_f32@T={T},N={N},variant={_lib._gae_variant_from_env()[0]}"), "peak_source": which,
             "bytes_per_launch": 21 * E, "us_per_launch": round(sec * 1e6, 2),
             "variant": dict(zip(("variant", "warps", "stages", "ctas_per_sm"), _lib._gae_variant_from_env()))}
 
@@ -227,7 +238,8 @@ def gemm_roofline(rows: int, peaks: dict, which: str) -> dict:
     achieved = flops / sec / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])) / 2.0
     return {"kernel": "gemm_tf32_kernel<256,3,0> (3xTF32 forward, 512->256)", "bound": "tensor", "achieved": round(achieved, 1),
-            "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
+            "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+            "traffic": ncu_traffic(f"gemm_tf32_kernel<256,3,0>@M={M},K={K},N={N}"),
             "peak_source": f"{which}: bf16_tflops_sustained / 2 (TF32 rate)", "flops_per_launch": flops,
             "executed_tf32_flops_per_launch": 3 * flops, "executed_frac": round(3 * achieved / peak, 4),
             "hbm_gbs": round(M * (K + N) * 4 / sec / 1e9, 1), "us_per_launch": round(sec * 1e6, 2), "rows": M}

@@ -116,21 +116,75 @@ class FlatAdam:
         self._clip_pending = False
         ops.invalidate_weight_cache()  # the Adam kernel rewrote the parameters through raw pointers
 
+    # ---- checkpoints: the on-disk format is torch.optim.Adam's, i.e. the reference's (template/agent.py:283-330) ----
+    _TORCH_ADAM_GROUP_DEFAULTS = {"amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                                  "differentiable": False, "fused": None, "decoupled_weight_decay": False}
+
     def state_dict(self) -> dict[str, Any]:
-        return {
-            "step": self.step_count,
-            "exp_avg": self.exp_avg.clone(),
-            "exp_avg_sq": self.exp_avg_sq.clone(),
-            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
-        }
+        """``{"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}`` exactly as ``torch.optim.Adam`` (the
+        reference's optimizer) writes it: per-parameter moment tensors in parameter order, ``step`` as an fp32 scalar
+        tensor, the group carrying ``param_names`` -- so checkpoints move between the reference agent and this one."""
+        state: dict[int, dict[str, torch.Tensor]] = {}
+        if self.step_count > 0:
+            for i, (p, off) in enumerate(zip(self.arena.params, self.arena.offsets)):
+                n = p.numel()
+                state[i] = {
+                    "step": torch.tensor(float(self.step_count), dtype=torch.float32),
+                    "exp_avg": self.exp_avg[off : off + n].view_as(p).clone(),
+                    "exp_avg_sq": self.exp_avg_sq[off : off + n].view_as(p).clone(),
+                }
+        groups = []
+        for g in self.param_groups:
+            out = {k: v for k, v in g.items() if k != "params"}
+            for k, v in self._TORCH_ADAM_GROUP_DEFAULTS.items():
+                out.setdefault(k, v)
+            out["params"] = list(range(len(g["params"])))
+            groups.append(out)
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, state: dict[str, Any]) -> None:
-        self.step_count = int(state["step"])
-        self.exp_avg.copy_(state["exp_avg"])
-        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        """Accepts a ``torch.optim.Adam`` state dict (from the reference or from :meth:`state_dict`); parameters are
+        matched by ``param_names`` when the checkpoint has them, by position otherwise.  The flat form written by
+        earlier versions of this class (``step`` / ``exp_avg`` / ``exp_avg_sq`` arenas) still loads."""
+        if "state" not in state:  # legacy flat form
+            self.step_count = int(state["step"])
+            self.exp_avg.copy_(state["exp_avg"])
+            self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        else:
+            saved_groups = state.get("param_groups", [])
+            saved_names = [n for g in saved_groups for n in g.get("param_names", [])]
+            saved_ids = [i for g in saved_groups for i in g.get("params", [])]
+            if len(saved_ids) != len(self.arena.params):
+                raise ValueError(f"loaded state dict has {len(saved_ids)} parameters, the optimizer has {len(self.arena.params)}")
+            if saved_names and len(saved_names) == len(saved_ids):
+                if sorted(saved_names) != sorted(self.arena.names):
+                    raise ValueError("loaded state dict names parameters this optimizer does not have: "
+                                     f"{sorted(set(saved_names) ^ set(self.arena.names))[:4]}")
+                by_name = dict(zip(saved_names, saved_ids))
+                order = [by_name[n] for n in self.arena.names]
+            else:
+                order = saved_ids
+            entries = state["state"]
+            steps = set()
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            for p, off, key in zip(self.arena.params, self.arena.offsets, order):
+                entry = entries.get(key, entries.get(str(key)))
+                if entry is None:
+                    continue
+                if tuple(entry["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {key} has shape {tuple(entry['exp_avg'].shape)}, parameter has {tuple(p.shape)}")
+                n = p.numel()
+                self.exp_avg[off : off + n].copy_(entry["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off : off + n].copy_(entry["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(entry["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): FlatAdam keeps one step count")
+            self.step_count = steps.pop() if steps else 0
         ops.invalidate_weight_cache()
         for g, saved in zip(self.param_groups, state.get("param_groups", [])):
-            g.update({k: v for k, v in saved.items() if k not in ("params", "param_names")})
+            g.update({k: v for k, v in saved.items() if k in ("lr", "betas", "eps", "weight_decay")})
+            g["betas"] = tuple(g["betas"])
 
 
 class AdamFactory:

@@ -172,3 +172,37 @@ def test_adaptive_lr_schedule_host_logic():
     scales = [hook._compute_scale(0.03) for _ in range(2)]
     assert scales[0] is None and scales[1] == pytest.approx(torch.exp(torch.tensor(-0.2 * 0.6931471805599453)).item())
     assert hook._accumulated_log_error == 0.0 and hook._count == 0
+
+
+def test_optimizer_state_dict_is_torch_adam_shaped_and_round_trips():
+    """Checkpoint layout (reference template/agent.py:283-330 stores `optimizer.state_dict()` of torch.optim.Adam)."""
+    spec = C.EnvironmentSpec(8, 235, 12, autoreset=True, final_state_is_missing=True)
+    agent = C.anymal_c_rough_ppo(device="cpu")(spec)
+    opt = agent.optimizer
+    assert opt.state_dict()["state"] == {}                       # like torch: no state before the first step
+    g = torch.Generator().manual_seed(0)
+    opt.exp_avg.copy_(torch.randn(opt.exp_avg.shape, generator=g))
+    opt.exp_avg_sq.copy_(torch.rand(opt.exp_avg_sq.shape, generator=g))
+    opt.step_count = 7
+    opt.param_groups[0]["lr"] = 5e-4
+    sd = opt.state_dict()
+    names = sd["param_groups"][0]["param_names"]
+    assert names == [n for n, _ in agent.named_parameters()] and sd["param_groups"][0]["params"] == list(range(len(names)))
+    assert sd["state"][0]["exp_avg"].shape == (512, 235) and float(sd["state"][3]["step"]) == 7.0
+    # a stock torch.optim.Adam over equally shaped parameters accepts it
+    stock = torch.optim.Adam([torch.nn.Parameter(torch.zeros_like(p)) for p in agent.parameters()], lr=1e-3)
+    stock.load_state_dict({"state": sd["state"], "param_groups": [{k: v for k, v in sd["param_groups"][0].items() if k != "param_names"}]})
+    assert stock.param_groups[0]["lr"] == 5e-4
+    # and a second agent restores bit-identical moments, matching by name even when the checkpoint order differs
+    other = C.anymal_c_rough_ppo(device="cpu")(spec).optimizer
+    perm = list(reversed(range(len(names))))
+    shuffled = {"state": {j: sd["state"][i] for j, i in enumerate(perm)},
+                "param_groups": [{**sd["param_groups"][0], "param_names": [names[i] for i in perm], "params": list(range(len(names)))}]}
+    other.load_state_dict(shuffled)
+    assert other.step_count == 7 and other.param_groups[0]["lr"] == 5e-4
+    for p, off in zip(other.arena.params, other.arena.offsets):
+        n = p.numel()
+        assert torch.equal(other.exp_avg[off:off + n], opt.exp_avg[off:off + n])
+        assert torch.equal(other.exp_avg_sq[off:off + n], opt.exp_avg_sq[off:off + n])
+    with pytest.raises(ValueError, match="parameters"):
+        other.load_state_dict({"state": {}, "param_groups": [{"params": [0, 1], "param_names": ["a", "b"]}]})

@@ -44,3 +44,58 @@ def test_plugin_registers_and_reference_trainer_accepts_the_agent(reference):
     assert trainer.agent.parallelism == 8 and trainer.agent.observation_dim == 235
     assert [h.name for h in trainer.agent.hook][:3] == ["module_initialization", "value_computation",
                                                         "generalized_advantage_estimation"]
+
+
+def test_checkpoints_move_between_the_reference_agent_and_this_one(reference):
+    """`agent.state_dict()` has the reference's on-disk layout -- module keys and shapes,
+    hook state, and the optimizer in torch.optim.Adam's format with `param_names` -- so a checkpoint trained with the
+    reference loads here (parameters + Adam moments land in the flat arenas) and one written here loads there."""
+    import torch
+
+    import cusrl_b200 as C
+    from cusrl.preset.ppo import PpoAgentFactory as RefFactory
+
+    kwargs = dict(num_steps_per_update=4, actor_hidden_dims=(16, 8), critic_hidden_dims=(16, 8), activation_fn="ELU",
+                  lr=1e-3, orthogonal_init=False, desired_kl_divergence=0.015, device="cpu")
+    spec = reference.EnvironmentSpec(num_instances=8, observation_dim=5, action_dim=2, autoreset=True, final_state_is_missing=True)
+    torch.manual_seed(0)
+    ref_agent = RefFactory(**kwargs)(spec)
+    for _ in range(4):
+        ref_agent.act(torch.randn(8, 5))
+        ref_agent.step(torch.randn(8, 5), torch.randn(8, 1), torch.zeros(8, 1, dtype=torch.bool), torch.zeros(8, 1, dtype=torch.bool))
+    ref_agent.update()  # 20 Adam steps: the optimizer state is populated
+    ref_sd = ref_agent.state_dict()
+
+    ours = C.PpoAgentFactory(**kwargs)(C.EnvironmentSpec(8, 5, 2, autoreset=True, final_state_is_missing=True))
+    our_sd = ours.state_dict()
+    for module in ("actor", "critic"):
+        assert list(our_sd[module]) == list(ref_sd[module])
+        assert all(our_sd[module][k].shape == ref_sd[module][k].shape for k in ref_sd[module])
+    assert list(our_sd["hook"]) == list(ref_sd["hook"])
+    assert our_sd["optimizer"]["param_groups"][0]["param_names"] == ref_sd["optimizer"]["param_groups"][0]["param_names"]
+    assert set(ref_sd["optimizer"]["param_groups"][0]) <= set(our_sd["optimizer"]["param_groups"][0])
+
+    # reference -> here
+    ours.load_state_dict({k: v for k, v in ref_sd.items() if k != "grad_scaler"})
+    for (name, p), (rname, rp) in zip(ours.named_parameters(), ref_agent.named_parameters()):
+        assert name == rname and torch.equal(p.detach(), rp.detach())
+    opt = ours.optimizer
+    assert opt.step_count == 20 and opt.param_groups[0]["lr"] == ref_sd["optimizer"]["param_groups"][0]["lr"]
+    flat = opt.flat_param
+    for i, (p, off) in enumerate(zip(opt.arena.params, opt.arena.offsets)):
+        assert p.data_ptr() == flat[off:].data_ptr()                                  # still a view of the arena
+        ref_state = ref_sd["optimizer"]["state"][i]
+        assert torch.equal(opt.exp_avg[off:off + p.numel()].view_as(p), ref_state["exp_avg"])
+        assert torch.equal(opt.exp_avg_sq[off:off + p.numel()].view_as(p), ref_state["exp_avg_sq"])
+    assert ours.hook["adaptive_lr_schedule"].state_dict() == ref_sd["hook"]["adaptive_lr_schedule"]
+
+    # here -> reference: torch.optim.Adam accepts what FlatAdam writes
+    back = ours.state_dict()
+    fresh = RefFactory(**kwargs)(spec)
+    fresh.load_state_dict({**back, "grad_scaler": ref_sd["grad_scaler"]})
+    for (_, p), (_, rp) in zip(fresh.named_parameters(), ref_agent.named_parameters()):
+        assert torch.equal(p.detach(), rp.detach())
+    got = fresh.optimizer.state_dict()["state"]
+    for i, st in ref_sd["optimizer"]["state"].items():
+        assert float(got[i]["step"]) == float(st["step"]) == 20.0
+        assert torch.equal(got[i]["exp_avg"], st["exp_avg"]) and torch.equal(got[i]["exp_avg_sq"], st["exp_avg_sq"])
