@@ -370,6 +370,11 @@ def main():
     line = None
     if rank == 0:
         roof_gae = gae_roofline(T, N, peaks, which)
+        # the same kernel on 16x the columns: a 33 MB launch lasts ~9 us, of which ~2.6 us are launch ramp and drain that
+        # any kernel of this size pays (a device copy of the same bytes reaches 0.66 of the 1 GiB copy rate); the larger
+        # launch shows the kernel's streaming rate without that fixed cost.  Context only: `frac` above is the metric.
+        big = gae_roofline(T, 16 * N, peaks, which)
+        roof_gae["same_kernel_16x_columns"] = {k: big[k] for k in ("achieved", "frac", "bytes_per_launch", "us_per_launch")}
         roof = gemm_roofline(T * N // 4, peaks, which)  # one minibatch of this rank (4 minibatches per epoch)
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -1,7 +1,10 @@
 // K1, TMA-staged variant: hook/on_policy/gae.py:8-20,85-110 on [T,N,1] leaves.
 //
 // The register-resident kernel (rollout_kernels.cu) issues every load of a column through the LSU; at 65536 x 24 it
-// stops at ~55 % of the HBM copy rate.  Here the bytes move through the TMA unit instead:
+// stops at ~55 % of the HBM copy rate.  This variant moves the bytes through the TMA unit instead.  MEASURED (round 1,
+// profiles/r01_kbench_gae_variants.jsonl): 9.5-10.4 us per launch against 9.3-9.5 us for the register kernel and 7.7 us
+// for a device-to-device copy of the same 33 MB -- the request path is not what limits a launch this short, so the
+// register kernel stays the default and this one is selectable (cusrl_b200_gae_set_variant) for larger rollouts.
 //   * a CTA of W warps owns column tiles of C = 32 W environments; one tile = the boxes {C columns x T rows} of
 //     reward / value / next_value (fp32) and done (u8), i.e. the WHOLE rollout of C environments (13 T C bytes);
 //   * an elected thread issues the four bulk-tensor loads of a tile into one shared-memory stage (mbarrier
@@ -110,9 +113,15 @@ __global__ void __launch_bounds__(256) gae_tma_kernel(const __grid_constant__ CU
       tma_store_2d(&tmA, R, col0, 0);
       if (p.has_ret) tma_store_2d(&tmRet, V, col0, 0);
       tma_store_commit();
-      // refill the stage of the PREVIOUS tile once its stores have finished reading it (one store group may stay in
-      // flight, so this never waits for the group committed just above)
-      if (i >= 1 && i - 1 + p.stages < my_tiles) {
+      if (p.stages == 1) {
+        // a single stage: the next tile can only be requested once the stores above have finished reading it
+        if (i + 1 < my_tiles) {
+          tma_store_wait_read();
+          issue_load(i + 1);
+        }
+      } else if (i >= 1 && i - 1 + p.stages < my_tiles) {
+        // refill the stage of the PREVIOUS tile once its stores have finished reading it (one store group may stay in
+        // flight, so this never waits for the group committed just above); tile i + 1 is already on its way
         bulk_wait_read_le1();
         issue_load(i - 1 + p.stages);
       }

@@ -14,17 +14,17 @@ step() {  # name timeout cmd...
 }
 for s in "$@"; do
   case $s in
-    tma_tests)  step tma_tests 300 python -m pytest tests/test_gae_tma_gpu.py -x -q -m gpu ;;
+    tma_tests)  step tma_tests 90 python -m pytest tests/test_gae_tma_gpu.py -x -q -m gpu ;;
     gae_tests)  step gae_tests 300 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k gae ;;
     kbench_gae) step kbench_gae 240 python tools/kbench.py --only gae ;;
     kbench)     step kbench 300 python tools/kbench.py ;;
-    ncu_gae)    step ncu_gae 300 ncu --set full --clock-control none --import-source on -k regex:gae -o "$out/gae" -f python tools/ncu_gae.py ;;
-    tests)      step tests 1200 python -m pytest tests -x -q -m gpu ;;
-    bench)      step bench 900 python bench.py ;;
+    ncu_gae)    step ncu_gae 110 ncu --set full --clock-control none --import-source on -k regex:gae -o "$out/gae" -f python tools/ncu_gae.py ;;
+    tests)      step tests 600 python -m pytest tests -x -q -m gpu --timeout 120 ;;
+    bench)      step bench 300 python bench.py ;;
     bench_ref)  step bench_ref 600 python bench.py --impl reference --steps 2 --warmup 1 ;;
     smoke)      step smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
     configs)    step configs 400 python tools/config_fps.py ;;
-    iter)       step iter 300 python tools/iter_profile.py ;;
+    iter)       step iter 70 python tools/iter_profile.py ;;
     launches)   step launches 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-eager ;;
     *) echo "unknown step $s" ;;
   esac
