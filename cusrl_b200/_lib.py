@@ -42,6 +42,7 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     ),
     "cusrl_b200_gae_set_config": (c_int, [c_int, c_int]),
     "cusrl_b200_gae_set_variant": (c_int, [c_int, c_int, c_int, c_int]),
+    "cusrl_b200_gae_set_schedule": (c_int, [c_int]),
     "cusrl_b200_advantage_stats_scratch_bytes": (c_size_t, [c_int64]),
     "cusrl_b200_advantage_stats_f32": (c_int, [P, c_int64, c_int64, P, P, c_size_t, P]),
     "cusrl_b200_advantage_normalize_f32": (c_int, [P, c_int64, c_int64, P, c_float, P]),
@@ -114,6 +115,8 @@ def load() -> ctypes.CDLL:
     variant = _gae_variant_from_env()
     if lib.cusrl_b200_gae_set_variant(*variant) != 0:
         raise RuntimeError(f"CUSRL_B200_GAE_VARIANT={variant} is not a valid (variant, warps, stages, ctas_per_sm)")
+    if lib.cusrl_b200_gae_set_schedule(GAE_DEFAULT_SCHEDULE) != 0:
+        raise RuntimeError(f"GAE_DEFAULT_SCHEDULE={GAE_DEFAULT_SCHEDULE} is not a valid schedule")
     _lib = lib
     return lib
 
@@ -122,6 +125,8 @@ def load() -> ctypes.CDLL:
 # cusrl_b200_gae_set_variant.  Chosen from the round-1 sweep on a B200 (profiles/); CUSRL_B200_GAE_VARIANT="v,w,s,c"
 # overrides it for experiments.  Both variants are bit-identical.
 GAE_DEFAULT_VARIANT = (0, 0, 2, 2)
+# Instruction schedule of the register-resident GAE kernel (cusrl_b200_gae_set_schedule): 1 = exact-length kernel.
+GAE_DEFAULT_SCHEDULE = int(__import__("os").environ.get("CUSRL_B200_GAE_SCHEDULE", "1"))
 
 
 def _gae_variant_from_env() -> tuple[int, int, int, int]:

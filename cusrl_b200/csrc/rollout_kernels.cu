@@ -149,6 +149,79 @@ __global__ void __launch_bounds__(128, (U * VEC >= 40 ? 2 : (U * VEC >= 16 ? 4 :
   }
 }
 
+// Exact-length variant (schedule 1): T is a template parameter, so no step is predicated, the addresses are a base
+// pointer plus t * pitch, and the loads are issued in ASCENDING time order while the recurrence starts at t = T-1 --
+// its first instruction depends on the loads issued LAST, so the compiler cannot hoist arithmetic into the load
+// sequence.  (ncu on the chunked kernel above: ptxas placed the first FMUL of step T-1 after 24 of the 96 loads; the warp
+// then sat on the long scoreboard with three quarters of its requests not yet issued -- two DRAM round trips.)
+// 64 threads x 7 blocks = 448 threads per SM hold all 65536 columns of the BASELINE rollout in one wave on 148 SMs
+// and leave 144 registers per thread (the 96 loaded values + addresses fit without spilling).
+template <int T_>
+__global__ void __launch_bounds__(64, 7) gae_exact_kernel(const GaeParams p) {
+  const int64_t C = p.N * p.Dv;
+  const int64_t c0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c0 >= C) return;
+  const int64_t n0 = p.Dv == 1 ? c0 : c0 / p.Dv;  // done broadcasts over Dv (gae.py:19)
+  const float* __restrict__ rp = p.reward + c0;
+  const float* __restrict__ vp = p.value + c0;
+  const float* __restrict__ np = p.next_value + c0;
+  const uint8_t* __restrict__ dp = p.done + n0;
+  float r[T_], v[T_], nv[T_];
+  uint8_t d[T_];
+#pragma unroll
+  for (int t = 0; t < T_; ++t) {
+    r[t] = ldg_stream(rp + t * C);
+    v[t] = ldg_stream(vp + t * C);
+    nv[t] = ldg_stream(np + t * C);
+  }
+#pragma unroll
+  for (int t = 0; t < T_; ++t) d[t] = __ldg(dp + t * p.N);
+  // the flags are the last requests issued; folding them into one mask frees T-1 registers for the recurrence
+  uint32_t done_mask = 0;
+#pragma unroll
+  for (int t = 0; t < T_; ++t) done_mask |= (d[t] ? 1u : 0u) << t;
+  float* __restrict__ ap = p.advantage + c0;
+  float* __restrict__ tp = p.ret ? p.ret + c0 : nullptr;
+  float adv_next = 0.f, adv2_next = 0.f;
+#pragma unroll
+  for (int t = T_ - 1; t >= 0; --t) {
+    // gae.py:17  advantage = reward + next_value * gamma - value
+    const float delta = __fsub_rn(__fadd_rn(r[t], __fmul_rn(nv[t], p.gamma)), v[t]);
+    float a = delta, a2 = delta;
+    if (t != T_ - 1) {
+      // gae.py:19  advantage[t] += not_done[t] * (gamma*lamda) * advantage[t+1]
+      const bool done = (done_mask >> t) & 1u;
+      a = __fadd_rn(delta, __fmul_rn(done ? 0.f : p.c_adv, adv_next));
+      if (p.two_lambda) a2 = __fadd_rn(delta, __fmul_rn(done ? 0.f : p.c_ret, adv2_next));
+    }
+    adv_next = a, adv2_next = a2;
+    ap[t * C] = a;
+    // gae.py:99-110  return = value + advantage (or the lamda_value scan)
+    if (tp) tp[t * C] = __fadd_rn(v[t], p.two_lambda ? a2 : a);
+  }
+}
+
+static int g_gae_schedule = 0;  // 0: chunked kernel above, 1: exact-length kernel when T has an instantiation
+
+template <int T_>
+static void launch_gae_exact(const GaeParams& p, int threads, cudaStream_t s) {
+  const int64_t C = p.N * p.Dv;
+  if (threads > 64) threads = 64;  // the kernel's launch bound
+  gae_exact_kernel<T_><<<(unsigned)((C + threads - 1) / threads), threads, 0, s>>>(p);
+}
+
+// returns false when T has no exact-length instantiation
+static bool try_launch_gae_exact(const GaeParams& p, int threads, cudaStream_t s) {
+  switch (p.T) {
+    case 8: launch_gae_exact<8>(p, threads, s); return true;
+    case 12: launch_gae_exact<12>(p, threads, s); return true;
+    case 16: launch_gae_exact<16>(p, threads, s); return true;
+    case 24: launch_gae_exact<24>(p, threads, s); return true;
+    case 32: launch_gae_exact<32>(p, threads, s); return true;
+    default: return false;
+  }
+}
+
 static int g_gae_vec = 1, g_gae_threads = 64;  // tuning knobs, see cusrl_b200_gae_set_config
 static int g_gae_variant = 0;                  // 0: register-resident LDG kernel, 1: TMA-staged kernel (gae_tma.cu)
 static GaeTmaConfig g_gae_tma_cfg = {0, 2, 2};  // see cusrl_b200_gae_set_variant
@@ -187,6 +260,8 @@ static int launch_gae(const GaeParams& p, cudaStream_t s) {
     const int rc = launch_gae_tma(p, g_gae_tma_cfg, s);
     if (rc != CUSRL_B200_EUNSUPPORTED) return rc;  // otherwise: layout not TMA-able, use the LDG kernel below
   }
+  if (!FUSED && g_gae_schedule == 1 && g_gae_vec == 1 && try_launch_gae_exact(p, g_gae_threads, s))
+    return check_launch("gae_exact_kernel");
   auto ok = [&](int vec) {
     if (p.Dv != 1 || (p.N % vec) != 0) return false;
     const size_t a = 4 * vec;
@@ -354,6 +429,12 @@ int cusrl_b200_gae_set_config(int vec, int threads) {
   if ((vec != 1 && vec != 2 && vec != 4) || threads < 32 || threads > 128 || (threads % 32)) return CUSRL_B200_EINVAL;
   g_gae_vec = vec;
   g_gae_threads = threads;
+  return 0;
+}
+
+int cusrl_b200_gae_set_schedule(int schedule) {
+  if (schedule != 0 && schedule != 1) return CUSRL_B200_EINVAL;
+  g_gae_schedule = schedule;
   return 0;
 }
 

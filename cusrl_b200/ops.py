@@ -35,6 +35,7 @@ _scratch: dict[tuple[int, str], torch.Tensor] = {}
 
 
 GAE_DEFAULT_VARIANT = _lib.GAE_DEFAULT_VARIANT
+GAE_DEFAULT_SCHEDULE = _lib.GAE_DEFAULT_SCHEDULE
 
 
 def launch_count() -> int:

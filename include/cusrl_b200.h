@@ -79,6 +79,10 @@ int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, con
 /* Tuning knob for K1 (process-wide): columns per thread (1, 2 or 4) and threads per block
  * (multiple of 32, <= 128).  Results are bit-identical for every setting. */
 int cusrl_b200_gae_set_config(int vec, int threads);
+/* Instruction schedule of the register-resident K1 kernel (process-wide): 0 = chunked kernel with a run-time T,
+ * 1 = exact-length kernel (T in {8, 12, 16, 24, 32}: every load issued before the first dependent instruction), other
+ * T fall back to 0.  Bit-identical results. */
+int cusrl_b200_gae_set_schedule(int schedule);
 /* Kernel variant of cusrl_b200_gae_f32 (process-wide): 0 = register-resident scan fed by vector loads, 1 = TMA-staged
  * scan (column tiles of 32*warps environments x T steps moved by bulk-tensor loads/stores through `stages`
  * shared-memory stages, grid sized for `ctas_per_sm` resident CTAs; warps = 0 picks the tile width per problem).

@@ -92,6 +92,32 @@ def test_gae_all_vector_widths(ops, vec, threads):
         lib.cusrl_b200_gae_set_config(1, 64)
 
 
+@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("T", [8, 12, 16, 24, 32, 7, 33])
+@pytest.mark.parametrize("N,Dv,threads", [(4096, 1, 64), (1001, 1, 32), (130, 3, 128)])
+def test_gae_both_schedules_bit_exact(ops, schedule, T, N, Dv, threads):
+    """Chunked kernel (run-time T) and exact-length kernel (T in {8,12,16,24,32}; others fall back): same bits as the
+    oracle for both lamda settings, with and without the return, ragged N and vector rewards."""
+    from cusrl_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(T * 131 + N + Dv)
+    reward, value, nv = (torch.randn(T, N, Dv, generator=g) for _ in range(3))
+    done = torch.rand(T, N, 1, generator=g) < 0.08
+    assert lib.cusrl_b200_gae_set_schedule(schedule) == 0 and lib.cusrl_b200_gae_set_config(1, threads) == 0
+    try:
+        for lamda_value in (None, 0.6):
+            ref_adv, ref_ret = O.advantage_and_return_ref(reward, done, value, nv, 0.99, 0.95, lamda_value)
+            adv, ret = ops.gae(reward.to(DEV), done.to(DEV), value.to(DEV), nv.to(DEV), 0.99, 0.95, lamda_value)
+            assert torch.equal(adv.cpu(), ref_adv) and torch.equal(ret.cpu(), ref_ret)
+        adv_only, none = ops.gae(reward.to(DEV), done.to(DEV), value.to(DEV), nv.to(DEV), 0.99, 0.95, compute_return=False)
+        assert none is None and torch.equal(adv_only.cpu(), O.advantage_and_return_ref(reward, done, value, nv, 0.99, 0.95, None)[0])
+    finally:
+        lib.cusrl_b200_gae_set_schedule(ops.GAE_DEFAULT_SCHEDULE)
+        lib.cusrl_b200_gae_set_config(1, 64)
+    assert lib.cusrl_b200_gae_set_schedule(2) != 0
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_next_value_golden(ops, golden, tag):
     g = golden("next_value")

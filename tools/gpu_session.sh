@@ -25,7 +25,7 @@ for s in "$@"; do
     smoke)      step smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
     configs)    step configs 400 python tools/config_fps.py ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
-    launches)   step launches 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-eager ;;
+    launches)   step launches 230 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-eager ;;
     *) echo "unknown step $s" ;;
   esac
 done

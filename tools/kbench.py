@@ -101,6 +101,13 @@ def main():
         gae_calls = [lambda d=d: ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95,
                                          advantage=d["adv"], ret=d["ret"]) for d in sets]
         lib.cusrl_b200_gae_set_variant(0, 0, 2, 2)
+        lib.cusrl_b200_gae_set_config(1, 64)
+        for schedule, threads in ((1, 64), (1, 32), (0, 64), (0, 32), (1, 64), (0, 64)):
+            lib.cusrl_b200_gae_set_schedule(schedule)
+            lib.cusrl_b200_gae_set_config(1, threads)
+            m, b = timer(gae_calls)
+            report("gae", 21 * E, m, b, peak, which, variant="ldg", schedule=schedule, vec=1, threads=threads, T=T, N=N)
+        lib.cusrl_b200_gae_set_schedule(0)
         for vec, threads in ((1, 32), (1, 64), (1, 96), (1, 128), (2, 32), (2, 64), (4, 32), (4, 64)):
             lib.cusrl_b200_gae_set_config(vec, threads)
             m, b = timer(gae_calls)
@@ -117,6 +124,7 @@ def main():
             m, b = timer(gae_calls)
             report("gae", 21 * E, m, b, peak, which, variant="tma", warps=warps, stages=stages, ctas_per_sm=ctas, T=T, N=N)
         lib.cusrl_b200_gae_set_variant(*ops.GAE_DEFAULT_VARIANT)
+        lib.cusrl_b200_gae_set_schedule(ops.GAE_DEFAULT_SCHEDULE)
     if want("gae") or want("copy"):
         # context: a device-to-device copy moving the same 33 MB (16.5 MB read + 16.5 MB written) on rotating buffers
         half = (21 * E // 2 + 15) // 16 * 16
