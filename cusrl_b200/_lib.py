@@ -125,8 +125,9 @@ def load() -> ctypes.CDLL:
 # cusrl_b200_gae_set_variant.  Chosen from the round-1 sweep on a B200 (profiles/); CUSRL_B200_GAE_VARIANT="v,w,s,c"
 # overrides it for experiments.  Both variants are bit-identical.
 GAE_DEFAULT_VARIANT = (0, 0, 2, 2)
-# Instruction schedule of the register-resident GAE kernel (cusrl_b200_gae_set_schedule): 1 = exact-length kernel.
-GAE_DEFAULT_SCHEDULE = int(__import__("os").environ.get("CUSRL_B200_GAE_SCHEDULE", "1"))
+# Instruction schedule of the register-resident GAE kernel (cusrl_b200_gae_set_schedule): 0 = chunked kernel, 1 =
+# exact-length kernel.  Measured on a B200 (profiles/r01_kbench_gae_variants.jsonl): 9.2-9.3 us vs 9.5 us -> 0.
+GAE_DEFAULT_SCHEDULE = int(__import__("os").environ.get("CUSRL_B200_GAE_SCHEDULE", "0"))
 
 
 def _gae_variant_from_env() -> tuple[int, int, int, int]:

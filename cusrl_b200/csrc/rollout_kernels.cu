@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(128, (U * VEC >= 40 ? 2 : (U * VEC >= 16 ? 4 :
 // pointer plus t * pitch, and the loads are issued in ASCENDING time order while the recurrence starts at t = T-1 --
 // its first instruction depends on the loads issued LAST, so the compiler cannot hoist arithmetic into the load
 // sequence.  (ncu on the chunked kernel above: ptxas placed the first FMUL of step T-1 after 24 of the 96 loads; the warp
-// then sat on the long scoreboard with three quarters of its requests not yet issued -- two DRAM round trips.)
+// then sat on the long scoreboard with three quarters of its requests not yet issued.)  MEASURED: 9.5 us per launch at
+// 65536 x 24 against 9.2-9.3 us for the chunked kernel -- with 14 warps per SM the other warps cover that stall, and the
+// launch is bounded by its fixed ramp / drain cost (profiles/r01_gae_ncu.md).  Kept selectable, not the default.
 // 64 threads x 7 blocks = 448 threads per SM hold all 65536 columns of the BASELINE rollout in one wave on 148 SMs
 // and leave 144 registers per thread (the 96 loaded values + addresses fit without spilling).
 template <int T_>
