@@ -108,6 +108,33 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
   }
 }
 
+// Same update with the learning rate and the step count read from DEVICE memory, so that a captured CUDA graph of the
+// optimizer step stays valid while both change between replays.  The bias corrections 1 - beta^step are evaluated in
+// double like torch does on the host (adam.py), then rounded to float exactly as the host path rounds them.
+__global__ void __launch_bounds__(256) adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                            float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                            const float* __restrict__ coef_dev, const float* __restrict__ lr_dev,
+                                                            const int64_t* __restrict__ step_dev, float beta1, float beta2,
+                                                            float eps, float weight_decay) {
+  const float coef = coef_dev ? *coef_dev : 1.f;
+  const double step = (double)*step_dev;
+  const float bc1 = (float)(1.0 - pow((double)beta1, step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+  const float step_size = *lr_dev / bc1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i] * coef;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = gi + weight_decay * pi;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
 }  // namespace cusrl_b200
 
 using namespace cusrl_b200;
@@ -189,6 +216,22 @@ int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, fl
                                                                        beta1, beta2, eps, weight_decay, (float)bc1,
                                                                        (float)sqrt(bc2));
   return check_launch("adam_step_kernel");
+}
+
+int cusrl_b200_adam_step_dev_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 const float* coef_dev, const float* lr_dev, const int64_t* step_dev, float beta1, float beta2,
+                                 float eps, float weight_decay, void* stream) {
+  CUSRL_REQUIRE(param && grad && exp_avg && exp_avg_sq && lr_dev && step_dev, CUSRL_B200_EINVAL, "adam_step_dev: null pointer");
+  CUSRL_REQUIRE(n >= 0, CUSRL_B200_EINVAL, "adam_step_dev: negative size");
+  CUSRL_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, CUSRL_B200_EINVAL,
+                "adam_step_dev: invalid betas / eps");
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_step_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, coef_dev, lr_dev,
+                                                                           step_dev, beta1, beta2, eps, weight_decay);
+  return check_launch("adam_step_dev_kernel");
 }
 
 }  // extern "C"

@@ -36,6 +36,28 @@ class Metric:
 class Metrics:
     def __init__(self):
         self._data: dict[str, Metric] = {}
+        # while a CUDA graph is being captured the merge into the running means is postponed: its weights
+        # (count / total) are host numbers that differ from replay to replay (template/graphs.py)
+        self._deferred: list[tuple[str, torch.Tensor, int]] | None = None
+
+    def begin_deferred(self) -> None:
+        """Until :meth:`end_deferred`, recorded (name, mean tensor, count) triples are collected instead of merged."""
+        self._deferred = []
+
+    def end_deferred(self) -> list[tuple[str, torch.Tensor, int]]:
+        out, self._deferred = self._deferred or [], None
+        return out
+
+    def apply(self, entries) -> None:
+        """Merge triples collected in deferred mode (their tensors hold the values of the latest graph replay)."""
+        for name, mean, count in entries:
+            self._data.setdefault(name, Metric()).update(mean, count)
+
+    def _merge(self, name: str, mean: torch.Tensor, count: int) -> None:
+        if self._deferred is not None:
+            self._deferred.append((name, mean, count))
+        else:
+            self._data.setdefault(name, Metric()).update(mean, count)
 
     def clear(self) -> None:
         self._data.clear()
@@ -69,11 +91,11 @@ class Metrics:
                 raise ValueError(f"Failed to update metric '{name}'") from error
             if value.numel() == 0:
                 continue
-            self._data.setdefault(name, Metric()).update(value.mean(), value.numel())
+            self._merge(name, value.mean(), value.numel())
 
     def record_mean(self, name: str, mean: torch.Tensor, count: int) -> None:
         """Record a mean that a kernel already reduced over `count` elements (0-dim device tensor)."""
-        self._data.setdefault(name, Metric()).update(mean.detach().reshape(()), count)
+        self._merge(name, mean.detach().reshape(()), count)
 
     def summary(self, prefix: str = "") -> dict[str, float]:
         if prefix and not prefix.endswith("/"):

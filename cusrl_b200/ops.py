@@ -29,6 +29,7 @@ __all__ = [
     "grad_sumsq_",
     "clip_coef",
     "adam_step_",
+    "adam_step_dev_",
 ]
 
 _scratch: dict[tuple[int, str], torch.Tensor] = {}
@@ -55,11 +56,16 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    """Every tensor that crosses the C ABI must live on the GPU: there is no CPU or PyTorch fallback for any kernel."""
+    if not t.is_cuda:
+        raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+
+
 def _ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> int | None:
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+    _require_cuda(t, name)
     if not t.is_contiguous():
         raise ValueError(f"cusrl_b200: '{name}' must be contiguous")
     if dtype is not None and t.dtype != dtype:
@@ -232,8 +238,8 @@ def gather_rows(
     n_src = None
     arr = (GatherField * len(fields))()
     for k, (src, dst) in enumerate(fields):
-        if not (src.is_cuda and dst.is_cuda):
-            raise RuntimeError("cusrl_b200: gather_rows needs CUDA tensors (no CPU fallback exists)")
+        _require_cuda(src, "gather_rows source")
+        _require_cuda(dst, "gather_rows destination")
         if src.dtype != dst.dtype:
             raise TypeError("gather_rows: src/dst dtype mismatch")
         s2 = src.reshape(src.shape[0], -1) if src.is_contiguous() else src
@@ -385,6 +391,29 @@ def adam_step_(
     _lib.check(code, "adam_step")
 
 
+def adam_step_dev_(
+    param: torch.Tensor,
+    grad: torch.Tensor,
+    exp_avg: torch.Tensor,
+    exp_avg_sq: torch.Tensor,
+    step_dev: torch.Tensor,
+    lr_dev: torch.Tensor,
+    betas: tuple[float, float] = (0.9, 0.999),
+    eps: float = 1e-8,
+    weight_decay: float = 0.0,
+    coef: torch.Tensor | None = None,
+) -> None:
+    """:func:`adam_step_` with the step count (int64 [1]) and learning rate (float32 [1]) read from device memory, the
+    form a captured CUDA graph can replay while both keep changing."""
+    f32 = torch.float32
+    code = _lib.load().cusrl_b200_adam_step_dev_f32(
+        _ptr(param, f32, "param"), _ptr(grad, f32, "grad"), _ptr(exp_avg, f32, "exp_avg"),
+        _ptr(exp_avg_sq, f32, "exp_avg_sq"), param.numel(), _ptr(coef, f32, "coef"), _ptr(lr_dev, f32, "lr_dev"),
+        _ptr(step_dev, torch.int64, "step_dev"), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), _stream(),
+    )  # fmt: skip
+    _lib.check(code, "adam_step_dev")
+
+
 # ---------------------------------------------------------------------------------------------- K6
 # Dense layers on tcgen05 (csrc/gemm_tf32.cu, csrc/gemm_wgrad_tf32.cu) and SIMT heads (csrc/head_kernels.cu).
 GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))  # 3 = 3xTF32 (fp32-equivalent), 1 = TF32
@@ -453,8 +482,7 @@ def weight_prep(w: torch.Tensor, transposed: bool = True, out: dict[str, torch.T
 
 def _rows(t: torch.Tensor, name: str) -> tuple[int, int]:
     """(data_ptr, leading dimension) of a 2-D tensor with unit inner stride."""
-    if not t.is_cuda:
-        raise RuntimeError(f"cusrl_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+    _require_cuda(t, name)
     if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
         raise ValueError(f"cusrl_b200: '{name}' must be a 2-D float32 tensor with a dense last dim")
     return t.data_ptr(), t.stride(0)

@@ -10,6 +10,7 @@ flushed with one device-to-host copy, and ``autocast`` / ``compile`` are refused
 
 from __future__ import annotations
 
+import os
 from collections.abc import Iterable, Mapping
 from contextlib import contextmanager, nullcontext
 from dataclasses import dataclass
@@ -137,6 +138,9 @@ class ActorCritic:
         self.metrics = Metrics()
         self.iteration = 0
         self.step_index = 0
+        # opt-in CUDA-graph replay of the train step (template/graphs.py); not part of the reference's surface
+        self.cuda_graphs = os.environ.get("CUSRL_B200_CUDA_GRAPHS", "0") not in ("", "0")
+        self._train_step_graphs = None
 
         self.actor_factory, self.critic_factory, self.optimizer_factory = actor_factory, critic_factory, optimizer_factory
         self.hook = HookComposite(hooks)
@@ -243,7 +247,26 @@ class ActorCritic:
         return summary
 
     def _train_step(self, metadata: dict[str, Any], batch: dict[str, Any]) -> None:
-        """actor_critic.py:302-320 (no GradScaler: fp32 only)."""
+        """actor_critic.py:302-320 (no GradScaler: fp32 only).  With ``cuda_graphs`` the two halves of the step are
+        captured once per batch layout and replayed (template/graphs.py); the gradient allreduce between them always
+        runs eagerly, so the multi-GPU data path is the same in both modes."""
+        if self.cuda_graphs and self.device.type == "cuda":
+            if self._train_step_graphs is None:
+                from .graphs import TrainStepGraphs
+
+                self._train_step_graphs = TrainStepGraphs(self)
+            self._train_step_graphs(metadata, batch)
+        else:
+            self._train_step_eager(metadata, batch)
+
+    def _train_step_eager(self, metadata: dict[str, Any], batch: dict[str, Any]) -> None:
+        objectives = self._train_step_forward_backward(metadata, batch)
+        if objectives is not None:
+            distributed.reduce_gradients(self.optimizer)
+        self._train_step_optimize(metadata, batch, objectives)
+
+    def _train_step_forward_backward(self, metadata: dict[str, Any], batch: dict[str, Any]):
+        """First half of the step: objectives of every hook, their sum in dict order, backward into the flat arena."""
         self.actor.clear_intermediate_repr()
         self.critic.clear_intermediate_repr()
         self.hook.pre_objective(metadata, batch)
@@ -252,7 +275,11 @@ class ActorCritic:
             loss = sum(objectives.values())
             self.optimizer.zero_grad()
             loss.backward()
-            distributed.reduce_gradients(self.optimizer)
+        return objectives
+
+    def _train_step_optimize(self, metadata: dict[str, Any], batch: dict[str, Any], objectives) -> None:
+        """Second half, after the cross-rank gradient average: clip, Adam, records, post-objective hooks."""
+        if objectives is not None:
             self.hook.pre_optim(self.optimizer)
             self.optimizer.step()
             self.hook.post_optim()

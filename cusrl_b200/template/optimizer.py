@@ -84,6 +84,32 @@ class FlatAdam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.clip_coef = torch.ones(1, dtype=torch.float32, device=dev)
         self._clip_pending = False
+        # device-resident copies of the step count and learning rate (see use_device_scalars)
+        self.step_dev: torch.Tensor | None = None
+        self.lr_dev: torch.Tensor | None = None
+        self._lr_uploaded: float | None = None
+
+    # ---- device-resident scalars: what a captured CUDA graph of the optimizer step needs ----------------------------
+    def use_device_scalars(self) -> None:
+        """From now on ``step()`` reads the step count and the learning rate from device memory
+        (``cusrl_b200_adam_step_dev_f32``), so a CUDA graph containing the step stays valid across replays.  The step
+        counter is advanced on the device by the step itself; the learning rate is uploaded by
+        :meth:`sync_device_scalars`, which callers invoke OUTSIDE any capture."""
+        if self.step_dev is None:
+            dev = self.arena.flat.device
+            self.step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
+            self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._lr_uploaded = None
+        self.sync_device_scalars()
+
+    def sync_device_scalars(self) -> None:
+        """Upload the learning rate if a schedule changed it (one fill, no host sync).  Never call while capturing."""
+        if self.step_dev is None:
+            return
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_uploaded:
+            self.lr_dev.fill_(lr)
+            self._lr_uploaded = lr
 
     # the two arenas, exposed for the collective (distributed.reduce_gradients) and for kernels
     @property
@@ -110,9 +136,19 @@ class FlatAdam:
     def step(self) -> None:
         g = self.param_groups[0]
         self.step_count += 1
-        ops.adam_step_(
-            self.arena.flat, self.arena.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
-            g["betas"], g["eps"], g["weight_decay"], coef=self.clip_coef if self._clip_pending else None)
+        coef = self.clip_coef if self._clip_pending else None
+        if self.step_dev is not None:
+            if float(g["lr"]) != self._lr_uploaded:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("FlatAdam: the learning rate changed inside a CUDA-graph capture; call "
+                                       "sync_device_scalars() before capturing")
+                self.sync_device_scalars()
+            self.step_dev.add_(1)
+            ops.adam_step_dev_(self.arena.flat, self.arena.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
+                               self.lr_dev, g["betas"], g["eps"], g["weight_decay"], coef=coef)
+        else:
+            ops.adam_step_(self.arena.flat, self.arena.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                           g["lr"], g["betas"], g["eps"], g["weight_decay"], coef=coef)
         self._clip_pending = False
         ops.invalidate_weight_cache()  # the Adam kernel rewrote the parameters through raw pointers
 
@@ -182,6 +218,8 @@ class FlatAdam:
                 raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): FlatAdam keeps one step count")
             self.step_count = steps.pop() if steps else 0
         ops.invalidate_weight_cache()
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step_count)
         for g, saved in zip(self.param_groups, state.get("param_groups", [])):
             g.update({k: v for k, v in saved.items() if k in ("lr", "betas", "eps", "weight_decay")})
             g["betas"] = tuple(g["betas"])

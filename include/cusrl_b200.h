@@ -178,6 +178,12 @@ int cusrl_b200_clip_coef_f32(const double* sumsq_dev, float max_norm, float* nor
 int cusrl_b200_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                              int64_t n, const float* coef_dev, float lr, float beta1, float beta2,
                              float eps, float weight_decay, int64_t step, void* stream);
+/* The same step with the learning rate (*lr_dev, f32) and the step count (*step_dev, i64, >= 1) read from device
+ * memory: a CUDA graph that contains the optimizer step stays valid while both change between replays. */
+int cusrl_b200_adam_step_dev_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                 int64_t n, const float* coef_dev, const float* lr_dev,
+                                 const int64_t* step_dev, float beta1, float beta2, float eps,
+                                 float weight_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K6  dense layers of the MLP actor/critic on tcgen05 tensor cores (TMA-fed, TMEM accumulators) --

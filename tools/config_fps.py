@@ -19,6 +19,8 @@ from cusrl_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--graphs", action="store_true", help="replay the train step from CUDA graphs (agent.cuda_graphs = True)")
+ap.add_argument("--only", default="")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 
@@ -41,12 +43,15 @@ def rnd(envs):
 for name, envs, make in (("mlp_ppo_4096", 4096, mlp), ("lstm_ppo_4096", 4096, lstm), ("mlp_ppo_rnd_16384", 16384, rnd)):
     torch.manual_seed(42)
     env = C.SyntheticEnvironment(envs, device=dev, seed=42)
+    if args.only and args.only not in name:
+        continue
     agent = make(envs).from_environment(env)
+    agent.cuda_graphs = args.graphs
     data = RolloutData(24, envs, dev, seed=1000, pinned_host=False)
     n0 = ops.launch_count()
     seconds, metrics = time_iterations(agent, data, args.steps, args.warmup, False)
     launches = (ops.launch_count() - n0) // (args.steps + args.warmup)
-    print(json.dumps({"config": name, "envs": envs, "rollout_steps": 24, "env_steps_per_s": round(args.steps * 24 * envs / seconds, 1),
+    print(json.dumps({"config": name, "cuda_graphs": args.graphs, "envs": envs, "rollout_steps": 24, "env_steps_per_s": round(args.steps * 24 * envs / seconds, 1),
                       "ms_per_iteration": round(seconds / args.steps * 1e3, 3), "gpu_launches_per_iteration": int(launches),
                       "metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")}}), flush=True)
     del agent, data, env
