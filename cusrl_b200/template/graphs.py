@@ -1,5 +1,10 @@
 """CUDA-graph capture of the per-minibatch train step (opt-in: ``agent.cuda_graphs = True`` or ``CUSRL_B200_CUDA_GRAPHS=1``).
 
+STATUS: EXPERIMENTAL -- written at the end of round 1 and NOT yet run to completion on a B200 (the GPU budget ran out
+during its first run).  Its control flow is exercised on the CPU with ``torch.cuda.graph`` mocked
+(``tools/host_overhead_cpu.py --graphs``); the default (eager) train step does not touch this module.  First item of the
+next round: ``CUSRL_B200_TEST_GRAPHS=1 pytest -m gpu tests/test_graphs_gpu.py``.
+
 Why.  One train step of the MLP preset is ~60 kernel launches of this library plus ~100 small PyTorch launches, issued
 from Python at ~10-20 us each.  At 65536 environments on one GPU the kernels are long enough to hide that; when the
 environments are split over 8 ranks (8192 per rank, BASELINE.json's scale-out configuration) or the rollout is small
