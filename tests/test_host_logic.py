@@ -263,3 +263,51 @@ def test_graph_runner_control_flow_with_mocked_capture():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "graph runner: 1 capture(s), 58 replays, optimizer step_count 60" in res.stdout, res.stdout
+
+
+def test_gradient_clipping_groups_host_logic(monkeypatch):
+    """Reference cusrl_test/hook/on_policy/test_gradient_clipping.py:29-50 on the flat arena: parameters are grouped by
+    the longest matching name prefix, each group is clipped to its own limit, the pre-clip norm is recorded as
+    `grad_norm/<prefix or default>`.  The three kernels the hook launches are replaced by their one-line definitions
+    (include/cusrl_b200.h, K9) so the HOST logic -- prefix matching, arena ranges, record keys -- runs on the CPU; the
+    kernels themselves are covered by tests/test_kernels_gpu.py."""
+    from types import SimpleNamespace
+
+    from cusrl_b200 import ops
+    from cusrl_b200.metrics import Metrics
+    from cusrl_b200.template.optimizer import FlatAdam
+
+    def grad_sumsq_(grad, sumsq):
+        return sumsq.add_(grad.double().square().sum())
+
+    def clip_coef(sumsq, max_norm, norm, coef):
+        norm.copy_(sumsq.sqrt().float())
+        coef.copy_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+
+    monkeypatch.setattr(ops, "grad_sumsq_", grad_sumsq_)
+    monkeypatch.setattr(ops, "clip_coef", clip_coef)
+    monkeypatch.setattr(ops, "scale_", lambda x, scale: x.mul_(scale))
+
+    model = torch.nn.ModuleDict({"actor": torch.nn.Linear(2, 2), "critic": torch.nn.Linear(2, 1),
+                                 "actor_extra": torch.nn.Linear(3, 1)})
+    optimizer = FlatAdam(model.named_parameters(), lr=0.1)
+    hook = C.GradientClipping(max_grad_norm=0.5, actor=0.25)
+    hook.agent = SimpleNamespace(metrics=Metrics())
+    optimizer.flat_grad.fill_(1.0)
+    hook.pre_optim(optimizer)
+
+    def norm(prefixes):
+        return torch.cat([p.grad.reshape(-1) for n, p in model.named_parameters() if n.split(".")[0] in prefixes]).norm().item()
+
+    assert norm({"actor"}) == pytest.approx(0.25, abs=1e-5)                 # 6 ones: sqrt(6) clipped to 0.25
+    assert norm({"critic", "actor_extra"}) == pytest.approx(0.5, abs=1e-5)  # "actor_extra" is NOT under prefix "actor"
+    summary = hook.agent.metrics.summary()
+    assert set(summary) == {"grad_norm/actor", "grad_norm/default"}
+    assert summary["grad_norm/actor"] == pytest.approx(6 ** 0.5, rel=1e-6)
+    assert summary["grad_norm/default"] == pytest.approx(7 ** 0.5, rel=1e-6)
+    # longest prefix wins; unlimited groups are left alone
+    hook = C.GradientClipping(max_grad_norm=None, **{"actor": 1.0, "actor.bias": None})
+    assert list(hook.groups) == ["actor.bias", "actor"] and hook._match_prefix("actor.bias") == "actor.bias"
+    assert hook._match_prefix("actor.weight") == "actor" and hook._match_prefix("actors.weight") == ""
+    with pytest.raises(ValueError, match="'max_grad_norm' must be non-negative"):
+        C.GradientClipping(max_grad_norm=-1.0)
