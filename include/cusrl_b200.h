@@ -17,7 +17,11 @@
  *   - tensors are dense row-major with the reference's layouts: rollout leaves are time-major
  *     [T, N, C] (template/buffer.py:144), minibatch leaves are [B, C];
  *   - bool leaves (terminated / truncated / done) are passed as uint8 (torch.bool storage);
- *   - stateless and re-entrant: safe to call from several host threads on different streams.
+ *   - compute entry points are stateless and re-entrant: safe to call from several host threads on
+ *     different streams.  The only process-wide state are the *_set_config / *_set_variant /
+ *     *_set_schedule tuning knobs (they select between bit-identical kernels and are meant to be set
+ *     once at start-up) and one-time per-kernel attribute setup, which assumes the reference's
+ *     process model: ONE device per process (utils/config.py:37-38, cuda:{LOCAL_RANK}).
  */
 #ifndef CUSRL_B200_H_
 #define CUSRL_B200_H_
