@@ -24,8 +24,9 @@ for s in "$@"; do
     bench_ref)  step bench_ref 600 python bench.py --impl reference --steps 2 --warmup 1 ;;
     smoke)      step smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
     configs)    step configs 400 python tools/config_fps.py ;;
-    tests_all)  step tests_all 60 python -m pytest tests -q -m gpu --timeout 40 ;;
-    graphs_fps) step graphs_fps 40 bash -c "python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --graphs" ;;
+    tests_all)  step tests_all 600 python -u -m pytest tests -q -m gpu --timeout 120 ;;
+    graphs_tests) step graphs_tests 300 env CUSRL_B200_TEST_GRAPHS=1 python -u -m pytest tests/test_graphs_gpu.py -x -v -m gpu --timeout 120 ;;
+    graphs_fps) step graphs_fps 120 bash -c "python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --graphs" ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
     launches)   step launches 230 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-gpu-eager ;;
     *) echo "unknown step $s" ;;
