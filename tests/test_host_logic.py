@@ -311,3 +311,29 @@ def test_gradient_clipping_groups_host_logic(monkeypatch):
     assert hook._match_prefix("actor.weight") == "actor" and hook._match_prefix("actors.weight") == ""
     with pytest.raises(ValueError, match="'max_grad_norm' must be non-negative"):
         C.GradientClipping(max_grad_norm=-1.0)
+
+
+def test_metric_is_exact_for_one_record_and_a_weighted_mean_for_many():
+    """Reference utils/metrics.py:11-40 semantics: mean of the recorded means weighted by element count."""
+    from cusrl_b200.metrics import Metric, Metrics
+
+    m = Metric()
+    assert m.count == 0 and m.mean.numel() == 0
+    x = torch.tensor(0.1234567)
+    m.update(x, 1_572_864)
+    assert torch.equal(m.mean, x)                       # a metric recorded once per update is kept bit-exactly
+    x.add_(1.0)
+    assert float(m.mean) == pytest.approx(0.1234567)    # ... and does not alias the recorded tensor
+    g = torch.Generator().manual_seed(0)
+    values, counts = torch.randn(20, generator=g), [393216] * 19 + [17]
+    m = Metric()
+    for v, c in zip(values, counts):
+        m.update(v, c)
+    expected = float((values.double() * torch.tensor(counts, dtype=torch.float64)).sum() / sum(counts))
+    assert m.count == sum(counts) and float(m.mean) == pytest.approx(expected, rel=1e-6)
+    m.update(torch.tensor(5.0), 0)                      # empty records are ignored
+    assert m.count == sum(counts)
+    metrics = Metrics()
+    metrics.record(a=torch.tensor([1.0, 3.0]), b=2.0, c=None, d=torch.tensor([]))
+    metrics.record(a=torch.tensor([5.0]))
+    assert metrics.summary("Agent") == {"Agent/a": 3.0, "Agent/b": 2.0}

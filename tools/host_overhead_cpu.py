@@ -22,6 +22,7 @@ ap.add_argument("--envs", type=int, default=256)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--recurrent", action="store_true")
+ap.add_argument("--count-ops", action="store_true", help="count ATen operators dispatched per iteration (deterministic)")
 ap.add_argument("--graphs", action="store_true",
                 help="drive the CUDA-graph runner with torch.cuda.graph mocked (capture = run the host code, replay = "
                      "nothing): checks its control flow and shows the host time a replayed step costs")
@@ -87,15 +88,40 @@ for _ in range(2):
     run_iteration(agent, data)
 n0 = Stub.calls
 pr = cProfile.Profile() if args.profile else None
-t0 = time.perf_counter()
+torch.set_num_threads(1)  # tiny CPU tensors: intra-op threads only add noise
+if args.count_ops:
+    # deterministic proxy for host cost: ATen operators dispatched per iteration from the calling thread (every one is a
+    # kernel launch or an allocation on the GPU); wall-clock on a shared CPU box is too noisy to compare small changes
+    from collections import Counter
+
+    from torch.utils._python_dispatch import TorchDispatchMode
+
+    class OpCounter(TorchDispatchMode):
+        def __init__(self):
+            super().__init__()
+            self.ops = Counter()
+
+        def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+            self.ops[str(func.overloadpacket)] += 1
+            return func(*args, **(kwargs or {}))
+
+    n0 = Stub.calls
+    with OpCounter() as counter:
+        run_iteration(agent, data)
+    total = sum(counter.ops.values())
+    print(f"ATen ops dispatched in one iteration (calling thread): {total}; stubbed C-ABI calls: {Stub.calls - n0}")
+    print("  " + ", ".join(f"{k.replace('aten.', '')} {v}" for k, v in counter.ops.most_common(14)))
 if pr:
     pr.enable()
+times = []
 for _ in range(args.iters):
+    t0 = time.perf_counter()
     run_iteration(agent, data)
+    times.append(time.perf_counter() - t0)
 if pr:
     pr.disable()
-dt = (time.perf_counter() - t0) / args.iters
-print(f"host time per iteration: {dt * 1e3:.2f} ms with {(Stub.calls - n0) // args.iters} stubbed C-ABI calls "
+dt = sum(times) / len(times)
+print(f"host time per iteration: {dt * 1e3:.2f} ms (best {min(times) * 1e3:.2f} ms) with {(Stub.calls - n0) // args.iters} stubbed C-ABI calls "
       f"({args.envs} envs, CPU tensors, kernels not executed)")
 if args.graphs:
     print(f"graph runner: {runner.captures} capture(s), {runner.replays} replays, optimizer step_count "
