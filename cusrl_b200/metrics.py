@@ -118,7 +118,8 @@ class Metrics:
         if not self._data:
             return {}
         names = list(self._data)
-        device = next((m.mean.device for m in self._data.values() if m.mean.is_cuda), torch.device("cpu"))
-        packed = torch.stack([self._data[n].mean.reshape(()).to(device) for n in names])
+        means = [self._data[n].mean for n in names]
+        device = next((m.device for m in means if m.is_cuda), torch.device("cpu"))
+        packed = torch.stack([m.reshape(()).to(device) for m in means])
         values = packed.tolist()  # the single host sync of an update
         return {f"{prefix}{n}": v for n, v in zip(names, values)}
