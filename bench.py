@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-envs", type=int, default=4096, help="environments of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline (oracle port on cuda:0)")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-on-cuda:0 baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of timed CPU iterations")
     return ap.parse_args()
 
 
@@ -246,55 +247,99 @@ def gemm_roofline(rows: int, peaks: dict, which: str) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_iteration_rate(envs: int, T: int, iters: int, warmup: int, threads: int, device: str = "cpu") -> tuple[float, float]:
-    """env-steps/s of the oracle port (the reference's PyTorch arithmetic restated, oracle/ppo_path.py) on `threads`
-    host threads for a bounded sample of `envs` environments.  With device="cuda" the same eager PyTorch code (fp32
-    SGEMM, TF32 off, ~100 kernel launches per minibatch) runs on the GPU: the "reference's own 1-GPU PyTorch PPO"
-    denominator of BASELINE.json's target, reported as `torch_eager_gpu`."""
-    from oracle import ppo_path as O
+# The reference arm: the UNMODIFIED reference package (baseline/_ref, see tools/install_reference.py) driven through its
+# own public API -- cusrl.preset.ppo.PpoAgentFactory with the Isaac-Velocity-Rough-Anymal-C-v0 values of
+# cusrl/zoo/isaaclab/locomotion.py:48-59, agent.act / agent.step / agent.update exactly as cusrl/template/trainer.py:296-321
+# calls them.  None of this repository's kernels, modules or oracle code is on that path.
+ANYMAL_C_ROUGH = dict(num_steps_per_update=24, actor_hidden_dims=(512, 256, 128), critic_hidden_dims=(512, 256, 128),
+                      activation_fn="ELU", lr=1e-3, sampler_epochs=5, sampler_mini_batches=4, orthogonal_init=False,
+                      entropy_loss_weight=0.005, desired_kl_divergence=0.015)
 
-    torch.set_num_threads(threads)
-    cfg = O.PpoConfig()
-    g = torch.Generator(device=device).manual_seed(0)
-    params = O.init_mlp_params_ref(cfg.obs_dim, cfg.act_dim, cfg.hidden, generator=torch.Generator().manual_seed(0))
-    agent = O.OraclePpo(cfg, {k: v.to(device) for k, v in params.items()})
-    obs = torch.randn(T + 1, envs, cfg.obs_dim, generator=g, device=device)
-    reward = torch.randn(T, envs, 1, generator=g, device=device)
-    term = torch.rand(T, envs, 1, generator=g, device=device) < 0.01
-    trunc = torch.rand(T, envs, 1, generator=g, device=device) < 0.001
 
-    def iteration():
-        leaves = {k: [] for k in ("observation", "action", "action_logp", "action_dist.mean", "action_dist.std", "value")}
-        for t in range(T):
-            tr = agent.act(obs[t], torch.randn(envs, cfg.act_dim, generator=g, device=device))
-            for k in leaves:
-                leaves[k].append(tr[k])
-        buf = {k: torch.stack(v) for k, v in leaves.items()}
-        buf.update(next_observation=obs[1:], reward=reward.clone(), terminated=term, truncated=trunc, done=term | trunc)
-        perms = [torch.randperm(T * envs, generator=g, device=device) for _ in range(cfg.epochs)]
-        agent.update(buf, perms)
-        if device != "cpu":
+def _import_reference():
+    sys.path.insert(0, str(ROOT / "tools"))
+    from install_reference import import_reference
+
+    # the reference reads the torchrun variables at import (cusrl/utils/config.py:31-38) and would open a process group
+    # on its first collective; this arm runs on ONE process (rank 0), so it must not see them
+    for key in ("LOCAL_RANK", "RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(key, None)
+    return import_reference()
+
+
+class ReferenceRun:
+    """The reference agent on `device` ("cpu" or "cuda:0") with `envs` synthetic environments, same data recipe as
+    :class:`RolloutData`."""
+
+    def __init__(self, device: str, envs: int, T: int, seed: int = 1000):
+        cusrl = _import_reference()
+        from cusrl.template.environment import EnvironmentSpec
+
+        self.device, self.envs, self.T = torch.device(device), envs, T
+        torch.manual_seed(42)
+        kwargs = dict(ANYMAL_C_ROUGH, num_steps_per_update=T)
+        spec = EnvironmentSpec(num_instances=envs, observation_dim=OBS, action_dim=ACT, reward_dim=1, autoreset=True,
+                               final_state_is_missing=True)
+        self.agent = cusrl.preset.ppo.PpoAgentFactory(device=device, **kwargs)(spec)
+        self.data = RolloutData(T, envs, self.device, seed=seed, pinned_host=False)
+
+    def iteration(self) -> dict:
+        return run_iteration(self.agent, self.data)
+
+    def time(self, iters: int, warmup: int, budget_s: float | None = None) -> tuple[float, float, int]:
+        """(env-steps/s, seconds per iteration, timed iterations).  CUDA events on the GPU like the reference's Timer
+        (cusrl/utils/timing.py:49-94), perf_counter on the CPU (:32-46).  `budget_s` bounds the timed iterations by the
+        duration of the last warm-up iteration so the whole call ends within minutes."""
+        cuda = self.device.type == "cuda"
+        last = None
+        for _ in range(max(warmup, 1)):
+            t0 = time.perf_counter()
+            self.iteration()
+            if cuda:
+                torch.cuda.synchronize()
+            last = time.perf_counter() - t0
+        if budget_s is not None:
+            iters = max(1, min(iters, int(budget_s / max(last, 1e-9))))
+        if cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            self.iteration()
+        if cuda:
+            b.record()
             torch.cuda.synchronize()
-
-    for _ in range(warmup):
-        iteration()
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        iteration()
-    dt = (time.perf_counter() - t0) / iters
-    return T * envs / dt, dt
+            dt = a.elapsed_time(b) * 1e-3 / iters
+        else:
+            dt = (time.perf_counter() - t0) / iters
+        return self.T * self.envs / dt, dt, iters
 
 
-def pick_cpu_threads(T: int, max_threads: int) -> tuple[int, dict]:
+def pick_cpu_threads(T: int, max_threads: int, envs: int = 1024) -> tuple[int, dict]:
     """PyTorch-CPU does not scale to every hardware thread on this workload (128 threads were 20x slower than 32 on the
-    GPU box's host): calibrate on a small sample and use the fastest setting, so the baseline is the CPU at its best."""
+    GPU box's host): calibrate on a small sample (one warm-up + three timed reference iterations per setting) and use the
+    fastest setting, so the baseline is the CPU at its best."""
+    run = ReferenceRun("cpu", envs, T)
     rates = {}
     for th in (8, 16, 32, 64, max_threads):
         if th > max_threads or th in rates:
             continue
-        rates[th], _ = cpu_port_iteration_rate(256, T, iters=1, warmup=1 if not rates else 0, threads=th)
+        torch.set_num_threads(th)
+        rates[th], _, _ = run.time(iters=3, warmup=1)
     best = max(rates, key=rates.get)
+    torch.set_num_threads(best)
     return best, {str(k): round(v, 1) for k, v in rates.items()}
+
+
+def reference_cpu_baseline(envs: int, T: int, iters: int, warmup: int, host_threads: int, budget_s: float | None):
+    """`cpu_baseline` object: the reference's own CPU path on this box's host cores."""
+    threads, calib = pick_cpu_threads(T, host_threads)
+    run = ReferenceRun("cpu", envs, T)
+    rate, dt, done = run.time(iters, warmup, budget_s)
+    return {"value": round(rate, 1), "unit": "env-steps/s", "cores": threads, "kind": "reference",
+            "sample": f"{envs} envs x {T} steps per iteration, {max(warmup, 1)} warm-up + {done} timed iterations "
+                      f"({dt:.2f} s each); unmodified reference (baseline/_ref) on device='cpu'",
+            "thread_calibration_env_steps_per_s": calib}, dt, done
 
 
 # ------------------------------------------------------------------------------------------------
@@ -306,22 +351,21 @@ def main():
     host_threads = os.cpu_count() or 1
 
     if args.impl == "reference":
-        # the reference's own CPU path (oracle port), rank 0 only, bounded sample of the same workload
+        # The reference arm of this tier: the UNMODIFIED reference (baseline/_ref) through its own act/step/update on the
+        # box's host cores, rank 0 only, on the SAME workload (all args.envs environments).  One CPU iteration at 65536
+        # environments takes tens of seconds, so the number of timed iterations is bounded by --ref-budget seconds
+        # (never fewer than one); `steps` reports the iterations actually timed, `steps_requested` what was asked for.
         if rank != 0:
             return
-        threads, calib = pick_cpu_threads(T, host_threads)
-        rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=max(1, args.steps), warmup=min(1, args.warmup),
-                                           threads=threads)
-        host_threads = threads
+        cpu, dt, done = reference_cpu_baseline(args.envs, T, iters=max(1, args.steps), warmup=1,
+                                               host_threads=host_threads, budget_s=args.ref_budget)
+        rate = cpu["value"]
         line = {
-            "impl": "reference", "metric": "ppo_env_steps_per_sec", "value": round(rate, 1), "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
-            "cpu_baseline": {"value": round(rate, 1), "unit": "env-steps/s", "cores": host_threads, "kind": "port",
-                             "sample": f"{args.cpu_envs} envs x {T} steps per iteration (of {args.envs}), same preset",
-                             "thread_calibration_env_steps_per_s": calib},
-            "e2e": {"value": round(rate, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "impl": "reference", "metric": "ppo_env_steps_per_sec", "value": rate, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": done, "warmup": 1, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "cpu_baseline": cpu,
+            "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), flush=True)
         return
@@ -376,31 +420,38 @@ def main():
         big = gae_roofline(T, 16 * N, peaks, which)
         roof_gae["same_kernel_16x_columns"] = {k: big[k] for k in ("achieved", "frac", "bytes_per_launch", "us_per_launch")}
         roof = gemm_roofline(T * N // 4, peaks, which)  # one minibatch of this rank (4 minibatches per epoch)
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            threads, calib = pick_cpu_threads(T, host_threads)
-            rate, dt = cpu_port_iteration_rate(args.cpu_envs, T, iters=2, warmup=1, threads=threads)
-            cpu = {"value": round(rate, 1), "unit": "env-steps/s", "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_envs} envs x {T} steps, 1 warm-up + 2 timed iterations ({dt:.2f} s each)",
-                   "thread_calibration_env_steps_per_s": calib}
-        eager = None
-        if not args.no_gpu_eager and world == 1:
-            # the same workload (all args.envs environments) through the oracle's eager PyTorch code on this GPU
+        # ---- baselines (N = 1 only), both the UNMODIFIED reference from baseline/_ref, never on the product path
+        ref_cuda = None
+        if not args.no_reference_cuda and world == 1:
+            # BASELINE.json's >= 10x denominator: "the reference's own 1-GPU PyTorch PPO" = the reference code with
+            # device="cuda" on this GPU, same workload (all args.envs environments), CUDA-event timed like its Timer
             del agent, env
             torch.cuda.empty_cache()
             try:
-                rate, dt = cpu_port_iteration_rate(args.envs, T, iters=2, warmup=1, threads=min(host_threads, 16), device="cuda")
-                eager = {"value": round(rate, 1), "unit": "env-steps/s", "kind": "port", "ms_per_step": round(dt * 1e3, 2),
-                         "note": "oracle/ppo_path.py (the reference's arithmetic in eager PyTorch, fp32 SGEMM, TF32 off) on "
-                                 f"cuda:0, {args.envs} envs x {T} steps, 1 warm-up + 2 timed iterations, wall clock + synchronize"}
+                run = ReferenceRun("cuda:0", args.envs, T)
+                rate, dt, done = run.time(iters=3, warmup=2)
+                ref_cuda = {"value": round(rate, 1), "unit": "env-steps/s", "kind": "reference", "ms_per_step": round(dt * 1e3, 2),
+                            "speedup_value": round(value / rate, 2),
+                            "speedup_e2e": None if e2e is None else round(e2e["value"] / rate, 2),
+                            "note": "unmodified reference (baseline/_ref): cusrl.preset.ppo.PpoAgentFactory with the "
+                                    f"locomotion.py:48-59 values on cuda:0, {args.envs} envs x {T} steps, same act/step/update "
+                                    f"calls and data, 2 warm-up + {done} timed iterations, CUDA events"}
+                del run
+                torch.cuda.empty_cache()
             except Exception as error:  # a baseline must never take the bench line down with it
-                eager = {"value": None, "error": f"{type(error).__name__}: {error}"[:300]}
+                ref_cuda = {"value": None, "error": f"{type(error).__name__}: {error}"[:300]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cpu, _, _ = reference_cpu_baseline(args.cpu_envs, T, iters=3, warmup=1, host_threads=host_threads, budget_s=30.0)
+            except Exception as error:
+                cpu = {"value": None, "error": f"{type(error).__name__}: {error}"[:300]}
         line = {
             "metric": "ppo_env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary(), "roofline": roof, "roofline_gae": roof_gae, "cpu_baseline": cpu, "torch_eager_gpu": eager,
+            "clocks": clocks.summary(), "roofline": roof, "roofline_gae": roof_gae, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
             "last_metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")},
         }
     if distributed:

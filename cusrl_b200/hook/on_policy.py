@@ -432,9 +432,11 @@ class OnPolicyStatistics(Hook):
         action_dist, _ = actor(obs, memory=buffer.get("actor_memory"), done=buffer["done"])
         old = buffer["action_dist"]
         E = obs.shape[0] * obs.shape[1]
-        out = ops.policy_stats(old["mean"], old["std"], action_dist["mean"].contiguous(),
-                               actor.distribution.std.param.detach(), buffer["action"], buffer["action_logp"],
-                               buffer["advantage"])
+        # leaves whose rows the buffer pads to 16-byte multiples (action dims 17-19, 21-23, ...) are narrow views of the
+        # padded storage: the statistics kernel takes dense rows, so those (and only those) are compacted first
+        out = ops.policy_stats(old["mean"].contiguous(), old["std"].contiguous(), action_dist["mean"].contiguous(),
+                               actor.distribution.std.param.detach(), buffer["action"].contiguous(),
+                               buffer["action_logp"], buffer["advantage"])
         agent.metrics.record_mean("kl_divergence", out[0], E)
         agent.metrics.record_mean("importance_weighted_advantage", out[1], E)
         agent.metrics.record_mean("action_std", out[2], E * old["std"].shape[-1])

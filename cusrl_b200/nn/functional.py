@@ -164,6 +164,17 @@ def mlp_head_forward(x: torch.Tensor, weights, biases, activation: str, head_wei
 _SIMT_HEADS = {(no, 1) for no in range(1, 17)} | {(no, 2) for no in (1, 2, 4, 6, 8)}
 
 
+def simt_head_supported(out_features: int, in_features: int) -> bool:
+    """Shapes instantiated in csrc/head_kernels.cu (latent 128 with 1..16 outputs, latent 256 with 1/2/4/6/8)."""
+    return in_features % 128 == 0 and (out_features, in_features // 128) in _SIMT_HEADS
+
+
+def _pad_rows(t: torch.Tensor, rows: int) -> torch.Tensor:
+    out = torch.zeros(rows, *t.shape[1:], dtype=t.dtype, device=t.device)
+    out[: t.shape[0]].copy_(t)
+    return out
+
+
 class _HeadFunction(torch.autograd.Function):
     """y = x W^T + b for an output head fed by a non-MLP backbone (e.g. the LSTM): the fp32 SIMT head when its shape is
     instantiated (csrc/head_kernels.cu), otherwise the tcgen05 dense-layer kernels (needs out_features % 4 == 0)."""
@@ -172,11 +183,19 @@ class _HeadFunction(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         x = _rows_ok(x)
         No, K = weight.shape
-        simt = K % 128 == 0 and (No, K // 128) in _SIMT_HEADS
+        simt = simt_head_supported(No, K)
+        ctx.padded = None
         if simt:
             y = ops.head_fwd(x, weight, bias)
-        else:
+        elif No % 4 == 0:
             y = ops.tc_linear_fwd(x, ops.prepared_weight(weight), bias, No, 0, ops.GEMM_PRECISION)
+        else:
+            # e.g. a 21-dimensional action head: the dense-layer kernels need 16-byte output rows, so the layer runs with
+            # zero rows appended to W (and zero columns to dY in the backward); the public tensors keep their shapes
+            Np = (No + 3) // 4 * 4
+            ctx.padded = ops.weight_prep(_pad_rows(weight.detach(), Np))
+            bias_p = None if bias is None else _pad_rows(bias.detach(), Np)
+            y = ops.tc_linear_fwd(x, ctx.padded, bias_p, Np, 0, ops.GEMM_PRECISION)[:, :No]
         ctx.save_for_backward(x, weight, bias)
         ctx.simt = simt
         return y
@@ -195,9 +214,19 @@ class _HeadFunction(torch.autograd.Function):
             dx = ops.head_bwd(dy, x, weight, 0, dw, db, need_dh=need_dx, accumulate=arena)
             if not arena:
                 grads = [dw, db]
-        else:
+        elif ctx.padded is None:
             _wgrad(dy, x, weight, bias, grads, 0)
             dx = ops.tc_linear_dgrad(dy, ops.prepared_weight(weight), None, weight.shape[1], 0, ops.GEMM_PRECISION) if need_dx else None
+        else:
+            No, K = weight.shape
+            Np = ctx.padded["hi"].shape[0]
+            dy_p = torch.zeros(dy.shape[0], Np, device=dy.device)
+            dy_p[:, :No].copy_(dy)
+            dw_p = torch.empty(Np, K, device=dy.device)
+            db_p = torch.empty(Np, device=dy.device) if bias is not None else None
+            ops.tc_linear_wgrad(dy_p, x, dw_p, db_p, ops.GEMM_PRECISION, accumulate=False)
+            grads = [dw_p[:No], None if db_p is None else db_p[:No]]
+            dx = ops.tc_linear_dgrad(dy_p, ctx.padded, None, K, 0, ops.GEMM_PRECISION) if need_dx else None
         return dx, grads[0], grads[1]
 
 

@@ -24,6 +24,13 @@ __all__ = ["Module", "Mlp", "MlpFactory", "NormalDist", "NormalDistFactory", "Ac
 LOG_SQRT_2PI = math.log(math.sqrt(2.0 * math.pi))
 
 
+def standard_normal_like(mean: Tensor) -> Tensor:
+    """The exploration noise: one Philox draw from torch's global generator of the mean's device, the same draw
+    ``torch.distributions.Normal.rsample`` makes (reference distribution.py:203), so the generator advances identically.
+    Looked up through the module at call time: the parity tests substitute a seeded stream here."""
+    return torch.empty_like(mean).normal_()
+
+
 def _activation_name(fn: str | type[nn.Module]) -> str:
     name = fn if isinstance(fn, str) else fn.__name__
     if name not in F.ACTIVATIONS:
@@ -161,7 +168,7 @@ class NormalDist(Module):
 
     def sample_from_dist(self, dist_params: dict[str, Tensor]) -> tuple[Tensor, Tensor]:
         mean, std = dist_params["mean"], dist_params["std"]
-        eps = torch.empty_like(mean).normal_()  # same draw as torch Normal.rsample (distribution.py:203)
+        eps = standard_normal_like(mean)
         sample = mean + eps * std
         return sample, self.compute_logp(dist_params, sample)
 
@@ -199,6 +206,12 @@ class Actor(Module):
         lins = self.backbone.linears()
         if not self.backbone.ends_with_activation:
             raise ValueError("Actor expects an activation-terminated Mlp backbone (reference preset/ppo.py:137-140)")
+        if not F.simt_head_supported(*head.weight.shape):
+            # heads outside the fused SIMT shapes (e.g. 21 actions, or a latent width that is not 128 / 256): trunk node
+            # + the general head node
+            latent = self.backbone(observation)
+            self.intermediate_repr["backbone.output"] = latent
+            return F.linear_head(latent, head.weight, head.bias), memory
         mean, latent = F.mlp_head_forward(observation, [m.weight for m in lins], [m.bias for m in lins],
                                           self.backbone.activation, head.weight, head.bias)
         self.intermediate_repr["backbone.output"] = latent
@@ -266,6 +279,10 @@ class Value(Module):
         lins = self.backbone.linears()
         if not self.backbone.ends_with_activation:
             raise ValueError("Value expects an activation-terminated Mlp backbone (reference preset/ppo.py:143-147)")
+        if not F.simt_head_supported(*self.value_head.weight.shape):
+            latent = self.backbone(state)
+            self.intermediate_repr["backbone.output"] = latent
+            return F.linear_head(latent, self.value_head.weight, self.value_head.bias), memory
         value, latent = F.mlp_head_forward(state, [m.weight for m in lins], [m.bias for m in lins],
                                            self.backbone.activation, self.value_head.weight, self.value_head.bias)
         self.intermediate_repr["backbone.output"] = latent

@@ -33,6 +33,12 @@ __all__ = [
 ]
 
 _scratch: dict[tuple[int, str], torch.Tensor] = {}
+# Workspaces that were outgrown.  They are never handed back to the allocator: a captured CUDA graph (template/graphs.py)
+# has the pointer of the workspace it was captured with baked into its kernel arguments, and replaying it after the
+# allocator reused that memory would corrupt whatever lives there now.  Workspaces are small (<= a few MB) and grow a
+# handful of times per process.
+_retired_scratch: list[torch.Tensor] = []
+CHECK_INDICES = __import__("os").environ.get("CUSRL_B200_CHECK_INDICES", "0") not in ("", "0")
 
 
 GAE_DEFAULT_VARIANT = _lib.GAE_DEFAULT_VARIANT
@@ -83,6 +89,8 @@ def _get_scratch(device: torch.device, key: str, nbytes: int) -> torch.Tensor:
     k = (device.index or 0, key)
     buf = _scratch.get(k)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired_scratch.append(buf)
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         _scratch[k] = buf
     return buf
@@ -236,6 +244,12 @@ def gather_rows(
     bytes of every destination row are written as zeros. Reference: mini_batch_sampler.py:76,89.
     """
     n_src = None
+    if CHECK_INDICES and index.numel():
+        # debug aid (one host sync): the kernel clamps out-of-range indices instead of faulting
+        lo, hi = int(index.min()), int(index.max())
+        limit = fields[0][0].shape[0] if fields else 0
+        if lo < 0 or hi >= limit:
+            raise IndexError(f"gather_rows: indices span [{lo}, {hi}] but the sources have {limit} rows")
     arr = (GatherField * len(fields))()
     for k, (src, dst) in enumerate(fields):
         _require_cuda(src, "gather_rows source")

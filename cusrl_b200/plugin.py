@@ -1,8 +1,11 @@
 """Drop-in registration with the UNMODIFIED reference CLI:
 
-    python -m cusrl train -m cusrl_b200.plugin -env Isaac-Velocity-Rough-Anymal-C-v0 -alg ppo-b200
-    python -m cusrl train -m cusrl_b200.plugin -env Synthetic-AnymalC-Rough-v0     -alg ppo-b200 -- --num_iterations 10
-    torchrun --nproc-per-node 8 -m cusrl train -m cusrl_b200.plugin -env ... -alg ppo-b200
+    python -m cusrl train -env Isaac-Velocity-Rough-Anymal-C-v0 -alg ppo-b200 -m cusrl_b200.plugin
+    python -m cusrl train -env Synthetic-AnymalC-Rough-v0 -alg ppo-b200 -m cusrl_b200.plugin -- --num-iterations 10
+    torchrun --nproc-per-node 8 -m cusrl train -env ... -alg ppo-b200 -m cusrl_b200.plugin
+
+(``-m`` takes the REST of the command line up to ``--`` as the module's own arguments, cusrl/cli/train.py:29-30, so it
+goes last.)  Exercised end to end on a B200 by tests/test_cli_gpu.py against the unmodified reference in baseline/_ref.
 
 ``-m <module>`` makes the reference import this module before the experiment lookup (cusrl/cli/train.py:29-32,45);
 importing it calls the reference's own ``cusrl.zoo.register_experiment`` (cusrl/zoo/registry.py:27-82) with
@@ -16,6 +19,9 @@ This module needs the reference package (``import cusrl``) and is not imported b
 """
 
 from __future__ import annotations
+
+import json
+import os
 
 import torch
 
@@ -55,9 +61,23 @@ def make_synthetic_env(id: str = "Synthetic-AnymalC-Rough-v0", argv=None, **kwar
     return SyntheticAnymalEnvironment(**kwargs)
 
 
+class MetricsJsonl(cusrl.template.trainer.TrainerHook):
+    """Appends the trainer's per-iteration log dict (``Agent/*``, ``Perf/agent_fps``, ...; cusrl/template/trainer.py:374-397)
+    to the file named by ``CUSRL_B200_METRICS_JSONL``, one JSON object per line, on the main process."""
+
+    def __init__(self, path: str):
+        self.path = path
+
+    def pre_log_info(self, info):
+        if cusrl.utils.distributed.is_main_process():
+            with open(self.path, "a") as f:
+                f.write(json.dumps({k: float(v) for k, v in info.items()}) + "\n")
+
+
 def _register() -> None:
+    hooks = [MetricsJsonl(path)] if (path := os.environ.get("CUSRL_B200_METRICS_JSONL")) else []
     common = dict(algorithm_name=ALGORITHM_NAME, agent_meta_factory=anymal_c_rough_ppo, num_iterations=1500,
-                  checkpoint_interval=100)
+                  checkpoint_interval=100, trainer_hooks=hooks)
     register_experiment(environment_name="Synthetic-AnymalC-Rough-v0", training_env_factory=make_synthetic_env, **common)
     try:  # the real simulator adapter, when IsaacLab is installed (same env list as cusrl/zoo/isaaclab/locomotion.py:40-47)
         from cusrl.environment import make_isaaclab_env

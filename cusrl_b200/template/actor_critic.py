@@ -275,6 +275,11 @@ class ActorCritic:
             loss = sum(objectives.values())
             self.optimizer.zero_grad()
             loss.backward()
+            arena = getattr(self.optimizer, "arena", None)
+            if arena is not None:
+                # a hook that detached a p.grad from the flat arena must not make the allreduce / clip / Adam kernels
+                # work on stale memory: such gradients are folded back into the arena here (pointer compares only)
+                arena.rebind_gradients()
         return objectives
 
     def _train_step_optimize(self, metadata: dict[str, Any], batch: dict[str, Any], objectives) -> None:

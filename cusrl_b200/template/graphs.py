@@ -67,7 +67,7 @@ class TrainStepGraphs:
     # ---- cache keys --------------------------------------------------------------------------------------------------
     def _hyper_key(self) -> tuple:
         agent = self.agent
-        hooks = tuple((hook.name, tuple((m, repr(getattr(hook, m, None))) for m in sorted(hook._mutable)))
+        hooks = tuple((hook.name, tuple((m, repr(getattr(hook, m, None))) for m in sorted(getattr(hook, "_mutable", ()))))
                       for hook in agent.hook.active_hooks())
         groups = tuple((tuple(g["betas"]), g["eps"], g["weight_decay"]) for g in agent.optimizer.param_groups)
         return hooks, groups, ops.GEMM_PRECISION, distributed.world_size()

@@ -20,7 +20,7 @@ from torch import nn
 from .. import distributed
 from .buffer import Buffer
 
-__all__ = ["Hook", "HookComposite", "camel_to_snake"]
+__all__ = ["Hook", "HookComposite", "camel_to_snake", "is_hook"]
 
 _MISSING = object()
 
@@ -172,6 +172,22 @@ class Hook:
             print(f"\033[1;31m{cls.__name__}: {message}\033[0m")
 
 
+_LIFECYCLE = ("pre_init", "init", "post_init", "pre_act", "post_act", "post_step", "should_update", "pre_update",
+              "pre_objective", "objective", "pre_optim", "post_optim", "post_objective", "post_update", "apply_schedule",
+              "named_parameters", "state_dict", "load_state_dict", "train", "update_attribute", "active_", "name_")
+
+
+def is_hook(obj: Any) -> bool:
+    """A :class:`Hook`, or any object with the reference's hook protocol -- in particular instances of the REFERENCE's
+    own ``cusrl.template.Hook`` subclasses (``HookParameterSchedule`` / ``HookActivationSchedule`` of
+    cusrl/hook/control/schedule.py:12-77, ``AdvantageReduction``, user hooks), which address the other hooks by name
+    through ``agent.hook[name]`` and must keep working next to the B200 hooks."""
+    if isinstance(obj, Hook):
+        return True
+    return (all(callable(getattr(obj, name, None)) for name in _LIFECYCLE)
+            and all(hasattr(obj, attr) for attr in ("name", "active", "training_only")))
+
+
 class HookComposite(Hook):
     """Runs a list of hooks in order; addressable by hook name."""
 
@@ -180,7 +196,7 @@ class HookComposite(Hook):
         self._hooks = tuple(hooks)
         self._named_hooks: dict[str, Hook] = {}
         for hook in self._hooks:
-            if not isinstance(hook, Hook):
+            if not is_hook(hook):
                 raise TypeError(f"Expected a Hook instance, but got '{type(hook).__name__}'")
             if hook.name in self._named_hooks:
                 raise RuntimeError(f"Hook '{hook.name}' already exists")

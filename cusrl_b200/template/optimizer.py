@@ -56,6 +56,25 @@ class ParamArena:
             p.grad = self.flat_grad[off : off + n].view_as(p)
         self.numel = total
 
+    def rebind_gradients(self) -> int:
+        """Make every ``p.grad`` the arena view again.  ``module.zero_grad()`` (set_to_none=True by default) or a user
+        hook's ``p.grad = None`` detaches a parameter from the arena: autograd then allocates a fresh gradient tensor, the
+        weight-gradient kernels stop accumulating in place and the optimizer would step on a stale arena.  A detached
+        gradient that holds values (autograd wrote it) is copied into its arena slice first, so nothing is lost.
+        Returns the number of parameters that had to be re-bound."""
+        fixed = 0
+        base = self.flat_grad.data_ptr()
+        for p, off in zip(self.params, self.offsets):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + 4 * off:
+                continue
+            view = self.flat_grad[off : off + p.numel()].view_as(p)
+            if g is not None:
+                view.copy_(g)
+            p.grad = view
+            fixed += 1
+        return fixed
+
     def segment(self, name_prefix: str) -> list[tuple[int, int]]:
         """(offset, count) ranges of every parameter whose name equals or starts with `prefix.`."""
         out = []
@@ -121,7 +140,9 @@ class FlatAdam:
         return self.arena.flat_grad
 
     def zero_grad(self, set_to_none: bool = False) -> None:
-        """Gradients are accumulated in place by the wgrad kernels, so zero the arena (one memset)."""
+        """Gradients are accumulated in place by the wgrad kernels, so zero the arena (one memset) -- after re-binding
+        any ``p.grad`` that something detached from it since the last step."""
+        self.arena.rebind_gradients()
         self.arena.flat_grad.zero_()
 
     def compute_grad_norm(self, max_norm: float) -> torch.Tensor:
@@ -135,6 +156,7 @@ class FlatAdam:
 
     def step(self) -> None:
         g = self.param_groups[0]
+        self.arena.rebind_gradients()  # gradients autograd produced outside the arena are folded in, never dropped
         self.step_count += 1
         coef = self.clip_coef if self._clip_pending else None
         if self.step_dev is not None:

@@ -61,6 +61,11 @@ class SectionTimer:
 class Trainer:
     def __init__(self, environment, agent, num_iterations: int = 1, verbose: bool = False):
         self.environment, self.agent, self.num_iterations, self.verbose = environment, agent, num_iterations, verbose
+        if not getattr(getattr(environment, "spec", None), "autoreset", True):
+            # the reference resets finished instances itself when the environment does not (trainer.py:306-312, one host
+            # sync per step); this loop omits that branch, so it must not silently train on dead episodes
+            raise ValueError("cusrl_b200.Trainer drives autoreset environments only (spec.autoreset must be True); use the "
+                             "reference Trainer (python -m cusrl train -m cusrl_b200.plugin) for the others")
         self.timer = SectionTimer(agent.device)
         self.iteration = 0
         self.history: list[dict[str, float]] = []

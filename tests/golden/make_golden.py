@@ -20,6 +20,7 @@ from types import SimpleNamespace
 
 HERE = Path(__file__).resolve().parent
 REFERENCE = Path(os.environ.get("CUSRL_REFERENCE", "/root/reference"))
+sys.path.insert(0, str(HERE))
 sys.path.insert(0, str(HERE / "_shims"))
 sys.path.insert(0, str(REFERENCE))
 
@@ -335,7 +336,143 @@ def make_lstm():
     save("lstm", **res)
 
 
+# ------------------------------------------------------------------------------------------------
+# Fixtures at BASELINE.json's shapes: inputs are regenerated from seeds on both sides (recipes.py); only what the
+# reference computed from them is stored (scalar series, checksums, strided samples).
+def make_iteration_anymal(N: int = 4096, T: int = 24):
+    """A whole reference PPO iteration (24 x act/step + update) at BASELINE.json config 2: 4096 envs x 24 steps, obs 235,
+    act 12, MLP 512-256-128 ELU, the Anymal-C-rough preset values (zoo/isaaclab/locomotion.py:48-59), on CPU."""
+    import recipes as R
+    from cusrl.template.environment import EnvironmentSpec
+    import torch.distributions.normal as normal_mod
+
+    factory = cusrl.preset.ppo.PpoAgentFactory(
+        num_steps_per_update=T, actor_hidden_dims=(512, 256, 128), critic_hidden_dims=(512, 256, 128),
+        activation_fn="ELU", lr=1e-3, sampler_epochs=5, sampler_mini_batches=4, orthogonal_init=False,
+        entropy_loss_weight=0.005, desired_kl_divergence=0.015, device="cpu")
+    spec = EnvironmentSpec(num_instances=N, observation_dim=R.OBS, action_dim=R.ACT, reward_dim=1, autoreset=True,
+                           final_state_is_missing=True)
+    torch.set_num_threads(8)
+    agent = factory(spec)
+    R.set_seeded_parameters(agent.named_parameters(), seed=1)
+    stream = R.anymal_stream(T, N, seed=2)
+    noise = R.noise_stream(T, N, R.ACT, seed=3)
+    step = {"t": 0}
+    real_normal = normal_mod._standard_normal
+    normal_mod._standard_normal = lambda shape, dtype, device: noise[step["t"]].to(dtype=dtype, device=device).reshape(shape)
+    try:
+        for t in range(T):
+            step["t"] = t
+            agent.act(stream["obs"][t])
+            ready = agent.step(stream["obs"][t + 1], stream["reward"][t], stream["terminated"][t], stream["truncated"][t])
+    finally:
+        normal_mod._standard_normal = real_normal
+    assert ready
+    out = {"shape": np.array([N, T])}
+    for key in ("action", "action_logp", "action_dist.mean", "value"):
+        out.update(R.flatten_fingerprints(f"rollout/{key}", R.fingerprint(agent.buffer.storage[key])))
+
+    minibatch_logs = []
+    real_record = agent.record
+
+    def spy_record(metrics=None, /, **kwargs):
+        if "surrogate_loss" in kwargs:
+            minibatch_logs.append([float(kwargs["value_loss"]), float(kwargs["surrogate_loss"]), float(kwargs["entropy_loss"])])
+        return real_record(metrics, **kwargs)
+
+    real_randperm = torch.randperm
+    seeded = R.SeededRandperm(seed=4)
+    torch.randperm = seeded
+    agent.record = spy_record
+    try:
+        metrics = agent.update()
+    finally:
+        torch.randperm = real_randperm
+    assert seeded.calls == 6
+    out["minibatch_losses"] = np.array(minibatch_logs, dtype=np.float64)
+    for key in ("advantage", "return", "next_value"):
+        out.update(R.flatten_fingerprints(f"post/{key}", R.fingerprint(agent.buffer.storage[key])))
+    names = []
+    for name, p in agent.named_parameters():
+        names.append(name)
+        out.update(R.flatten_fingerprints(f"param1/{name}", R.fingerprint(p)))
+    out["param_names"] = np.array(names)
+    out["metric_names"] = np.array(sorted(metrics))
+    out["metric_values"] = np.array([metrics[k] for k in sorted(metrics)], dtype=np.float64)
+    out["lr_after"] = np.float64(agent.optimizer.param_groups[0]["lr"])
+    torch.set_num_threads(1)
+    save("iteration_anymal", **out)
+
+
+def make_lstm_anymal(T: int = 24, N: int = 1024, I: int = 235, H: int = 256, L: int = 2):
+    """Reference Rnn (LSTM 2 x 256 on 235 inputs, the config-3 backbone) on one temporal minibatch [24, 1024, 235]."""
+    import recipes as R
+
+    torch.set_num_threads(8)
+    rnn = cusrl.Rnn.Factory("LSTM", hidden_size=H, num_layers=L)(I)
+    R.set_seeded_parameters(rnn.named_parameters(), seed=5)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(T, N, I, generator=g)
+    done = torch.rand(T, N, 1, generator=g) < 0.011
+    memory = {"hidden": torch.randn(N, L * H, generator=g) * 0.5, "cell": torch.randn(N, L * H, generator=g) * 0.5}
+    gout = torch.randn(T, N, H, generator=g) / (T * N)
+    out, _ = rnn(x, memory={k: v.clone() for k, v in memory.items()}, done=done)
+    (out * gout).sum().backward()
+    res = {"shape": np.array([T, N, I, H, L])}
+    res.update(R.flatten_fingerprints("out", R.fingerprint(out, 4096)))
+    names = []
+    for k, p_ in rnn.named_parameters():
+        names.append(k)
+        res.update(R.flatten_fingerprints(f"grad/{k}", R.fingerprint(p_.grad, 1024)))
+    res["param_names"] = np.array(names)
+    torch.set_num_threads(1)
+    save("lstm_anymal", **res)
+
+
+def make_rnd_anymal(T: int = 24, N: int = 16384, D: int = 235):
+    """RandomNetworkDistillation at BASELINE.json config 4: 16384 envs x 24 steps, nets 235 -> 128 -> 128 -> 16
+    (cusrl_test/hook/auxiliary/test_rnd.py:13-17), one minibatch of T*N/4 samples for the objective."""
+    import recipes as R
+    from cusrl.hook.auxiliary.rnd import RandomNetworkDistillation
+
+    torch.set_num_threads(8)
+    hook = RandomNetworkDistillation(cusrl.Mlp.Factory([128, 128]), output_dim=16, reward_scale=0.1)
+    recorded = {}
+    hook.agent = SimpleNamespace(state_dim=D, setup_module=lambda m: m, record=lambda **kw: recorded.update(kw))
+    hook.init()
+    for net in ("target", "predictor"):
+        R.set_seeded_parameters(((f"{net}.{k}", p) for k, p in getattr(hook, net).named_parameters()), seed=8)
+    g = torch.Generator().manual_seed(9)
+    buffer = Buffer(T, N, device="cpu")
+    buffer["next_observation"] = torch.randn(T, N, D, generator=g)
+    buffer["reward"] = torch.randn(T, N, 1, generator=g)
+    hook.pre_update(buffer)
+    out = {"shape": np.array([T, N, D])}
+    out.update(R.flatten_fingerprints("reward_after", R.fingerprint(buffer["reward"], 4096)))
+    out["rnd_reward_mean"] = recorded["rnd_reward"].double().mean().reshape(1)
+    B = T * N // 4
+    batch = {"next_observation": buffer["next_observation"].flatten(0, 1)[:B]}
+    loss = hook.objective({}, batch)["rnd_loss"]
+    loss.backward()
+    out["rnd_loss"] = loss.detach().double().reshape(1)
+    names = []
+    for k, p in hook.predictor.named_parameters():
+        names.append(k)
+        out.update(R.flatten_fingerprints(f"grad/{k}", R.fingerprint(p.grad, 1024)))
+    out["param_names"] = np.array(names)
+    torch.set_num_threads(1)
+    save("rnd_anymal", **out)
+
+
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    big = {"iteration_anymal": make_iteration_anymal, "lstm_anymal": make_lstm_anymal, "rnd_anymal": make_rnd_anymal}
+    if only:
+        for name in only:
+            (big.get(name) or globals()[f"make_{name}"])()
+        sys.exit(0)
+    for fn in big.values():
+        fn()
     make_lstm()
     make_rnd()
     make_gae()

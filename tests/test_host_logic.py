@@ -337,3 +337,35 @@ def test_metric_is_exact_for_one_record_and_a_weighted_mean_for_many():
     metrics.record(a=torch.tensor([1.0, 3.0]), b=2.0, c=None, d=torch.tensor([]))
     metrics.record(a=torch.tensor([5.0]))
     assert metrics.summary("Agent") == {"Agent/a": 3.0, "Agent/b": 2.0}
+
+
+def test_detached_gradients_are_rebound_to_the_arena():
+    """`module.zero_grad()` (set_to_none) or a hook's `p.grad = None` detaches a parameter from the flat
+    gradient arena; the gradients autograd then allocates must be folded back in, not silently dropped."""
+    from cusrl_b200.template.optimizer import ParamArena
+
+    lin = torch.nn.Linear(5, 3)
+    arena = ParamArena(lin.named_parameters())
+    assert arena.rebind_gradients() == 0
+    lin.zero_grad()
+    assert lin.weight.grad is None
+    lin(torch.randn(2, 5)).sum().backward()
+    fresh = lin.weight.grad.clone()
+    assert lin.weight.grad.data_ptr() != arena.flat_grad.data_ptr()
+    assert arena.rebind_gradients() == 2
+    assert torch.equal(lin.weight.grad, fresh) and lin.weight.grad.data_ptr() == arena.flat_grad.data_ptr()
+    assert torch.equal(arena.flat_grad[: fresh.numel()].view_as(fresh), fresh)
+
+
+def test_trainer_refuses_environments_without_autoreset():
+    import cusrl_b200 as C
+
+    class Env:
+        spec = C.EnvironmentSpec(4, 3, 2, autoreset=False)
+        num_instances = 4
+
+    class Agent:
+        device = torch.device("cpu")
+
+    with pytest.raises(ValueError, match="autoreset"):
+        C.Trainer(Env(), Agent())

@@ -1,5 +1,6 @@
-"""CPU, build container only: the plugin registers with the UNMODIFIED reference (mounted at /root/reference) and the
-reference's own Trainer accepts the B200 agent factory.  Skipped wherever the reference checkout is absent (GPU box)."""
+"""CPU: the plugin registers with the UNMODIFIED reference (baseline/_ref, or /root/reference in the build container), the
+reference's own Trainer accepts the B200 agent factory, reference-side hooks drive the B200 hooks by name, and
+checkpoints move both ways."""
 
 from __future__ import annotations
 
@@ -9,14 +10,19 @@ from pathlib import Path
 
 import pytest
 
-REFERENCE = Path(os.environ.get("CUSRL_REFERENCE", "/root/reference"))
-pytestmark = pytest.mark.skipif(not (REFERENCE / "cusrl").is_dir(), reason="reference checkout not available")
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+from install_reference import reference_path  # noqa: E402
+
+try:
+    _PATHS = reference_path()   # baseline/_ref (travels to the GPU box), else the build container's /root/reference
+except RuntimeError:
+    _PATHS = None
+pytestmark = pytest.mark.skipif(_PATHS is None, reason="reference package not available (run tools/install_reference.py)")
 
 
 @pytest.fixture(scope="module")
 def reference():
-    shims = Path(__file__).resolve().parent / "golden" / "_shims"
-    added = [str(shims), str(REFERENCE)]
+    added = list(_PATHS)
     sys.path[:0] = added
     try:
         import cusrl
@@ -99,3 +105,32 @@ def test_checkpoints_move_between_the_reference_agent_and_this_one(reference):
     for i, st in ref_sd["optimizer"]["state"].items():
         assert float(got[i]["step"]) == float(st["step"]) == 20.0
         assert torch.equal(got[i]["exp_avg"], st["exp_avg"]) and torch.equal(got[i]["exp_avg_sq"], st["exp_avg_sq"])
+
+
+def test_reference_side_schedule_hooks_drive_the_b200_hooks(reference):
+    """the reference's control hooks address hooks BY NAME through ``agent.hook[name]``
+    (cusrl/hook/control/schedule.py:12-77) and must keep working when mixed into the B200 hook list."""
+    import cusrl_b200 as C
+    from cusrl.hook.control.schedule import HookActivationSchedule, HookParameterSchedule
+
+    factory = C.anymal_c_rough_ppo(num_steps_per_update=4, actor_hidden_dims=(16, 128), critic_hidden_dims=(16, 128),
+                                   device="cpu").to_underlying()
+    factory.register_hook(HookParameterSchedule("ppo_surrogate_loss", "clip_ratio", lambda it: 0.2 if it < 2 else 0.1))
+    factory.register_hook(HookActivationSchedule("entropy_loss", lambda it: it < 3))
+    agent = factory(C.EnvironmentSpec(8, 5, 2, autoreset=True, final_state_is_missing=True))
+    names = [h.name for h in agent.hook]
+    assert "ppo_surrogate_loss_clip_ratio_schedule" in names and "entropy_loss_activation_schedule" in names
+    assert agent.hook["ppo_surrogate_loss"].clip_ratio == 0.2 and agent.hook["entropy_loss"].active
+    agent.metrics.clear()
+    agent.hook.apply_schedule(2)
+    assert agent.hook["ppo_surrogate_loss"].clip_ratio == 0.1
+    assert agent.metrics["ppo_surrogate_loss_clip_ratio"].mean.item() == pytest.approx(0.1)
+    agent.hook.apply_schedule(3)
+    assert not agent.hook["entropy_loss"].active
+    with pytest.raises(ValueError, match="No hook named"):
+        bad = C.anymal_c_rough_ppo(device="cpu").to_underlying()
+        bad.register_hook(HookParameterSchedule("no_such_hook", "weight", lambda it: 1.0))
+        bad(C.EnvironmentSpec(8, 5, 2, autoreset=True, final_state_is_missing=True))
+    # non-hooks are still refused
+    with pytest.raises(TypeError, match="Expected a Hook instance"):
+        C.HookComposite([object()])
