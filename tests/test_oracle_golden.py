@@ -160,3 +160,54 @@ def test_full_iteration_matches_reference(golden):
     assert agent.metrics["kl_divergence"] == pytest.approx(vals["Agent/kl_divergence"], rel=1e-3, abs=1e-7)
     assert agent.metrics["action_std"] == pytest.approx(vals["Agent/action_std"], rel=1e-5)
     assert cfg.lr * agent.lr_scale == pytest.approx(float(g.np("lr_after")), rel=1e-9)
+
+
+def test_full_iteration_at_config2_shape_matches_reference(golden):
+    """The oracle at BASELINE.json config 2 (4096 envs x 24 steps, obs 235, act 12, MLP 512-256-128) against the live
+    reference's own iteration (golden `iteration_anymal.npz`; inputs regenerated from the shared seeded recipes)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import recipes as R
+
+    g = golden("iteration_anymal")
+    N, T = (int(v) for v in g.np("shape"))
+    cfg = O.PpoConfig()
+    names = g.np("param_names").tolist()
+    params = {}
+    shapes = {k: tuple(v.shape) for k, v in O.init_mlp_params_ref(cfg.obs_dim, cfg.act_dim, cfg.hidden).items()}
+    for name in names:
+        params[name] = torch.ones(shapes[name]) if name.endswith("std.param") else R.seeded_parameter(name, shapes[name], seed=1)
+    torch.set_num_threads(8)
+    agent = O.OraclePpo(cfg, params)
+    stream, noise = R.anymal_stream(T, N, seed=2), R.noise_stream(T, N, R.ACT, seed=3)
+    leaves = {k: [] for k in ("observation", "action", "action_logp", "action_dist.mean", "action_dist.std", "value")}
+    for t in range(T):
+        tr = agent.act(stream["obs"][t], noise[t])
+        for k in leaves:
+            leaves[k].append(tr[k])
+    buf = {k: torch.stack(v) for k, v in leaves.items()}
+    buf.update(next_observation=stream["obs"][1:], reward=stream["reward"].clone(), terminated=stream["terminated"],
+               truncated=stream["truncated"], done=stream["terminated"] | stream["truncated"])
+
+    def check(prefix, tensor, rtol, atol):
+        fp = R.fingerprint(tensor)
+        assert torch.allclose(fp["sample"], g.t(f"{prefix}/sample"), rtol=rtol, atol=atol), prefix
+        ref_abs = float(g.np(f"{prefix}/abs_sum")[0])
+        assert abs(float(fp["abs_sum"]) - ref_abs) <= 10 * rtol * ref_abs + atol, prefix
+
+    for key in ("action", "action_logp", "action_dist.mean", "value"):
+        check(f"rollout/{key}", buf[key], 1e-5, 1e-5)
+    seeded = R.SeededRandperm(seed=4)
+    perms = [seeded(T * N) for _ in range(cfg.epochs)]
+    logs = agent.update(buf, perms)
+    for key in ("next_value", "return", "advantage"):
+        check(f"post/{key}", buf[key], 1e-5, 1e-5)
+    got = np.array([[d["value_loss"], d["surrogate_loss"], d["entropy_loss"]] for d in logs])
+    np.testing.assert_allclose(got, g.np("minibatch_losses"), rtol=5e-5, atol=2e-6)
+    vals = dict(zip(g.np("metric_names").tolist(), g.np("metric_values").tolist()))
+    assert agent.metrics["kl_divergence"] == pytest.approx(vals["Agent/kl_divergence"], rel=2e-3, abs=1e-7)
+    assert agent.metrics["action_std"] == pytest.approx(vals["Agent/action_std"], rel=1e-5)
+    assert cfg.lr * agent.lr_scale == pytest.approx(float(g.np("lr_after")), rel=1e-9)
+    torch.set_num_threads(1)

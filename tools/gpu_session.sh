@@ -19,7 +19,10 @@ for s in "$@"; do
     kbench_gae) step kbench_gae 240 python tools/kbench.py --only gae ;;
     kbench)     step kbench 300 python tools/kbench.py ;;
     ncu_gae)    step ncu_gae 110 ncu --set full --clock-control none --import-source on -k regex:gae -o "$out/gae" -f python tools/ncu_gae.py ;;
-    tests)      step tests 600 python -m pytest tests -x -q -m gpu --timeout 120 ;;
+    tests)      step tests 900 python -u -m pytest tests -q -m gpu --timeout 300 -rf ;;
+    tests_x)    step tests_x 900 python -u -m pytest tests -x -q -m gpu --timeout 300 ;;
+    bench_ref_full) step bench_ref_full 600 python bench.py --impl reference --steps 2 --warmup 1 --ref-budget 90 ;;
+    bench_short) step bench_short 600 python bench.py --steps 3 --warmup 3 ;;
     bench)      step bench 300 python bench.py ;;
     bench_ref)  step bench_ref 600 python bench.py --impl reference --steps 2 --warmup 1 ;;
     smoke)      step smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
