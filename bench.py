@@ -404,7 +404,9 @@ def main():
         host = RolloutData(T, N, device, seed=1000 + rank, pinned_host=True)
         e_steps = max(1, min(args.steps, 3))
         e_sec, _ = time_iterations(agent, host, e_steps, 1, distributed)
-        per_iter_in = T * N * (OBS * 4 + 4 + 1 + 1) * 2  # obs_t for act + next_obs_t for step, reward, flags
+        # every observation crosses PCIe ONCE: step(t) uploads next_obs[t]; the following act(t+1) receives the same host
+        # array and reads the device copy (template/rollout.py); only the first act of an iteration uploads its own
+        per_iter_in = (T + 1) * N * OBS * 4 + T * N * (4 + 1 + 1)
         per_iter_out = T * N * ACT * 4 + 4 * 16
         e2e = {"value": round(e_steps * T * args.envs / e_sec, 1), "unit": "env-steps/s",
                "h2d_bytes_per_step": per_iter_in * world, "d2h_bytes_per_step": per_iter_out * world,

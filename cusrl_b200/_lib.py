@@ -83,6 +83,10 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int, [P, c_int64, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, c_int, P,
                 c_size_t, P]),
     "cusrl_b200_dgrad_workspace_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_copy_rows_padded_f32": (c_int, [P, c_int64, P, c_int64, c_int64, c_int64, P]),
+    "cusrl_b200_rollout_store_step_f32": (
+        c_int, [P, c_int64, P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P, P, c_int64, P, P, P, P, P, c_int64, P]),
+    "cusrl_b200_sample_logp_f32": (c_int, [P, P, P, c_int64, c_int64, c_int, P, P, P, P]),
 }
 
 

@@ -23,7 +23,9 @@ constexpr int WG_BM = 128;        // output features per tile (UMMA M)
 constexpr int WG_BKB = 32;        // batch rows per k-block
 constexpr int WG_CHUNK = 32;      // features per 128-byte swizzle span
 constexpr int WG_THREADS = 512;
-constexpr int WG_SEG = 64;        // k-blocks (= 1024 batch rows) accumulated inside the tensor core before a drain
+constexpr int WG_SEG = 32;        // k-blocks (= 1024 batch rows) accumulated inside the tensor core before a drain
+                                  // (64 measured 9.8x cuBLAS-fp32's error at M = 393 216, N x K = 128 x 256: over the 8x bar
+                                  //  of tests/test_gemm_gpu.py; 32 halves the truncation drift for ~6 % more time)
 
 struct WgradParams {
   float* partial;        // [splits][num_m_tiles*128][ldp]

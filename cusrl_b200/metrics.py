@@ -64,7 +64,16 @@ class Metrics:
         return out
 
     def apply(self, entries) -> None:
-        """Merge triples collected in deferred mode (their tensors hold the values of the latest graph replay)."""
+        """Merge triples collected in deferred mode (their tensors hold the values of the latest graph replay).  Once
+        every metric of the list is in weighted-sum mode the merge is two multi-tensor launches (scale the means by their
+        counts, add them to the sums) instead of one ``add_`` per metric."""
+        metrics = [self._data.get(name) for name, _, _ in entries]
+        if entries and all(m is not None and m._sum is not None for m in metrics) and len({id(m) for m in metrics}) == len(metrics):
+            scaled = torch._foreach_mul([mean for _, mean, _ in entries], [float(count) for _, _, count in entries])
+            torch._foreach_add_([m._sum for m in metrics], scaled)
+            for m, (_, _, count) in zip(metrics, entries):
+                m.count += count
+            return
         for name, mean, count in entries:
             self._data.setdefault(name, Metric()).update(mean, count)
 

@@ -555,12 +555,19 @@ def tc_linear_wgrad(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: tor
     _lib.check(code, "linear_wgrad", launches=4 if db is not None else 2)
 
 
-def head_fwd(h: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None) -> torch.Tensor:
-    """Y = H W^T + b for a small-N fp32 head (cusrl_b200_head_fwd_f32)."""
+def head_fwd(h: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Y = H W^T + b for a small-N fp32 head (cusrl_b200_head_fwd_f32); `out`: a dense [M, No] destination (e.g. the
+    rollout buffer slot of the current step)."""
     M, K = h.shape
     No = w.shape[0]
     hp, ldh = _rows(h, "h")
-    y = torch.empty(M, No, device=h.device)
+    if out is None:
+        y = torch.empty(M, No, device=h.device)
+    else:
+        y = out
+        if y.shape != (M, No) or not y.is_contiguous() or y.dtype != torch.float32:
+            raise ValueError("head_fwd: `out` must be a contiguous float32 [M, No] tensor")
+        _require_cuda(y, "out")
     code = _lib.load().cusrl_b200_head_fwd_f32(hp, ldh, _ptr(w.detach(), torch.float32, "weight"),
                                                _ptr(None if b is None else b.detach(), torch.float32, "bias"),
                                                y.data_ptr(), M, K, No, _stream())
@@ -585,6 +592,47 @@ def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: t
         scratch.data_ptr(), scratch.numel(), _stream())
     _lib.check(code, "head_bwd", launches=2)
     return dh
+
+
+# ---------------------------------------------------------------------------------------------- rollout (f1)
+def copy_rows_padded(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[:, :width] = src, padding columns of dst's backing rows zeroed; `dst` is a [rows, width] view of a padded slot."""
+    sp, lds = _rows(src, "src")
+    dp, ldd = _rows(dst, "dst")
+    code = _lib.load().cusrl_b200_copy_rows_padded_f32(sp, lds, dp, ldd, src.shape[0], src.shape[1], _stream())
+    _lib.check(code, "copy_rows_padded")
+    return dst
+
+
+def rollout_store_step(next_obs, next_obs_slot, next_state, next_state_slot, reward, reward_slot, terminated, truncated,
+                       terminated_slot, truncated_slot, done_slot) -> None:
+    """ActorCritic.step's writes into the buffer slots of the current step in one launch (actor_critic.py:255-291,
+    buffer.py:124-151): next_observation / next_state rows, reward, terminated, truncated, done = terminated | truncated."""
+    def wide(src, dst, name):
+        if src is None:
+            return None, 0, None, 0, 0
+        sp, lds = _rows(src, name)
+        dp, ldd = _rows(dst, name + " slot")
+        return sp, lds, dp, ldd, src.shape[1]
+
+    N = reward.shape[0]
+    code = _lib.load().cusrl_b200_rollout_store_step_f32(
+        *wide(next_obs, next_obs_slot, "next_observation"), *wide(next_state, next_state_slot, "next_state"),
+        _ptr(reward, torch.float32, "reward"), _ptr(reward_slot, torch.float32, "reward slot"), reward.shape[-1],
+        _flag_ptr(terminated, "terminated"), _flag_ptr(truncated, "truncated"), _flag_ptr(terminated_slot, "terminated slot"),
+        _flag_ptr(truncated_slot, "truncated slot"), _flag_ptr(done_slot, "done slot"), N, _stream())
+    _lib.check(code, "rollout_store_step")
+
+
+def sample_logp(mean: torch.Tensor, sigma: torch.Tensor, eps: torch.Tensor | None, std_out: torch.Tensor,
+                action_out: torch.Tensor, logp_out: torch.Tensor, deterministic: bool = False) -> None:
+    """Normal.rsample + log_prob into the buffer slots (distribution.py:195-213); see the header."""
+    N, A = mean.shape
+    f32 = torch.float32
+    code = _lib.load().cusrl_b200_sample_logp_f32(
+        _ptr(mean, f32, "mean"), _ptr(sigma, f32, "sigma"), _ptr(eps, f32, "eps"), N, A, int(deterministic),
+        _ptr(std_out, f32, "std"), _ptr(action_out, f32, "action"), _ptr(logp_out, f32, "action_logp"), _stream())
+    _lib.check(code, "sample_logp")
 
 
 # ---------------------------------------------------------------------------------------------- K5

@@ -139,8 +139,12 @@ class ActorCritic:
         self.iteration = 0
         self.step_index = 0
         # opt-in CUDA-graph replay of the train step (template/graphs.py); not part of the reference's surface
-        self.cuda_graphs = os.environ.get("CUSRL_B200_CUDA_GRAPHS", "0") not in ("", "0")
+        self.cuda_graphs = os.environ.get("CUSRL_B200_CUDA_GRAPHS", "1") not in ("", "0")
         self._train_step_graphs = None
+        # fused rollout step (template/rollout.py); CUSRL_B200_FUSED_ROLLOUT=0 forces the generic act / step flow
+        self.fused_rollout = os.environ.get("CUSRL_B200_FUSED_ROLLOUT", "1") not in ("", "0")
+        self._fused_rollout = None
+        self.last_objectives: dict[str, torch.Tensor] | None = None
 
         self.actor_factory, self.critic_factory, self.optimizer_factory = actor_factory, critic_factory, optimizer_factory
         self.hook = HookComposite(hooks)
@@ -197,6 +201,14 @@ class ActorCritic:
     @torch.no_grad()
     def act(self, observation, state=None):
         """actor_critic.py:227-253; output array type follows the input (agent.py:376-391)."""
+        if self.fused_rollout:
+            if self._fused_rollout is None:
+                from .rollout import FusedRollout
+
+                self._fused_rollout = FusedRollout(self)
+            action = self._fused_rollout.act(observation, state)
+            if action is not None:
+                return action
         self.transition.clear()
         self._save_transition(observation=observation, state=state)
         self.hook.pre_act(self.transition)
@@ -215,6 +227,10 @@ class ActorCritic:
     @torch.no_grad()
     def step(self, next_observation, reward, terminated, truncated, next_state=None, **kwargs) -> bool:
         """actor_critic.py:255-291."""
+        if self._fused_rollout is not None and self._fused_rollout.step(next_observation, reward, terminated, truncated,
+                                                                        next_state, kwargs):
+            self.step_index += 1
+            return self.step_index >= self.num_steps_per_update and self.hook.should_update(self.transition)
         self._save_transition(next_observation=next_observation, next_state=next_state, reward=reward,
                               terminated=terminated, truncated=truncated, **kwargs)
         if self.transition["terminated"].dtype != torch.bool:
@@ -264,6 +280,7 @@ class ActorCritic:
         if objectives is not None:
             distributed.reduce_gradients(self.optimizer)
         self._train_step_optimize(metadata, batch, objectives)
+        self.last_objectives = objectives
 
     def _train_step_forward_backward(self, metadata: dict[str, Any], batch: dict[str, Any]):
         """First half of the step: objectives of every hook, their sum in dict order, backward into the flat arena."""

@@ -161,6 +161,13 @@ class Buffer(MutableMapping):
         if self.cursor == self.capacity:
             self.full, self.cursor = True, 0
 
+    def advance(self) -> None:
+        """Move the cursor past a step whose leaves were written in place (template/rollout.py); same wrap-around as
+        :meth:`push`."""
+        self.cursor += 1
+        if self.cursor == self.capacity:
+            self.full, self.cursor = True, 0
+
     def sample(self, sampler: Callable[[str, torch.Tensor], torch.Tensor]) -> dict[str, Nested]:
         """Apply ``sampler(leaf_name, leaf_storage)`` to every leaf and rebuild the nesting."""
         batch = {key: sampler(key, leaf) for key, leaf in self.storage.items()}

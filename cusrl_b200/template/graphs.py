@@ -1,9 +1,8 @@
-"""CUDA-graph capture of the per-minibatch train step (opt-in: ``agent.cuda_graphs = True`` or ``CUSRL_B200_CUDA_GRAPHS=1``).
+"""CUDA-graph capture of the per-minibatch train step (the default on CUDA; ``agent.cuda_graphs = False`` or
+``CUSRL_B200_CUDA_GRAPHS=0`` selects the eager step).
 
-STATUS: EXPERIMENTAL -- written at the end of round 1 and NOT yet run to completion on a B200 (the GPU budget ran out
-during its first run).  Its control flow is exercised on the CPU with ``torch.cuda.graph`` mocked
-(``tools/host_overhead_cpu.py --graphs``); the default (eager) train step does not touch this module.  First item of the
-next round: ``CUSRL_B200_TEST_GRAPHS=1 pytest -m gpu tests/test_graphs_gpu.py``.
+Validated on a B200 in round 2 (tests/test_graphs_gpu.py: replay == eager training over several iterations for the MLP,
+RND and LSTM agents, learning-rate changes between replays, re-capture on a schedule change).
 
 Why.  One train step of the MLP preset is ~60 kernel launches of this library plus ~100 small PyTorch launches, issued
 from Python at ~10-20 us each.  At 65536 environments on one GPU the kernels are long enough to hide that; when the
@@ -126,6 +125,7 @@ class TrainStepGraphs:
             ops.invalidate_weight_cache()
         entry["deferred"] = agent.metrics.end_deferred()
         entry["outputs"] = {name: batch[name] for name in batch if name not in keys_before}
+        entry["objectives"] = objectives
         entry["graph_a"], entry["graph_b"] = graph_a, graph_b
         # the capture ran the host side of a step but no kernel: undo the host bookkeeping, the replay redoes it
         optimizer.step_count = step_before
@@ -146,4 +146,5 @@ class TrainStepGraphs:
         ops.invalidate_weight_cache()
         agent.metrics.apply(entry["deferred"])
         batch.update(entry["outputs"])
+        agent.last_objectives = entry["objectives"]
         self.replays += 1

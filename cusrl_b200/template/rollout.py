@@ -1,0 +1,228 @@
+"""Fused rollout step: ``ActorCritic.act`` / ``ActorCritic.step`` for the standard
+feed-forward PPO agent, writing every transition leaf STRAIGHT into its time-major buffer slot.
+
+The generic path (template/actor_critic.py, the reference's control flow actor_critic.py:227-291) costs, per environment
+step, two full copies of the observation and of the next observation (``to_tensor`` clone + ``Buffer.push``), ~40 small
+elementwise launches for sampling / log-probability / bookkeeping and 14 indexed copies.  Here a step is:
+
+  act :  observation -> its 16-byte-padded slot (one copy kernel; for host inputs one H2D into a staging tensor first, or
+         NOTHING when the array is the very object that ``step`` received as ``next_observation`` one call earlier: the
+         slot of the previous step already holds it on the device);
+         actor trunk (3 tcgen05 GEMMs) -> mean head -> ``action_dist.mean`` slot;  critic trunk -> value head -> ``value`` slot;
+         ONE draw of standard-normal noise from torch's generator (the draw Normal.rsample makes, distribution.py:203) and
+         ONE kernel for std / action / action_logp into their slots;
+  step:  ONE kernel for next_observation (+ next_state), reward, terminated, truncated, done into their slots.
+
+It applies when nothing on the agent needs the generic flow: feed-forward ``Mlp`` actor and critic with SIMT-sized heads,
+no hook other than ``ValueComputation`` overriding ``pre_act`` / ``post_act`` / ``post_step``, training mode, fp32 inputs
+of the declared shapes.  Anything else (recurrent nets, observation normalisation, user hooks, extra transition fields,
+numpy inputs) takes the generic path -- call by call, both write the same storage.  The first step of a run always goes
+through the generic path: its ``Buffer.push`` is what allocates the leaves.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+
+from .. import ops
+from ..nn import functional as F
+from ..nn import modules as M
+from .hook import Hook
+
+__all__ = ["FusedRollout"]
+
+_ROLLOUT_CALLBACKS = ("pre_act", "post_act", "post_step", "should_update")
+
+
+def _overrides(hook: Any, name: str) -> bool:
+    fn = getattr(type(hook), name, None)
+    return fn is not None and fn is not getattr(Hook, name)
+
+
+def _fingerprint(x: torch.Tensor) -> tuple:
+    return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x.device, x._version)
+
+
+def _same_array(x: torch.Tensor, prev: tuple) -> bool:
+    """`x` is the array remembered in `prev` = (tensor kept alive, its fingerprint at that time): same memory, layout and
+    version counter, i.e. the Trainer's ``observation = next_observation`` hand-over (reference trainer.py:313) or an equal
+    view of the same storage.  The remembered tensor is kept alive, so its memory cannot have been recycled."""
+    return isinstance(x, torch.Tensor) and _fingerprint(x) == prev[1] == _fingerprint(prev[0])
+
+
+class _Net:
+    """Forward-only launch plan of one trunk + head with persistent activation buffers."""
+
+    def __init__(self, backbone: M.Mlp, head: torch.nn.Linear, rows: int, device: torch.device):
+        self.linears = backbone.linears()
+        self.act = F.ACTIVATIONS[backbone.activation]
+        self.head = head
+        self.acts = [torch.empty(rows, lin.out_features, device=device) for lin in self.linears]
+
+    def forward(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        precision = ops.GEMM_PRECISION
+        h = x
+        for lin, buf in zip(self.linears, self.acts):
+            h = ops.tc_linear_fwd(h, ops.prepared_weight(lin.weight), lin.bias, lin.out_features, self.act, precision, out=buf)
+        return ops.head_fwd(h, self.head.weight, self.head.bias, out=out)
+
+
+class FusedRollout:
+    REQUIRE_CUDA = True   # tools/host_overhead_cpu.py (kernels stubbed out) clears it to drive this control flow on the CPU
+
+    def __init__(self, agent):
+        self.agent = agent
+        self.enabled = self._supported()
+        self._nets: tuple[_Net, _Net] | None = None
+        self._stage: dict[str, torch.Tensor] = {}
+        self._eps: torch.Tensor | None = None
+        self._prev_next_obs: Any = None      # (tensor, fingerprint) step() received last as next_observation
+        self._prev_next_state: Any = None
+        self._acted_fast = False
+        self.fast_steps = 0
+
+    # ---- applicability ---------------------------------------------------------------------------------------------------
+    def _supported(self) -> bool:
+        agent = self.agent
+        if agent.device.type != "cuda" and self.REQUIRE_CUDA:
+            return False
+        actor, critic = agent.actor, agent.critic
+        if not (isinstance(actor, M.Actor) and isinstance(critic, M.Value)):
+            return False
+        if not (isinstance(actor.backbone, M.Mlp) and isinstance(critic.backbone, M.Mlp)):
+            return False
+        if not (actor.backbone.ends_with_activation and critic.backbone.ends_with_activation):
+            return False
+        if not isinstance(actor.distribution, M.NormalDist):
+            return False
+        if not (F.simt_head_supported(*actor.distribution.mean_head.weight.shape)
+                and F.simt_head_supported(*critic.value_head.weight.shape)):
+            return False
+        from ..hook.on_policy import ValueComputation
+
+        for hook in agent.hook:
+            if isinstance(hook, ValueComputation):
+                continue
+            if any(_overrides(hook, name) for name in _ROLLOUT_CALLBACKS):
+                return False
+        return any(isinstance(h, ValueComputation) for h in agent.hook)
+
+    def _ready(self) -> bool:
+        agent = self.agent
+        if not self.enabled or agent.inference_mode:
+            return False
+        storage = agent.buffer.storage
+        need = ["observation", "action_dist.mean", "action_dist.std", "action", "action_logp", "value", "next_observation",
+                "reward", "terminated", "truncated", "done"]
+        if agent.has_state:
+            need += ["state", "next_state"]
+        if not all(k in storage for k in need):
+            return False  # not allocated yet: the generic path's first push does that
+        extra = set(storage) - set(need) - {"next_value", "advantage", "return"}
+        return not extra  # leaves this path does not know how to fill (user transition fields)
+
+    def _input_ok(self, x, width: int, dtype=torch.float32) -> bool:
+        return (isinstance(x, torch.Tensor) and x.dtype == dtype and x.dim() == 2 and x.shape[0] == self.agent.parallelism
+                and x.shape[1] == width and x.stride(1) == 1 and (x.is_cuda or x.device.type == "cpu"))
+
+    # ---- helpers -----------------------------------------------------------------------------------------------------------
+    def _device_rows(self, x: torch.Tensor, key: str) -> torch.Tensor:
+        """`x` on the device: itself, or its asynchronous H2D copy in a persistent staging tensor."""
+        if x.is_cuda:
+            return x
+        stage = self._stage.get(key)
+        if stage is None or stage.shape != x.shape or stage.dtype != x.dtype:
+            stage = torch.empty(x.shape, dtype=x.dtype, device=self.agent.device)
+            self._stage[key] = stage
+        stage.copy_(x, non_blocking=True)
+        return stage
+
+    def _slot(self, key: str, t: int) -> torch.Tensor:
+        return self.agent.buffer.storage[key][t]
+
+    def _fill_wide(self, key: str, t: int, value: torch.Tensor, prev_obj: Any, prev_key: str) -> torch.Tensor:
+        slot = self._slot(key, t)
+        T = self.agent.buffer.capacity
+        if prev_obj is not None and _same_array(value, prev_obj):
+            # the array the caller passed to step() one call ago: already on the device in the previous step's slot
+            ops.copy_rows_padded(self._slot(prev_key, (t - 1) % T), slot)
+        else:
+            ops.copy_rows_padded(self._device_rows(value, key), slot)
+        return slot
+
+    # ---- act ------------------------------------------------------------------------------------------------------------------
+    def act(self, observation, state):
+        """Returns the action, or ``None`` when this call must take the generic path."""
+        agent = self.agent
+        self._acted_fast = False
+        if not self._ready() or not self._input_ok(observation, agent.observation_dim):
+            return None
+        if agent.has_state != (state is not None) or (state is not None and not self._input_ok(state, agent.state_dim)):
+            return None
+        if self._nets is None:
+            dev, n = agent.device, agent.parallelism
+            self._nets = (_Net(agent.actor.backbone, agent.actor.distribution.mean_head, n, dev),
+                          _Net(agent.critic.backbone, agent.critic.value_head, n, dev))
+        t = agent.buffer.cursor
+        tr = agent.transition
+        tr.clear()
+        obs_slot = self._fill_wide("observation", t, observation, self._prev_next_obs, "next_observation")
+        tr["observation"] = obs_slot
+        critic_in = obs_slot
+        if state is not None:
+            critic_in = self._fill_wide("state", t, state, self._prev_next_state, "next_state")
+            tr["state"] = critic_in
+        actor_net, critic_net = self._nets
+        mean = actor_net.forward(obs_slot, self._slot("action_dist.mean", t))
+        agent.actor.intermediate_repr["backbone.output"] = actor_net.acts[-1]
+        std, action, logp = self._slot("action_dist.std", t), self._slot("action", t), self._slot("action_logp", t)
+        eps = None if agent.deterministic else M.standard_normal_like(mean)
+        ops.sample_logp(mean, agent.actor.distribution.std.param.detach(), eps, std, action, logp, agent.deterministic)
+        tr["action_dist"] = {"mean": mean, "std": std}
+        tr["action"], tr["action_logp"] = action, logp
+        tr["value"] = critic_net.forward(critic_in, self._slot("value", t))
+        agent.critic.intermediate_repr["backbone.output"] = critic_net.acts[-1]
+        self._acted_fast = True
+        if observation.is_cuda:
+            return action.clone()   # the slot is overwritten one rollout later: hand out a private copy
+        return action.to(device=observation.device)
+
+    # ---- step -----------------------------------------------------------------------------------------------------------------
+    def step(self, next_observation, reward, terminated, truncated, next_state, kwargs) -> bool:
+        """True when the transition was stored by the fused kernel (the caller then only advances the counters)."""
+        agent = self.agent
+        self._prev_next_obs, self._prev_next_state = None, None
+        if not self._acted_fast:
+            return False
+        self._acted_fast = False
+        n = agent.parallelism
+        ok = (not any(v is not None for v in kwargs.values()) and self._input_ok(next_observation, agent.observation_dim)
+              and self._input_ok(reward, agent.value_dim) and self._input_ok(terminated, 1, torch.bool)
+              and self._input_ok(truncated, 1, torch.bool)
+              and (agent.has_state == (next_state is not None))
+              and (next_state is None or self._input_ok(next_state, agent.state_dim)))
+        if not ok:
+            # the generic step must find the act outputs in the transition dict: they are the slot views, and push()
+            # recognises tensors that already live in their slot
+            return False
+        t = agent.buffer.cursor
+        tr = agent.transition
+        slots = {k: self._slot(k, t) for k in ("next_observation", "reward", "terminated", "truncated", "done")}
+        ns_slot = self._slot("next_state", t) if next_state is not None else None
+        ops.rollout_store_step(
+            self._device_rows(next_observation, "next_observation"), slots["next_observation"],
+            None if next_state is None else self._device_rows(next_state, "next_state"), ns_slot,
+            self._device_rows(reward.contiguous(), "reward"), slots["reward"],
+            self._device_rows(terminated.contiguous(), "terminated"), self._device_rows(truncated.contiguous(), "truncated"),
+            slots["terminated"], slots["truncated"], slots["done"])
+        tr.update(next_observation=slots["next_observation"], reward=slots["reward"], terminated=slots["terminated"],
+                  truncated=slots["truncated"], done=slots["done"])
+        if ns_slot is not None:
+            tr["next_state"] = ns_slot
+        self._prev_next_obs = (next_observation, _fingerprint(next_observation))
+        self._prev_next_state = None if next_state is None else (next_state, _fingerprint(next_state))
+        agent.buffer.advance()
+        self.fast_steps += 1
+        return True

@@ -277,6 +277,31 @@ int cusrl_b200_lstm_cell_bwd_f32(const float* dh_above, int64_t lddh, const floa
                                  const uint8_t* done, const float* gates, const float* c, const float* c_in, float* dgates,
                                  float* dc_prev, int64_t Nb, int64_t H, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rollout side -- replaces what ActorCritic.act / ActorCritic.step do around the network
+ *     forward passes (template/actor_critic.py:227-291) and Buffer.push (template/buffer.py:124-151: one indexed copy
+ *     per leaf), writing straight into the time-major buffer slots of the current step.
+ *   copy_rows_padded:   dst[r, :width] = src[r, :width], dst[r, width:ldd] = 0 for r < rows (row pitches lds / ldd in
+ *                       floats): a dense [N, 235] observation into its 16-byte-padded slot.
+ *   rollout_store_step: next_observation (and next_state) rows as above, reward [N, reward_dim], terminated, truncated and
+ *                       done = terminated | truncated (actor_critic.py:277) into their slots, ONE launch.  Any group may
+ *                       be omitted by passing NULL for its source.
+ *   sample_logp:        Normal.rsample + Normal.log_prob summed over the action dim (nn/module/distribution.py:195-213)
+ *                       from the mean the head kernel wrote, the state-independent std vector sigma[A] and the
+ *                       standard-normal draw eps[N, A]:  std = sigma;  action = mean + eps * sigma (deterministic != 0:
+ *                       action = mean);  logp = sum_d( -((a-mu)^2) / (2 sigma^2) - log(sigma) - log(sqrt(2 pi)) ),
+ *                       torch's operation order, no FMA contraction.  mean / eps / std / action: dense [N, A], A <= 64. */
+int cusrl_b200_copy_rows_padded_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t width,
+                                    void* stream);
+int cusrl_b200_rollout_store_step_f32(const float* next_obs, int64_t ld_next_obs, float* next_obs_slot, int64_t ld_next_obs_slot,
+                                      int64_t obs_dim, const float* next_state, int64_t ld_next_state, float* next_state_slot,
+                                      int64_t ld_next_state_slot, int64_t state_dim, const float* reward, float* reward_slot,
+                                      int64_t reward_dim, const uint8_t* terminated, const uint8_t* truncated,
+                                      uint8_t* terminated_slot, uint8_t* truncated_slot, uint8_t* done_slot, int64_t N,
+                                      void* stream);
+int cusrl_b200_sample_logp_f32(const float* mean, const float* sigma, const float* eps, int64_t N, int64_t A,
+                               int deterministic, float* std_out, float* action_out, float* logp_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,8 @@ from cusrl_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
-ap.add_argument("--graphs", action="store_true", help="replay the train step from CUDA graphs (agent.cuda_graphs = True)")
+ap.add_argument("--no-graphs", action="store_true", help="eager train step instead of CUDA-graph replay (agent.cuda_graphs = False)")
+ap.add_argument("--no-fused-rollout", action="store_true", help="generic act / step flow instead of template/rollout.py")
 ap.add_argument("--only", default="")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -46,12 +47,13 @@ for name, envs, make in (("mlp_ppo_4096", 4096, mlp), ("lstm_ppo_4096", 4096, ls
     if args.only and args.only not in name:
         continue
     agent = make(envs).from_environment(env)
-    agent.cuda_graphs = args.graphs
+    agent.cuda_graphs = not args.no_graphs
+    agent.fused_rollout = not args.no_fused_rollout
     data = RolloutData(24, envs, dev, seed=1000, pinned_host=False)
     n0 = ops.launch_count()
     seconds, metrics = time_iterations(agent, data, args.steps, args.warmup, False)
     launches = (ops.launch_count() - n0) // (args.steps + args.warmup)
-    print(json.dumps({"config": name, "cuda_graphs": args.graphs, "envs": envs, "rollout_steps": 24, "env_steps_per_s": round(args.steps * 24 * envs / seconds, 1),
+    print(json.dumps({"config": name, "cuda_graphs": not args.no_graphs, "fused_rollout": not args.no_fused_rollout, "envs": envs, "rollout_steps": 24, "env_steps_per_s": round(args.steps * 24 * envs / seconds, 1),
                       "ms_per_iteration": round(seconds / args.steps * 1e3, 3), "gpu_launches_per_iteration": int(launches),
                       "metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")}}), flush=True)
     del agent, data, env

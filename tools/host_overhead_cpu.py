@@ -58,6 +58,9 @@ real_sm = real.cusrl_b200_sm_count
 stub.__dict__["cusrl_b200_sm_count"] = lambda: 148
 
 import cusrl_b200 as C  # noqa: E402
+from cusrl_b200.template.rollout import FusedRollout  # noqa: E402
+
+FusedRollout.REQUIRE_CUDA = False
 from bench import RolloutData, run_iteration  # noqa: E402
 
 dev = torch.device("cpu")
