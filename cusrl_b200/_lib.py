@@ -40,6 +40,11 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int,
         [P, P, P, P, P, c_float, P, P, P, c_int64, c_int64, c_int64, c_double, c_double, c_double, P],
     ),
+    "cusrl_b200_gae_chain_supported": (c_int, [c_int64, c_int64]),
+    "cusrl_b200_gae_chain_scratch_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_gae_set_chain_threads": (c_int, [c_int]),
+    "cusrl_b200_gae_chain_f32": (
+        c_int, [P, P, P, P, P, c_float, P, P, P, c_int64, c_int64, c_double, c_double, c_double, P, P, c_size_t, P]),
     "cusrl_b200_gae_set_config": (c_int, [c_int, c_int]),
     "cusrl_b200_gae_set_variant": (c_int, [c_int, c_int, c_int, c_int]),
     "cusrl_b200_gae_set_schedule": (c_int, [c_int]),

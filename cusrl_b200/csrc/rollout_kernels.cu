@@ -296,6 +296,92 @@ static int launch_gae(const GaeParams& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The whole pre-update chain of the PPO preset in ONE launch (Dv == 1): K3 next_value (value.py:68-82) formed on the fly
+// and published, K1 advantage / return scan (gae.py:8-20,85-110), and the block partial sums K2 needs for the advantage
+// mean / variance (advantage.py:110-111) -- the three reference stages re-read the same [T, N] leaves three times.
+// One thread per env column, the whole rollout of the column in registers (exact-length schedule: loads ascending in
+// time, recurrence descending), THREADS a compile-time block size so that 65536 columns are one wave of one CTA per SM.
+// Arithmetic is the FUSED branch of gae_kernel above, same op order, contraction disabled: bit-identical results.
+// partials: [gridDim.x][2] doubles (sum | sum of squares of the advantages of the block's columns).
+// ------------------------------------------------------------------------------------------------
+template <int T_, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 384 ? 1 : (THREADS >= 192 ? 2 : 4))) gae_chain_kernel(const GaeParams p, double* __restrict__ partials) {
+  __shared__ double smem[2 * 32];
+  const int64_t N = p.N;
+  const int64_t c0 = blockIdx.x * (int64_t)THREADS + threadIdx.x;
+  const bool live = c0 < N;
+  const int64_t c = live ? c0 : 0;  // dead threads of the last block read column 0 and store nothing
+  float r[T_], v[T_];
+  uint8_t te[T_], tr[T_];
+#pragma unroll
+  for (int t = 0; t < T_; ++t) {
+    r[t] = ldg_stream(p.reward + t * N + c);
+    v[t] = ldg_stream(p.value + t * N + c);
+  }
+#pragma unroll
+  for (int t = 0; t < T_; ++t) {
+    te[t] = __ldg(p.done + t * N + c);
+    tr[t] = __ldg(p.truncated + t * N + c);
+  }
+  float v_next = ldg_stream(p.boot + c);
+  uint32_t term_mask = 0, trunc_mask = 0;
+#pragma unroll
+  for (int t = 0; t < T_; ++t) term_mask |= (te[t] ? 1u : 0u) << t, trunc_mask |= (tr[t] ? 1u : 0u) << t;
+  float adv_next = 0.f, adv2_next = 0.f, s = 0.f, q = 0.f;
+#pragma unroll
+  for (int t = T_ - 1; t >= 0; --t) {
+    // value.py:68-82: shift / bootstrap, then terminated, then truncated (final_state_is_missing branch)
+    float nv = v_next;
+    const bool is_term = (term_mask >> t) & 1u, is_trunc = (trunc_mask >> t) & 1u;
+    if (is_term) nv = p.termination_value;
+    if (is_trunc) nv = v[t];
+    const bool done = is_term || is_trunc;  // actor_critic.py:277
+    // gae.py:17  advantage = reward + next_value * gamma - value
+    const float delta = __fsub_rn(__fadd_rn(r[t], __fmul_rn(nv, p.gamma)), v[t]);
+    float a = delta, a2 = delta;
+    if (t != T_ - 1) {
+      // gae.py:19  advantage[t] += not_done[t] * (gamma*lamda) * advantage[t+1]
+      a = __fadd_rn(delta, __fmul_rn(done ? 0.f : p.c_adv, adv_next));
+      if (p.two_lambda) a2 = __fadd_rn(delta, __fmul_rn(done ? 0.f : p.c_ret, adv2_next));
+    }
+    adv_next = a, adv2_next = a2, v_next = v[t];
+    s += a, q += a * a;
+    if (live) {
+      p.advantage[t * N + c0] = a;
+      if (p.ret) p.ret[t * N + c0] = __fadd_rn(v[t], p.two_lambda ? a2 : a);  // gae.py:99-110
+      if (p.next_value_out) p.next_value_out[t * N + c0] = nv;
+    }
+  }
+  double acc[2] = {live ? (double)s : 0.0, live ? (double)q : 0.0};
+  block_sum<2>(acc, smem);
+  if (threadIdx.x == 0) partials[2 * blockIdx.x + 0] = acc[0], partials[2 * blockIdx.x + 1] = acc[1];
+}
+
+static int g_gae_chain_threads = 448;  // 65536 columns = 147 CTAs of 448 threads: one wave, one CTA per SM (gae_set_chain_threads)
+
+template <int T_>
+static unsigned launch_gae_chain_t(const GaeParams& p, double* partials, cudaStream_t s) {
+  const int64_t N = p.N;
+  switch (g_gae_chain_threads) {
+    case 128: { const unsigned g = (unsigned)((N + 127) / 128); gae_chain_kernel<T_, 128><<<g, 128, 0, s>>>(p, partials); return g; }
+    case 256: { const unsigned g = (unsigned)((N + 255) / 256); gae_chain_kernel<T_, 256><<<g, 256, 0, s>>>(p, partials); return g; }
+    default: { const unsigned g = (unsigned)((N + 447) / 448); gae_chain_kernel<T_, 448><<<g, 448, 0, s>>>(p, partials); return g; }
+  }
+}
+
+// returns the number of blocks launched (= partial pairs written), 0 when T has no instantiation
+static unsigned launch_gae_chain(const GaeParams& p, double* partials, cudaStream_t s) {
+  switch (p.T) {
+    case 8: return launch_gae_chain_t<8>(p, partials, s);
+    case 12: return launch_gae_chain_t<12>(p, partials, s);
+    case 16: return launch_gae_chain_t<16>(p, partials, s);
+    case 24: return launch_gae_chain_t<24>(p, partials, s);
+    case 32: return launch_gae_chain_t<32>(p, partials, s);
+    default: return 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: hook/on_policy/advantage.py:108-115
 // ------------------------------------------------------------------------------------------------
 constexpr int kStatsThreads = 256;
@@ -504,6 +590,47 @@ int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, con
   p.c_ret = p.two_lambda ? (float)(gamma * lamda_value) : p.c_adv;
   p.termination_value = termination_value;
   return launch_gae<true>(p, (cudaStream_t)stream);
+}
+
+int cusrl_b200_gae_set_chain_threads(int threads) {
+  if (threads != 128 && threads != 256 && threads != 448) return CUSRL_B200_EINVAL;
+  g_gae_chain_threads = threads;
+  return 0;
+}
+
+size_t cusrl_b200_gae_chain_scratch_bytes(int64_t N) {
+  if (N <= 0) return 0;
+  return (size_t)((N + 127) / 128) * 2 * sizeof(double);
+}
+
+int cusrl_b200_gae_chain_supported(int64_t T, int64_t Dv) {
+  return Dv == 1 && (T == 8 || T == 12 || T == 16 || T == 24 || T == 32);
+}
+
+int cusrl_b200_gae_chain_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* value,
+                             const float* boot_value, float termination_value, float* next_value_out, float* advantage,
+                             float* ret, int64_t T, int64_t N, double gamma, double lamda, double lamda_value,
+                             float* mean_var, void* scratch, size_t scratch_bytes, void* stream) {
+  CUSRL_REQUIRE(reward && terminated && truncated && value && boot_value && advantage && mean_var && scratch,
+                CUSRL_B200_EINVAL, "gae_chain: null pointer");
+  if (int e = gae_common_checks(T, N, 1, gamma, lamda, lamda_value)) return e;
+  CUSRL_REQUIRE(cusrl_b200_gae_chain_supported(T, 1), CUSRL_B200_EUNSUPPORTED,
+                "gae_chain: rollout length %lld has no instantiation (8, 12, 16, 24, 32)", (long long)T);
+  CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_gae_chain_scratch_bytes(N) && aligned_to(scratch, 8), CUSRL_B200_ESCRATCH,
+                "gae_chain: scratch too small or misaligned");
+  GaeParams p{};
+  p.reward = reward, p.done = terminated, p.truncated = truncated, p.value = value, p.boot = boot_value;
+  p.next_value_out = next_value_out, p.advantage = advantage, p.ret = ret, p.T = T, p.N = N, p.Dv = 1;
+  p.gamma = (float)gamma;
+  p.c_adv = (float)(gamma * lamda);  // python double product rounded once (gae.py:19)
+  p.two_lambda = lamda_value >= 0;
+  p.c_ret = p.two_lambda ? (float)(gamma * lamda_value) : p.c_adv;
+  p.termination_value = termination_value;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = launch_gae_chain(p, (double*)scratch, s);
+  if (int e = check_launch("gae_chain_kernel")) return e;
+  adv_stats_finalize<<<1, 256, 0, s>>>((const double*)scratch, (int)blocks, 1, T * N, mean_var);
+  return check_launch("adv_stats_finalize");
 }
 
 size_t cusrl_b200_advantage_stats_scratch_bytes(int64_t Dv) {

@@ -52,6 +52,16 @@ def _first(mapping, *keys):
     raise KeyError(f"none of {keys} found")
 
 
+def _active_neighbor(hook: Hook, offset: int):
+    """The active hook `offset` places after (+) / before (-) `hook` in the agent's hook list, or None."""
+    hooks = list(hook.agent.hook.active_hooks())
+    for i, h in enumerate(hooks):
+        if h is hook:
+            j = i + offset
+            return hooks[j] if 0 <= j < len(hooks) else None
+    return None
+
+
 def _leaf(buffer: Buffer, name: str, like: Tensor) -> Tensor:
     """Persistent ``[T, N, Dv]`` leaf `name` in the buffer (allocated on first use, then overwritten in place)."""
     if name not in buffer:
@@ -123,6 +133,15 @@ class ValueComputation(Hook):
         next_value = _leaf(buffer, "next_value", value)
         next_state = _first(buffer, "next_state", "next_observation")
         boot = critic.evaluate(next_state[-1], memory=self._critic_memory)
+        buffer.private.pop("pending_next_value", None)
+        nxt = _active_neighbor(self, +1)
+        if (not self.bootstrap_truncated_states and isinstance(nxt, GeneralizedAdvantageEstimation) and not nxt.recompute
+                and value.dim() == 3 and ops.gae_chain_supported(value.shape[0], value.shape[2])):
+            # The hook that runs NEXT is the B200 GAE hook: it forms next_value on the fly inside its scan and publishes it
+            # to buffer["next_value"] from the same launch (K3 + K1 + the K2 statistics fused, ops.gae_chain), so nothing
+            # is launched here.  No other hook runs in between, so nobody can observe the leaf before it is written.
+            buffer.private["pending_next_value"] = (boot.contiguous(), float(self.termination_value), next_value)
+            return
         trunc_value = None
         if self.bootstrap_truncated_states:
             # value.py:74-80 evaluates the critic on next_state[truncated] (data-dependent size -> host sync);
@@ -168,6 +187,14 @@ class GeneralizedAdvantageEstimation(Hook):
         value = data["value"]
         if isinstance(data, Buffer):
             advantage, ret = _leaf(data, "advantage", value), _leaf(data, "return", value)
+            data.private.pop("advantage_stats", None)
+            pending = data.private.pop("pending_next_value", None)
+            if pending is not None:
+                boot, termination_value, next_value = pending
+                mean_var = ops.gae_chain(data["reward"], data["terminated"], data["truncated"], value, boot, self.gamma,
+                                         self.lamda, self.lamda_value, termination_value, next_value, advantage, ret)
+                data.private["advantage_stats"] = (mean_var, advantage.data_ptr())
+                return
         else:
             advantage, ret = torch.empty_like(value), torch.empty_like(value)
             data["advantage"], data["return"] = advantage, ret
@@ -185,15 +212,23 @@ class AdvantageNormalization(Hook):
 
     def pre_update(self, buffer) -> None:
         if not self.mini_batch_wise:
-            self.normalize_(buffer["advantage"])
+            advantage = buffer["advantage"]
+            stats = buffer.private.pop("advantage_stats", None)
+            if (stats is not None and stats[1] == advantage.data_ptr()
+                    and isinstance(_active_neighbor(self, -1), GeneralizedAdvantageEstimation)):
+                # the GAE hook that ran immediately before already reduced the statistics in its own launch
+                self.normalize_(advantage, mean_var=stats[0])
+            else:
+                self.normalize_(advantage)
 
     def objective(self, metadata, batch):
         if self.mini_batch_wise:
             self.normalize_(batch["advantage"])
 
     @torch.no_grad()
-    def normalize_(self, advantage: Tensor) -> None:
-        mean_var = ops.advantage_stats(advantage)
+    def normalize_(self, advantage: Tensor, mean_var: Tensor | None = None) -> None:
+        if mean_var is None:
+            mean_var = ops.advantage_stats(advantage)
         if self.synchronize:
             distributed.reduce_mean_var_(mean_var)
         ops.advantage_normalize_(advantage, mean_var, 1e-8)

@@ -19,6 +19,7 @@ __all__ = [
     "next_value",
     "gae",
     "gae_fused",
+    "gae_chain",
     "advantage_stats",
     "advantage_normalize_",
     "merge_mean_var",
@@ -191,6 +192,44 @@ def gae_fused(
     )  # fmt: skip
     _lib.check(code, "gae_fused")
     return advantage, ret
+
+
+def gae_chain_supported(T: int, Dv: int) -> bool:
+    return bool(_lib.load().cusrl_b200_gae_chain_supported(T, Dv))
+
+
+def gae_chain(
+    reward: torch.Tensor,
+    terminated: torch.Tensor,
+    truncated: torch.Tensor,
+    value: torch.Tensor,
+    boot_value: torch.Tensor,
+    gamma: float,
+    lamda: float,
+    lamda_value: float | None,
+    termination_value: float,
+    next_value_out: torch.Tensor | None,
+    advantage: torch.Tensor,
+    ret: torch.Tensor | None,
+    mean_var: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """K3 + K1 + the K2 statistics in one launch (value.py:68-82, gae.py:8-20,85-110, advantage.py:110-111), Dv == 1.
+    Returns mean_var = [mean | unbiased var] of the advantages."""
+    T, N, Dv = _tnd(value)
+    if Dv != 1:
+        raise ValueError("gae_chain: value_dim must be 1")
+    lib = _lib.load()
+    scratch = _get_scratch(value.device, "gaechain", lib.cusrl_b200_gae_chain_scratch_bytes(N))
+    mean_var = torch.empty(2, dtype=torch.float32, device=value.device) if mean_var is None else mean_var
+    f32 = torch.float32
+    code = lib.cusrl_b200_gae_chain_f32(
+        _ptr(reward, f32, "reward"), _flag_ptr(terminated, "terminated"), _flag_ptr(truncated, "truncated"),
+        _ptr(value, f32, "value"), _ptr(boot_value, f32, "boot_value"), float(termination_value),
+        _ptr(next_value_out, f32, "next_value"), _ptr(advantage, f32, "advantage"), _ptr(ret, f32, "return"),
+        T, N, float(gamma), float(lamda), -1.0 if lamda_value is None else float(lamda_value),
+        _ptr(mean_var, f32, "mean_var"), scratch.data_ptr(), scratch.numel(), _stream())
+    _lib.check(code, "gae_chain", launches=2)
+    return mean_var
 
 
 # ---------------------------------------------------------------------------------------------- K2

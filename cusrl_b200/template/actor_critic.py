@@ -280,7 +280,9 @@ class ActorCritic:
         if objectives is not None:
             distributed.reduce_gradients(self.optimizer)
         self._train_step_optimize(metadata, batch, objectives)
-        self.last_objectives = objectives
+        # detached: a live reference to the losses would keep the step's autograd graph (and the parameters' AccumulateGrad
+        # nodes, with the stream they were created on) alive into the next step
+        self.last_objectives = None if objectives is None else {k: v.detach() for k, v in objectives.items()}
 
     def _train_step_forward_backward(self, metadata: dict[str, Any], batch: dict[str, Any]):
         """First half of the step: objectives of every hook, their sum in dict order, backward into the flat arena."""

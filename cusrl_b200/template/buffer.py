@@ -72,6 +72,9 @@ class Buffer(MutableMapping):
         self.schema: dict[str, Nested] = {}
         self.storage: dict[str, torch.Tensor] = {}   # public (possibly narrow) views
         self._backing: dict[str, torch.Tensor] = {}  # padded allocations behind `storage`
+        # hand-shakes between ADJACENT B200 hooks that fuse their kernels across the hook boundary (hook/on_policy.py:
+        # next_value -> GAE -> advantage statistics in one launch); never part of the data contract
+        self.private: dict[str, Any] = {}
 
     # ---- bookkeeping ---------------------------------------------------------------------------
     def get_parallelism(self) -> int:
@@ -79,6 +82,7 @@ class Buffer(MutableMapping):
 
     def clear(self) -> None:
         self.cursor, self.full = 0, False
+        self.private.clear()
         self.storage.clear()
         self._backing.clear()
         self.schema.clear()

@@ -62,6 +62,7 @@ class TrainStepGraphs:
         self._hyper: tuple | None = None
         self.replays = 0
         self.captures = 0
+        self._side_stream = None
 
     # ---- cache keys --------------------------------------------------------------------------------------------------
     def _hyper_key(self) -> tuple:
@@ -85,9 +86,12 @@ class TrainStepGraphs:
             self._hyper = hyper
         key = self._batch_key(metadata, batch)
         entry = self._entries.setdefault(key, {"seen": 0})
-        if entry.get("eager_only") or entry["seen"] < self.WARMUP:
-            entry["seen"] += 1
+        if entry.get("eager_only"):
             agent._train_step_eager(metadata, batch)
+            return
+        if entry["seen"] < self.WARMUP:
+            entry["seen"] += 1
+            self._warmup_step(metadata, batch)
             return
         if "graph_a" not in entry:
             if not self._capture(entry, metadata, batch):
@@ -95,8 +99,26 @@ class TrainStepGraphs:
                 return
         self._replay(entry, batch)
 
+    def _warmup_step(self, metadata: dict[str, Any], batch: dict[str, Any]) -> None:
+        """An eager step on a SIDE stream.  Autograd's AccumulateGrad node of a parameter remembers the stream it was
+        created on and is shared by every graph that is alive at the same time; a node born on the legacy default stream
+        makes the backward pass inside a capture synchronise the legacy stream with the capturing one, which CUDA refuses
+        (cudaErrorStreamCaptureImplicit -- observed on a B200).  Warming up off the default stream is the documented
+        recipe for whole-network capture."""
+        if self.agent.device.type != "cuda":  # the CPU control-flow harness (tools/host_overhead_cpu.py)
+            self.agent._train_step_eager(metadata, batch)
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        current = torch.cuda.current_stream()
+        self._side_stream.wait_stream(current)
+        with torch.cuda.stream(self._side_stream):
+            self.agent._train_step_eager(metadata, batch)
+        current.wait_stream(self._side_stream)
+
     def _capture(self, entry: dict[str, Any], metadata: dict[str, Any], batch: dict[str, Any]) -> bool:
         agent, optimizer = self.agent, self.agent.optimizer
+        agent.last_objectives = None
         optimizer.use_device_scalars()
         ops.invalidate_weight_cache()  # the operand copies of the weights must be rebuilt INSIDE the graph
         keys_before = set(batch)
@@ -125,7 +147,7 @@ class TrainStepGraphs:
             ops.invalidate_weight_cache()
         entry["deferred"] = agent.metrics.end_deferred()
         entry["outputs"] = {name: batch[name] for name in batch if name not in keys_before}
-        entry["objectives"] = objectives
+        entry["objectives"] = {name: value.detach() for name, value in objectives.items()}
         entry["graph_a"], entry["graph_b"] = graph_a, graph_b
         # the capture ran the host side of a step but no kernel: undo the host bookkeeping, the replay redoes it
         optimizer.step_count = step_before

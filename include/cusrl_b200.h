@@ -82,6 +82,19 @@ int cusrl_b200_gae_fused_f32(const float* reward, const uint8_t* terminated, con
 
 /* Tuning knob for K1 (process-wide): columns per thread (1, 2 or 4) and threads per block
  * (multiple of 32, <= 128).  Results are bit-identical for every setting. */
+/* K3 + K1 + K2 statistics in ONE launch (+ a one-block finalisation), Dv == 1: next_value formed on the fly and published
+ * (next_value_out may be NULL), advantage / return exactly as cusrl_b200_gae_fused_f32 (bit-identical), and
+ * mean_var[2] = [mean | unbiased variance] of the advantages (torch.var_mean(correction=1), advantage.py:110-111) from fp64
+ * block partials -- the input of cusrl_b200_advantage_normalize_f32.  T must be one of 8, 12, 16, 24, 32
+ * (cusrl_b200_gae_chain_supported); scratch: cusrl_b200_gae_chain_scratch_bytes(N) bytes, 8-byte aligned.
+ * cusrl_b200_gae_set_chain_threads selects the CTA size (128 / 256 / 448; bit-identical advantages). */
+int cusrl_b200_gae_chain_supported(int64_t T, int64_t Dv);
+size_t cusrl_b200_gae_chain_scratch_bytes(int64_t N);
+int cusrl_b200_gae_set_chain_threads(int threads);
+int cusrl_b200_gae_chain_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* value,
+                             const float* boot_value, float termination_value, float* next_value_out, float* advantage,
+                             float* ret, int64_t T, int64_t N, double gamma, double lamda, double lamda_value,
+                             float* mean_var, void* scratch, size_t scratch_bytes, void* stream);
 int cusrl_b200_gae_set_config(int vec, int threads);
 /* Instruction schedule of the register-resident K1 kernel (process-wide): 0 = chunked kernel with a run-time T,
  * 1 = exact-length kernel (T in {8, 12, 16, 24, 32}: every load issued before the first dependent instruction), other

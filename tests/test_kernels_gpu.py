@@ -142,6 +142,85 @@ def test_gae_fused_equals_separate(ops, T, N, Dv):
     assert torch.equal(adv.cpu(), ref_adv) and torch.equal(ret.cpu(), ref_ret)
 
 
+@pytest.mark.parametrize("T,N", [(24, 65536), (24, 1001), (8, 77), (32, 4096), (16, 449), (12, 128)])
+@pytest.mark.parametrize("lamda_value", [None, 0.9])
+@pytest.mark.parametrize("threads", [128, 256, 448])
+def test_gae_chain_equals_the_three_stages(ops, T, N, lamda_value, threads):
+    """K3 + K1 + K2 statistics in one launch (ops.gae_chain) against the oracle's three separate stages: next_value,
+    advantage and return BIT-exact (every CTA size), mean / unbiased variance to 1e-6 relative, and the normalised
+    advantages that follow from them to the north-star 1e-5."""
+    from cusrl_b200 import _lib
+
+    g = torch.Generator().manual_seed(N + T)
+    reward, value = torch.randn(T, N, 1, generator=g), torch.randn(T, N, 1, generator=g)
+    boot = torch.randn(N, 1, generator=g)
+    term = torch.rand(T, N, 1, generator=g) < 0.03
+    trunc = (torch.rand(T, N, 1, generator=g) < 0.03) & ~term
+    nv_ref = O.next_value_ref(value, term, trunc, boot, 0.25)
+    ref_adv, ref_ret = O.advantage_and_return_ref(reward, term | trunc, value, nv_ref, 0.99, 0.95, lamda_value)
+    nv, adv, ret = (torch.full((T, N, 1), float("nan"), device=DEV) for _ in range(3))
+    assert ops.gae_chain_supported(T, 1) and not ops.gae_chain_supported(T, 2) and not ops.gae_chain_supported(7, 1)
+    try:
+        assert _lib.load().cusrl_b200_gae_set_chain_threads(threads) == 0
+        mean_var = ops.gae_chain(reward.to(DEV), term.to(DEV), trunc.to(DEV), value.to(DEV), boot.to(DEV), 0.99, 0.95,
+                                 lamda_value, 0.25, nv, adv, ret)
+    finally:
+        _lib.load().cusrl_b200_gae_set_chain_threads(448)
+    assert torch.equal(nv.cpu(), nv_ref)
+    assert torch.equal(adv.cpu(), ref_adv) and torch.equal(ret.cpu(), ref_ret)
+    var, mean = torch.var_mean(ref_adv.double(), dim=(0, 1))
+    assert mean_var[0].item() == pytest.approx(mean.item(), rel=1e-6, abs=1e-7)
+    assert mean_var[1].item() == pytest.approx(var.item(), rel=1e-6)
+    ops.advantage_normalize_(adv, mean_var, 1e-8)
+    rel_close(adv, O.normalize_advantage_ref(ref_adv), rtol=1e-5, atol=2e-6)
+
+
+def test_pre_update_chain_fuses_across_adjacent_hooks_only():
+    """ValueComputation defers to the GAE hook only when that hook runs NEXT; a hook in between gets the unfused stages
+    (it may read buffer["next_value"]).  Both orders must give identical leaves."""
+    from cusrl_b200 import build
+
+    build.build()
+    import cusrl_b200 as C
+
+    class Peek(C.Hook):
+        def pre_update(self, buffer):
+            self.seen = buffer["next_value"].clone()
+
+    results = []
+    for with_peek in (False, True):
+        torch.manual_seed(3)
+        factory = C.anymal_c_rough_ppo(num_steps_per_update=8, actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128),
+                                       device=DEV).to_underlying()
+        peek = Peek()
+        if with_peek:
+            factory.register_hook(peek, after="value_computation")
+        env = C.SyntheticEnvironment(300, 19, 5, device=DEV, seed=4)
+        agent = factory.from_environment(env)
+        obs, _, _ = env.reset()
+        for _ in range(8):
+            agent.act(obs)
+            obs, _, reward, term, trunc, _ = env.step(None)
+            agent.step(obs, reward, term, trunc)
+        launches = {}
+        real_chain, real_next_value = C.ops.gae_chain, C.ops.next_value
+        C.ops.gae_chain = lambda *a, **k: (launches.__setitem__("chain", 1), real_chain(*a, **k))[1]
+        C.ops.next_value = lambda *a, **k: (launches.__setitem__("separate", 1), real_next_value(*a, **k))[1]
+        try:
+            agent.hook.pre_update(agent.buffer)
+        finally:
+            C.ops.gae_chain, C.ops.next_value = real_chain, real_next_value
+        assert launches == ({"separate": 1} if with_peek else {"chain": 1})
+        if with_peek:
+            assert torch.equal(peek.seen, agent.buffer["next_value"])
+        results.append({k: agent.buffer[k].clone() for k in ("next_value", "advantage", "return")})
+    for k in results[0]:
+        if k == "advantage":   # normalised with statistics reduced in a different order: equal to fp32 rounding
+            assert torch.allclose(results[0][k], results[1][k], rtol=1e-6, atol=1e-6)
+        else:
+            assert torch.equal(results[0][k], results[1][k]), k
+
+
 def test_gae_full_size_properties(ops):
     """65536 x 24 (BASELINE.json): checked through size-independent properties + a sampled oracle."""
     T, N = 24, 65536
