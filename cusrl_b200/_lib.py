@@ -88,6 +88,19 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int, [P, c_int64, P, P, c_int64, P, c_int64, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, c_int, P,
                 c_size_t, P]),
     "cusrl_b200_dgrad_workspace_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_colsum_workspace_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_colsum_f32": (c_int, [P, c_int64, c_int64, c_int64, P, c_int, P, c_size_t, P]),
+    "cusrl_b200_amax_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P]),
+    "cusrl_b200_split_f16": (c_int, [P, c_int64, c_int64, c_int64, P, P, P, c_int64, P]),
+    "cusrl_b200_weight_prep_f16": (c_int, [P, c_int64, c_int64, P, P, P, c_int64, P, P, c_int64, P, P]),
+    "cusrl_b200_linear_fwd_f16x3": (
+        c_int, [P, P, c_int64, P, P, P, c_int64, P, P, P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, P]),
+    "cusrl_b200_linear_dgrad_f16x3": (
+        c_int, [P, P, c_int64, P, P, P, c_int64, P, P, P, c_int64, P, P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int64,
+                c_int, P, c_int, P, c_size_t, P]),
+    "cusrl_b200_wgrad_f16x3_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "cusrl_b200_linear_wgrad_f16x3": (
+        c_int, [P, P, c_int64, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
     "cusrl_b200_copy_rows_padded_f32": (c_int, [P, c_int64, P, c_int64, c_int64, c_int64, P]),
     "cusrl_b200_rollout_store_step_f32": (
         c_int, [P, c_int64, P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P, P, c_int64, P, P, P, P, P, c_int64, P]),

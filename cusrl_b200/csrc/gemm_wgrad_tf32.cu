@@ -332,6 +332,23 @@ size_t cusrl_b200_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   return partial + colsum + 256;
 }
 
+size_t cusrl_b200_colsum_workspace_bytes(int64_t N) { return N > 0 ? (size_t)1184 * (size_t)N * sizeof(float) : 0; }
+
+int cusrl_b200_colsum_f32(const float* dZ, int64_t lddz, int64_t M, int64_t N, float* db, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  CUSRL_REQUIRE(dZ && db && workspace, CUSRL_B200_EINVAL, "colsum: null pointer");
+  CUSRL_REQUIRE(M > 0 && N > 0 && lddz >= N && M < (1ll << 31), CUSRL_B200_EINVAL, "colsum: bad sizes");
+  CUSRL_REQUIRE(workspace_bytes >= cusrl_b200_colsum_workspace_bytes(N), CUSRL_B200_ESCRATCH, "colsum: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int nb = sm_count() * 8;
+  if (nb > 1184) nb = 1184;
+  int rows_per_block = (int)((M + nb - 1) / nb);
+  nb = (int)((M + rows_per_block - 1) / rows_per_block);
+  colsum_partial_kernel<<<nb, 256, 0, s>>>(dZ, lddz, (int)M, (int)N, rows_per_block, (float*)workspace);
+  if (int e = check_launch("colsum_partial_kernel")) return e;
+  return colsum_finalize((const float*)workspace, nb, (int)N, db, accumulate, s);
+}
+
 int cusrl_b200_linear_wgrad_tf32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, float* dW, int64_t lddw,
                                  float* db, int64_t M, int64_t N, int64_t K, int precision, int accumulate,
                                  void* workspace, size_t workspace_bytes, void* stream) {

@@ -19,7 +19,7 @@ import torch
 
 from .. import ops
 
-__all__ = ["ACTIVATIONS", "linear_head", "mlp_forward", "mlp_head_forward"]
+__all__ = ["ACTIVATIONS", "f16_trunk_forward", "f16x3_supported", "linear_head", "mlp_forward", "mlp_head_forward"]
 
 ACTIVATIONS = {"Identity": 0, "ELU": 1, "ReLU": 2}
 
@@ -50,7 +50,7 @@ def _wgrad(dz, inp, weight, bias, grads, slot, bias_slot=None, bias_done=False):
     """Weight / bias gradient of one layer: accumulate into the flat arena when the parameter has one, otherwise hand
     fresh tensors to autograd through ``grads[slot]`` / ``grads[bias_slot]`` (default: the adjacent slot).
     ``bias_done``: the bias gradient was already produced by the kernel that produced ``dz`` (its column sums)."""
-    precision = ops.GEMM_PRECISION
+    precision = ops.tf32_passes()
     bias_slot = slot + 1 if bias_slot is None else bias_slot
     if _in_arena(weight, bias):
         ops.tc_linear_wgrad(dz, inp, weight.grad, None if (bias is None or bias_done) else bias.grad, precision, accumulate=True)
@@ -73,14 +73,96 @@ def _bias_target(weight, bias, grads, bias_slot):
     return grads[bias_slot], False
 
 
+# ---- precision 2: f16x3 (fp16 hi / lo split operands, csrc/f16x3_common.cuh) ---------------------------------------------
+def f16x3_supported(weights, biases) -> bool:
+    """The f16x3 kernels need output widths that are multiples of 4 and biases (for the analytic range bounds)."""
+    return all(w.shape[0] % 4 == 0 for w in weights) and all(b is not None for b in biases)
+
+
+def f16_trunk_forward(x: torch.Tensor, linears, act_code: int, last_act: bool):
+    """Forward of a Linear(+activation) stack on the f16x3 kernels: the input is split once (exact amax + split), hidden
+    activations stay fp16 hi / lo pairs written by the GEMM epilogues (never materialised in fp32), the last layer's output
+    is fp32.  Returns (x pair, [hidden pairs..., fp32 output])."""
+    xp = ops.split_f16(x if x.stride(-1) == 1 else x.contiguous())
+    h, acts = xp, []
+    n = len(linears)
+    for i, (w, b) in enumerate(linears):
+        code = act_code if (i < n - 1 or last_act) else 0
+        h = ops.f16_linear_fwd(h, ops.prepared_weight_f16(w, b), b, code, out_pair=i < n - 1)
+        acts.append(h)
+    return xp, acts
+
+
+def _f16_forward(ctx, x, act_code, last_act, has_head, n, params):
+    weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
+    xp, acts = f16_trunk_forward(x, list(zip(weights, biases)), act_code, last_act)
+    latent = acts[-1]
+    if has_head:
+        out = ops.head_fwd(latent, params[2 * n], params[2 * n + 1])
+    ctx.save_for_backward(latent, *params)
+    ctx.pairs = (xp, acts[:-1])   # fp16 pairs are not autograd tensors: they ride on the context
+    ctx.meta = (act_code, last_act, has_head, n)
+    if has_head:
+        ctx.mark_non_differentiable(latent)
+        return out, latent
+    return latent
+
+
+def _f16_backward(ctx, grad_out):
+    act_code, last_act, has_head, n = ctx.meta
+    x_req = ctx.needs_input_grad[0]
+    latent, params = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+    xp, hidden = ctx.pairs
+    weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
+    grads: list[torch.Tensor | None] = [None] * len(params)
+    last_code = act_code if last_act else 0
+    if has_head:
+        head_w, head_b = params[2 * n], params[2 * n + 1]
+        hw_grad, hb_grad = head_w.grad, (head_b.grad if head_b is not None else None)
+        arena = hw_grad is not None and (head_b is None or hb_grad is not None)
+        dw = hw_grad if arena else torch.empty_like(head_w)
+        db = hb_grad if arena else (torch.empty_like(head_b) if head_b is not None else None)
+        db_trunk, acc_trunk = _bias_target(weights[n - 1], biases[n - 1], grads, 2 * n - 1)
+        dz = ops.head_bwd(grad_out.contiguous(), latent, head_w, last_code, dw, db, need_dh=True, accumulate=arena,
+                          db_trunk=db_trunk, accumulate_trunk=acc_trunk)
+        if not arena:
+            grads[2 * n], grads[2 * n + 1] = dw, db
+    else:
+        dz = ops.act_grad_mul(grad_out, latent, last_code)
+        db_last, acc_last = _bias_target(weights[n - 1], biases[n - 1], grads, 2 * n - 1)
+        if db_last is not None:
+            ops.colsum_(dz, db_last, accumulate=acc_last)
+    dzp = ops.split_f16(dz)   # the gradient entering the trunk: exact amax + split; below it stays in pairs
+    for i in range(n - 1, -1, -1):
+        inp = hidden[i - 1] if i > 0 else xp
+        w = weights[i]
+        if w.requires_grad:
+            if _in_arena(w, biases[i]):
+                ops.f16_linear_wgrad(dzp, inp, w.grad, accumulate=True)
+            else:
+                grads[2 * i] = torch.empty_like(w)
+                ops.f16_linear_wgrad(dzp, inp, grads[2 * i], accumulate=False)
+        if i > 0:
+            db_below, acc_below = _bias_target(weights[i - 1], biases[i - 1], grads, 2 * i - 1)
+            dzp = ops.f16_linear_dgrad(dzp, ops.prepared_weight_f16(w, biases[i]), hidden[i - 1], act_code, out_pair=True,
+                                       db_below=db_below, accumulate=acc_below)
+        elif x_req:
+            dx = ops.f16_linear_dgrad(dzp, ops.prepared_weight_f16(w, biases[i]), None, 0, out_pair=False)
+            return (dx, None, None, None, *grads)
+    return (None, None, None, None, *grads)
+
+
 class _MlpHeadFunction(torch.autograd.Function):
     """(latent, out) = trunk(x), head(trunk(x)); `has_head=False` returns the trunk output only."""
 
     @staticmethod
     def forward(ctx, x, act_code, last_act, has_head, *params):
-        precision = ops.GEMM_PRECISION
+        precision = ops.tf32_passes()
         n = (len(params) - (2 if has_head else 0)) // 2
         weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
+        ctx.f16 = ops.GEMM_PRECISION == 2 and f16x3_supported(weights, biases)
+        if ctx.f16:
+            return _f16_forward(ctx, x, act_code, last_act, has_head, n, params)
         x = _rows_ok(x)
         acts = []
         h = x
@@ -100,9 +182,11 @@ class _MlpHeadFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, *unused):
+        if ctx.f16:
+            return _f16_backward(ctx, grad_out)
         act_code, last_act, has_head, n = ctx.meta
         x_req = ctx.needs_input_grad[0]
-        precision = ops.GEMM_PRECISION
+        precision = ops.tf32_passes()
         saved = ctx.saved_tensors
         x, acts, params = saved[0], saved[1 : 1 + n], saved[1 + n :]
         weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
@@ -188,14 +272,14 @@ class _HeadFunction(torch.autograd.Function):
         if simt:
             y = ops.head_fwd(x, weight, bias)
         elif No % 4 == 0:
-            y = ops.tc_linear_fwd(x, ops.prepared_weight(weight), bias, No, 0, ops.GEMM_PRECISION)
+            y = ops.tc_linear_fwd(x, ops.prepared_weight(weight), bias, No, 0, ops.tf32_passes())
         else:
             # e.g. a 21-dimensional action head: the dense-layer kernels need 16-byte output rows, so the layer runs with
             # zero rows appended to W (and zero columns to dY in the backward); the public tensors keep their shapes
             Np = (No + 3) // 4 * 4
             ctx.padded = ops.weight_prep(_pad_rows(weight.detach(), Np))
             bias_p = None if bias is None else _pad_rows(bias.detach(), Np)
-            y = ops.tc_linear_fwd(x, ctx.padded, bias_p, Np, 0, ops.GEMM_PRECISION)[:, :No]
+            y = ops.tc_linear_fwd(x, ctx.padded, bias_p, Np, 0, ops.tf32_passes())[:, :No]
         ctx.save_for_backward(x, weight, bias)
         ctx.simt = simt
         return y
@@ -216,7 +300,7 @@ class _HeadFunction(torch.autograd.Function):
                 grads = [dw, db]
         elif ctx.padded is None:
             _wgrad(dy, x, weight, bias, grads, 0)
-            dx = ops.tc_linear_dgrad(dy, ops.prepared_weight(weight), None, weight.shape[1], 0, ops.GEMM_PRECISION) if need_dx else None
+            dx = ops.tc_linear_dgrad(dy, ops.prepared_weight(weight), None, weight.shape[1], 0, ops.tf32_passes()) if need_dx else None
         else:
             No, K = weight.shape
             Np = ctx.padded["hi"].shape[0]
@@ -226,7 +310,7 @@ class _HeadFunction(torch.autograd.Function):
             db_p = torch.empty(Np, device=dy.device) if bias is not None else None
             ops.tc_linear_wgrad(dy_p, x, dw_p, db_p, ops.GEMM_PRECISION, accumulate=False)
             grads = [dw_p[:No], None if db_p is None else db_p[:No]]
-            dx = ops.tc_linear_dgrad(dy_p, ctx.padded, None, K, 0, ops.GEMM_PRECISION) if need_dx else None
+            dx = ops.tc_linear_dgrad(dy_p, ctx.padded, None, K, 0, ops.tf32_passes()) if need_dx else None
         return dx, grads[0], grads[1]
 
 

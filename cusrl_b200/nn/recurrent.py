@@ -27,7 +27,7 @@ class _LstmFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, h0, c0, done, num_layers, *weights):
-        precision = ops.GEMM_PRECISION
+        precision = ops.tf32_passes()
         T, Nb, _ = x.shape
         H = h0.shape[-1]
         dev = x.device
@@ -69,7 +69,7 @@ class _LstmFunction(torch.autograd.Function):
     def backward(ctx, d_out, _dh, _dc):
         from .functional import _wgrad
 
-        precision = ops.GEMM_PRECISION
+        precision = ops.tf32_passes()
         T, Nb, H, num_layers = ctx.meta
         weights = ctx.saved_tensors
         done = ctx.done

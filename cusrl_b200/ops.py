@@ -469,7 +469,13 @@ def adam_step_dev_(
 
 # ---------------------------------------------------------------------------------------------- K6
 # Dense layers on tcgen05 (csrc/gemm_tf32.cu, csrc/gemm_wgrad_tf32.cu) and SIMT heads (csrc/head_kernels.cu).
-GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))  # 3 = 3xTF32 (fp32-equivalent), 1 = TF32
+# 3 = 3xTF32 (fp32-equivalent), 2 = f16x3 (fp16 hi / lo split, fp32-equivalent, half the tensor time), 1 = single-pass TF32
+GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))
+
+
+def tf32_passes() -> int:
+    """`precision` argument for the tf32 kernels: layers the f16x3 path does not cover run as 3xTF32 when it is selected."""
+    return 3 if GEMM_PRECISION == 2 else GEMM_PRECISION
 
 _weights_epoch = 0
 _weight_cache: dict[int, tuple[tuple, dict[str, torch.Tensor], "weakref.ref"]] = {}
@@ -631,6 +637,185 @@ def head_bwd(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: t
         scratch.data_ptr(), scratch.numel(), _stream())
     _lib.check(code, "head_bwd", launches=2)
     return dh
+
+
+# ---------------------------------------------------------------------------------------------- K6, precision 2 (f16x3)
+# Dense layers on tcgen05 kind::f16 with fp16 hi / lo split operands (csrc/f16x3_common.cuh, gemm_f16x3.cu,
+# gemm_wgrad_f16x3.cu): fp32-equivalent products at half the tensor time of 3xTF32.
+class Pair:
+    """fp16 hi / lo split of an fp32 [rows, width] matrix: ``data[0]`` = hi, ``data[1]`` = lo (both [rows, ld], ld a multiple
+    of 8 halves, columns >= width zero) and ``bound`` = a device scalar that is >= max|x| (it fixes the power-of-two scale)."""
+
+    __slots__ = ("data", "bound", "width")
+
+    def __init__(self, data: torch.Tensor, bound: torch.Tensor, width: int):
+        self.data, self.bound, self.width = data, bound, width
+
+    @property
+    def rows(self) -> int:
+        return self.data.shape[1]
+
+    @property
+    def ld(self) -> int:
+        return self.data.shape[2]
+
+    @property
+    def hi(self) -> torch.Tensor:
+        return self.data[0]
+
+    @property
+    def lo(self) -> torch.Tensor:
+        return self.data[1]
+
+    def float(self) -> torch.Tensor:
+        """The fp32 matrix the pair represents (tests / debugging): (hi + lo) / scale."""
+        import math
+
+        b = float(self.bound)
+        scale = 1.0 if not (b > 0) else 2.0 ** max(-60, min(60, 15 - math.frexp(b)[1]))
+        return ((self.data[0].float() + self.data[1].float()) / scale)[:, : self.width]
+
+
+def pair_empty(rows: int, width: int, device) -> Pair:
+    ld = (width + 7) // 8 * 8
+    return Pair(torch.empty(2, rows, ld, dtype=torch.float16, device=device), torch.empty(1, dtype=torch.float32, device=device), width)
+
+
+def amax(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """max|x| of a 2-D fp32 tensor (unit inner stride) as a 1-element device tensor: the exact bound of an input."""
+    xp, ld = _rows(x, "x")
+    out = torch.empty(1, dtype=torch.float32, device=x.device) if out is None else out
+    code = _lib.load().cusrl_b200_amax_f32(xp, ld, x.shape[0], x.shape[1], _ptr(out, torch.float32, "bound"), _stream())
+    _lib.check(code, "amax")
+    return out
+
+
+def split_f16(x: torch.Tensor, bound: torch.Tensor | None = None, out: Pair | None = None) -> Pair:
+    """The fp16 hi / lo pair of a 2-D fp32 tensor; `bound` defaults to its exact amax (one extra pass)."""
+    xp, ld = _rows(x, "x")
+    rows, width = x.shape
+    out = pair_empty(rows, width, x.device) if out is None else out
+    if bound is None:
+        amax(x, out=out.bound)
+    else:
+        out.bound = bound
+    code = _lib.load().cusrl_b200_split_f16(xp, ld, rows, width, _ptr(out.bound, torch.float32, "bound"), out.data[0].data_ptr(),
+                                            out.data[1].data_ptr(), out.ld, _stream())
+    _lib.check(code, "split_f16")
+    return out
+
+
+def weight_prep_f16(w: torch.Tensor, bias: torch.Tensor | None, out: dict | None = None) -> dict:
+    """Pair, transposed pair and norm statistics of a weight matrix [N, K] (cusrl_b200_weight_prep_f16)."""
+    N, K = w.shape
+    ld, ldt = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    if out is None:
+        f16 = torch.float16
+        out = {"pair": torch.zeros(2, N, ld, dtype=f16, device=w.device), "pair_t": torch.zeros(2, K, ldt, dtype=f16, device=w.device),
+               "stats": torch.zeros(4, dtype=torch.float32, device=w.device), "shape": (N, K)}
+    code = _lib.load().cusrl_b200_weight_prep_f16(
+        _ptr(w.detach(), torch.float32, "weight"), N, K, None if bias is None else _ptr(bias.detach(), torch.float32, "bias"),
+        out["pair"][0].data_ptr(), out["pair"][1].data_ptr(), ld, out["pair_t"][0].data_ptr(), out["pair_t"][1].data_ptr(), ldt,
+        out["stats"].data_ptr(), _stream())
+    _lib.check(code, "weight_prep_f16", launches=2)
+    return out
+
+
+_weight_cache_f16: dict[int, tuple[tuple, dict, "weakref.ref"]] = {}
+
+
+def prepared_weight_f16(w: torch.Tensor, bias: torch.Tensor | None) -> dict:
+    """:func:`weight_prep_f16` of a parameter, rebuilt once per optimizer step (same protocol as :func:`prepared_weight`)."""
+    key = w.data_ptr()
+    stamp = (_weights_epoch, w._version, tuple(w.shape), None if bias is None else (bias.data_ptr(), bias._version))
+    hit = _weight_cache_f16.get(key)
+    alive = hit is not None and hit[2]() is not None
+    if alive and hit[0] == stamp:
+        return hit[1]
+    reuse = alive and hit[0][2] == stamp[2]
+    wp = weight_prep_f16(w, bias, out=hit[1] if reuse else None)
+    _weight_cache_f16[key] = (stamp, wp, hit[2] if reuse else weakref.ref(w))
+    if len(_weight_cache_f16) > 256:
+        for k in [k for k, v in _weight_cache_f16.items() if v[2]() is None]:
+            del _weight_cache_f16[k]
+    return wp
+
+
+def f16_linear_fwd(x: Pair, wp: dict, bias: torch.Tensor | None, act: int, out_pair: bool = True,
+                   out: "Pair | torch.Tensor | None" = None):
+    """Y = act(X W^T + b) from pairs; returns a Pair (its bound is the analytic one, published by the kernel) or fp32."""
+    N, K = wp["shape"]
+    M = x.rows
+    if x.width != K:
+        raise ValueError(f"f16_linear_fwd: input width {x.width} != weight K {K}")
+    lib = _lib.load()
+    w = wp["pair"]
+    if out_pair:
+        y = pair_empty(M, N, x.data.device) if out is None else out
+        args = (None, 0, y.data[0].data_ptr(), y.data[1].data_ptr(), y.ld, y.bound.data_ptr())
+    else:
+        y = torch.empty(M, N, device=x.data.device) if out is None else out
+        yp, ldy = _rows(y, "y")
+        args = (yp, ldy, None, None, 0, None)
+    code = lib.cusrl_b200_linear_fwd_f16x3(
+        x.data[0].data_ptr(), x.data[1].data_ptr(), x.ld, x.bound.data_ptr(), w[0].data_ptr(), w[1].data_ptr(), w.shape[2],
+        wp["stats"].data_ptr(), None if bias is None else _ptr(bias.detach(), torch.float32, "bias"), *args, M, N, K, act, _stream())
+    _lib.check(code, "linear_fwd_f16x3")
+    return y
+
+
+def f16_linear_dgrad(dy: Pair, wp: dict, x_act: Pair | None, act: int, out_pair: bool = True, db_below: torch.Tensor | None = None,
+                     accumulate: bool = False):
+    """dX = (dY W) * act'(x_act) from pairs (W as its transposed pair); `db_below` (+)= column sums of dX."""
+    N, K = wp["shape"]
+    M = dy.rows
+    if dy.width != N:
+        raise ValueError(f"f16_linear_dgrad: gradient width {dy.width} != weight N {N}")
+    lib = _lib.load()
+    wt = wp["pair_t"]
+    dev = dy.data.device
+    if out_pair:
+        dx = pair_empty(M, K, dev)
+        args = (None, 0, dx.data[0].data_ptr(), dx.data[1].data_ptr(), dx.ld, dx.bound.data_ptr())
+    else:
+        dx = torch.empty(M, (K + 3) // 4 * 4, device=dev)[:, :K]
+        args = (dx.data_ptr(), dx.stride(0), None, None, 0, None)
+    if db_below is not None:
+        ws = _get_scratch(dev, "dgrad", lib.cusrl_b200_dgrad_workspace_bytes(K))
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    else:
+        ws_ptr, ws_bytes = None, 0
+    aux = (None, None, 0, None) if x_act is None else (x_act.data[0].data_ptr(), x_act.data[1].data_ptr(), x_act.ld, x_act.bound.data_ptr())
+    code = lib.cusrl_b200_linear_dgrad_f16x3(
+        dy.data[0].data_ptr(), dy.data[1].data_ptr(), dy.ld, dy.bound.data_ptr(), wt[0].data_ptr(), wt[1].data_ptr(), wt.shape[2],
+        wp["stats"].data_ptr(), *aux, *args, M, N, K, act, _ptr(db_below, torch.float32, "db_below"), int(accumulate), ws_ptr,
+        ws_bytes, _stream())
+    _lib.check(code, "linear_dgrad_f16x3", launches=1 if db_below is None else 2)
+    return dx
+
+
+def colsum_(dz: torch.Tensor, db: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """db (+)= column sums of a 2-D fp32 tensor (the bias gradient of a dense layer)."""
+    M, N = dz.shape
+    dzp, ld = _rows(dz, "dz")
+    lib = _lib.load()
+    ws = _get_scratch(dz.device, "colsum", lib.cusrl_b200_colsum_workspace_bytes(N))
+    code = lib.cusrl_b200_colsum_f32(dzp, ld, M, N, _ptr(db, torch.float32, "db"), int(accumulate), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(code, "colsum", launches=2)
+    return db
+
+
+def f16_linear_wgrad(dz: Pair, x: Pair, dw: torch.Tensor, accumulate: bool = False) -> None:
+    """dW (+)= dZ^T X from the two pairs (cusrl_b200_linear_wgrad_f16x3)."""
+    M, N, K = dz.rows, dz.width, x.width
+    if x.rows != M or not dw.is_contiguous() or dw.shape != (N, K):
+        raise ValueError("f16_linear_wgrad: shape mismatch (dw must be a contiguous [N, K] tensor)")
+    lib = _lib.load()
+    ws = _get_scratch(dz.data.device, "wgrad16", lib.cusrl_b200_wgrad_f16x3_workspace_bytes(M, N, K))
+    code = lib.cusrl_b200_linear_wgrad_f16x3(
+        dz.data[0].data_ptr(), dz.data[1].data_ptr(), dz.ld, dz.bound.data_ptr(), x.data[0].data_ptr(), x.data[1].data_ptr(), x.ld,
+        x.bound.data_ptr(), dw.data_ptr(), K, M, N, K, int(accumulate), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(code, "linear_wgrad_f16x3", launches=2)
 
 
 # ---------------------------------------------------------------------------------------------- rollout (f1)

@@ -62,7 +62,12 @@ class _Net:
         self.acts = [torch.empty(rows, lin.out_features, device=device) for lin in self.linears]
 
     def forward(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        precision = ops.GEMM_PRECISION
+        pairs = [(lin.weight, lin.bias) for lin in self.linears]
+        if ops.GEMM_PRECISION == 2 and F.f16x3_supported(*zip(*pairs)):
+            _, acts = F.f16_trunk_forward(x, pairs, self.act, True)
+            self.acts[-1] = acts[-1]
+            return ops.head_fwd(acts[-1], self.head.weight, self.head.bias, out=out)
+        precision = ops.tf32_passes()
         h = x
         for lin, buf in zip(self.linears, self.acts):
             h = ops.tc_linear_fwd(h, ops.prepared_weight(lin.weight), lin.bias, lin.out_features, self.act, precision, out=buf)

@@ -315,6 +315,49 @@ int cusrl_b200_rollout_store_step_f32(const float* next_obs, int64_t ld_next_obs
 int cusrl_b200_sample_logp_f32(const float* mean, const float* sigma, const float* eps, int64_t N, int64_t A,
                                int deterministic, float* std_out, float* action_out, float* logp_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6, precision 2 ("f16x3") -- the same dense layers (nn.Linear + activation, nn/module/mlp.py:77-90, and their autograd)
+ *     on tcgen05 kind::f16 with fp16 hi / lo SPLIT operands:  x s = hi + lo,  hi = fp16(x s),  lo = fp16(x s - hi),  s a
+ *     per-tensor power of two derived from a device-resident upper bound of max|x|;
+ *     A B^T = (Ah Bh^T + Ah Bl^T + Al Bh^T) / (sA sB) with fp32 accumulation: fp32-equivalent results at 1.5 TF32 passes
+ *     instead of 3xTF32's three (accuracy and rationale: csrc/f16x3_common.cuh).
+ *   A "pair" is two dense fp16 matrices [rows, ld] (ld a multiple of 8 halves, columns >= width zero) plus one float bound.
+ *   amax:            bound[0] = max|x| of an fp32 [rows, width] array (row pitch ld floats) -- the exact bound of an input.
+ *   split_f16:       the pair of x with the scale of *bound.
+ *   weight_prep_f16: pair of W[N,K] (+ transposed pair [K, ldt]) and stats[4] = { max|W|, max_n sum_k|W_nk|,
+ *                    max_k sum_n|W_nk|, max|bias| }: the factors of the ANALYTIC output bounds
+ *                    bound(act(x W^T + b)) <= bound(x) stats[1] + stats[3]   and   bound((dz W) act') <= bound(dz) stats[2],
+ *                    which the GEMM kernels compute and publish (y_bound / dx_bound) without any extra pass.
+ *   linear_fwd_f16x3:   Y = act(X W^T + b); output EITHER fp32 (Y, ldy) OR a pair (Yhi, Ylo, ldyh, y_bound).  N % 4 == 0.
+ *   linear_dgrad_f16x3: dX = (dY W) * act'(Xact) with W given as the transposed pair; Xact pair optional; output fp32 or
+ *                       pair; db_below (+)= column sums of dX (optional; workspace as cusrl_b200_dgrad_workspace_bytes).
+ *   linear_wgrad_f16x3: dW (+)= dZ^T X from the two pairs (reduction over the M batch rows). */
+/* db[n] (+)= sum_m dZ[m, n]: the bias gradient of a dense layer from its fp32 pre-activation gradient (fixed-order, fp64
+ * finalisation); workspace: cusrl_b200_colsum_workspace_bytes(N) bytes. */
+size_t cusrl_b200_colsum_workspace_bytes(int64_t N);
+int cusrl_b200_colsum_f32(const float* dZ, int64_t lddz, int64_t M, int64_t N, float* db, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int cusrl_b200_amax_f32(const float* x, int64_t ld, int64_t rows, int64_t width, float* bound, void* stream);
+int cusrl_b200_split_f16(const float* x, int64_t ld, int64_t rows, int64_t width, const float* bound, uint16_t* hi, uint16_t* lo,
+                         int64_t ldh, void* stream);
+int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float* bias, uint16_t* hi, uint16_t* lo, int64_t ld,
+                               uint16_t* hi_t, uint16_t* lo_t, int64_t ldt, float* stats, void* stream);
+int cusrl_b200_linear_fwd_f16x3(const uint16_t* Xhi, const uint16_t* Xlo, int64_t ldx, const float* x_bound, const uint16_t* Whi,
+                                const uint16_t* Wlo, int64_t ldw, const float* w_stats, const float* bias, float* Y, int64_t ldy,
+                                uint16_t* Yhi, uint16_t* Ylo, int64_t ldyh, float* y_bound, int64_t M, int64_t N, int64_t K,
+                                int act, void* stream);
+int cusrl_b200_linear_dgrad_f16x3(const uint16_t* dYhi, const uint16_t* dYlo, int64_t lddy, const float* dy_bound,
+                                  const uint16_t* WThi, const uint16_t* WTlo, int64_t ldwt, const float* w_stats,
+                                  const uint16_t* Xact_hi, const uint16_t* Xact_lo, int64_t ldxa, const float* xact_bound,
+                                  float* dX, int64_t lddx32, uint16_t* dXhi, uint16_t* dXlo, int64_t lddx, float* dx_bound,
+                                  int64_t M, int64_t N, int64_t K, int act, float* db_below, int accumulate, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+size_t cusrl_b200_wgrad_f16x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int cusrl_b200_linear_wgrad_f16x3(const uint16_t* dZhi, const uint16_t* dZlo, int64_t lddz, const float* dz_bound,
+                                  const uint16_t* Xhi, const uint16_t* Xlo, int64_t ldx, const float* x_bound, float* dW,
+                                  int64_t lddw, int64_t M, int64_t N, int64_t K, int accumulate, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,11 @@ for s in "$@"; do
     tests_all)  step tests_all 600 python -u -m pytest tests -q -m gpu --timeout 120 ;;
     graphs_tests) step graphs_tests 300 env CUSRL_B200_TEST_GRAPHS=1 python -u -m pytest tests/test_graphs_gpu.py -x -v -m gpu --timeout 120 ;;
     graphs_fps) step graphs_fps 200 bash -c "python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --no-graphs --no-fused-rollout; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --no-graphs; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2" ;;
+    f16tests)   step f16tests 400 python -u -m pytest tests/test_gemm_f16x3_gpu.py -q -m gpu --timeout 60 -x -rf -s ;;
+    f16bench)   step f16bench 300 python tools/f16x3_bench.py ;;
+    tests_p2)   step tests_p2 900 env CUSRL_B200_GEMM_PRECISION=2 python -u -m pytest tests -q -m gpu --timeout 300 -rf ;;
+    bench_p2)   step bench_p2 600 env CUSRL_B200_GEMM_PRECISION=2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-cuda ;;
+    configs_p2) step configs_p2 400 env CUSRL_B200_GEMM_PRECISION=2 python tools/config_fps.py ;;
     fp16probe)  step fp16probe 300 python tools/fp16_split_probe.py ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
     launches)   step launches 230 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-reference-cuda ;;
