@@ -93,6 +93,11 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_amax_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P]),
     "cusrl_b200_split_f16": (c_int, [P, c_int64, c_int64, c_int64, P, P, P, c_int64, P]),
     "cusrl_b200_weight_prep_f16": (c_int, [P, c_int64, c_int64, P, P, P, c_int64, P, P, c_int64, P, P]),
+    "cusrl_b200_gather_split_f16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int64, P, P, P, c_int64, P]),
+    "cusrl_b200_head_bwd_f16pair": (
+        c_int, [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, P, c_int64, c_int64, c_int64, c_int, P, c_int, P, c_size_t, P]),
+    "cusrl_b200_f16x3_set_prefetch": (c_int, [c_int]),
+    "cusrl_b200_f16x3_set_tile": (c_int, [c_int]),
     "cusrl_b200_linear_fwd_f16x3": (
         c_int, [P, P, c_int64, P, P, P, c_int64, P, P, P, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int64, c_int, P]),
     "cusrl_b200_linear_dgrad_f16x3": (

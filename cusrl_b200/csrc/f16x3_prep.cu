@@ -39,76 +39,88 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
 
 // ---- split -----------------------------------------------------------------------------------------------------------
 // hi / lo [rows, ldh] halves from x [rows, width] fp32 (pitch ld); columns width..ldh-1 are written as zeros so the rows are
-// zero-padded TMA sources.  One warp per row, lanes stride 2-element units.
+// zero-padded TMA sources.  One thread per 8 consecutive columns: two 16-byte loads in, one 16-byte store per half out.
+__device__ __forceinline__ void split8(const float (&x)[8], float s, uint4& h, uint4& l) {
+  __half2* h2 = reinterpret_cast<__half2*>(&h);
+  __half2* l2 = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = x[2 * k] * s, b = x[2 * k + 1] * s;
+    h2[k] = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2[k]);
+    l2[k] = __floats2half2_rn(a - back.x, b - back.y);
+  }
+}
+
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int width,
                                                         const float* __restrict__ bound, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, int64_t ldh) {
   const float s = f16x3_scale(__ldg(bound));
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int units = (int)(ldh >> 1);
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    const float* src = x + r * ld;
-    __half2* h2 = reinterpret_cast<__half2*>(hi + r * ldh);
-    __half2* l2 = reinterpret_cast<__half2*>(lo + r * ldh);
-    for (int u = lane; u < units; u += 32) {
-      const int c = 2 * u;
-      const float a = c < width ? ldg_stream(src + c) * s : 0.f;
-      const float b = c + 1 < width ? ldg_stream(src + c + 1) * s : 0.f;
-      const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-      h2[u] = __halves2half2(ha, hb);
-      l2[u] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+  const int units = (int)(ldh >> 3);  // 8-column units per row
+  const int64_t total = rows * units;
+  const bool vec = (ld & 3) == 0 && aligned_to(x, 16);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / units;
+    const int c = (int)(i - r * units) * 8;
+    const float* src = x + r * ld + c;
+    float v[8];
+    if (vec && c + 8 <= width) {
+      const float4 a = ldg_stream4(src), b = ldg_stream4(src + 4);
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c + k < width ? ldg_stream(src + k) : 0.f;
     }
+    uint4 h, l;
+    split8(v, s, h, l);
+    *reinterpret_cast<uint4*>(hi + r * ldh + c) = h;
+    *reinterpret_cast<uint4*>(lo + r * ldh + c) = l;
   }
 }
 
 // ---- weights ---------------------------------------------------------------------------------------------------------
-// stats[4] = { max|W|, max_n sum_k |W[n,k]|, max_k sum_n |W[n,k]|, max|bias| }  (one block; the matrices are <= ~130 k entries)
-__global__ void __launch_bounds__(1024) weight_stats_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
-                                                            float* __restrict__ stats) {
-  __shared__ float red[3][32];
-  float amax = 0.f, row_l1 = 0.f, col_l1 = 0.f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float a = fabsf(w[(int64_t)n * K + k]);
+// stats[4] = { max|W|, max_n sum_k |W[n,k]|, max_k sum_n |W[n,k]|, max|bias| }, zeroed by the launcher; combined across
+// blocks with integer atomicMax (non-negative floats order like their bit patterns).  Blocks 0 .. row_blocks-1 take 8 rows
+// each (one warp per row, lanes along the contiguous K axis); the remaining blocks take 256 columns each (one thread per
+// column, coalesced across the block).  The L1 norms are rounded sums: consumers widen the bounds they build from them.
+__global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
+                                                           float* __restrict__ stats, int row_blocks) {
+  unsigned int* out = reinterpret_cast<unsigned int*>(stats);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x < row_blocks) {
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    float s = 0.f, amax = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float a = fabsf(__ldg(w + (int64_t)n * K + k));
       s += a, amax = fmaxf(amax, a);
     }
-    row_l1 = fmaxf(row_l1, s);
-  }
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += fabsf(w[(int64_t)n * K + k]);
-    col_l1 = fmaxf(col_l1, s);
-  }
-  float bmax = 0.f;
-  if (bias)
-    for (int n = threadIdx.x; n < N; n += blockDim.x) bmax = fmaxf(bmax, fabsf(bias[n]));
-  float v[4] = {amax, row_l1, col_l1, bmax};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
-  __shared__ float red4[4][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) red4[i][warp] = v[i];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float t = lane < nw ? red4[i][lane] : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
-      // the sums above are rounded: widen the L1 norms by a few ulps so they stay upper bounds
-      if (lane == 0) stats[i] = (i == WSTAT_ROW_L1 || i == WSTAT_COL_L1) ? t * 1.0001f : t;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     }
+    if (lane == 0) {
+      atomicMax(out + WSTAT_AMAX, __float_as_uint(amax));
+      atomicMax(out + WSTAT_ROW_L1, __float_as_uint(s));
+      if (bias) atomicMax(out + WSTAT_BIAS_MAX, __float_as_uint(fabsf(__ldg(bias + n))));
+    }
+  } else {
+    const int k = ((int)blockIdx.x - row_blocks) * 256 + threadIdx.x;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (k < K) {
+      int n = 0;
+      for (; n + 4 <= N; n += 4) {
+        s0 += fabsf(__ldg(w + (int64_t)n * K + k)), s1 += fabsf(__ldg(w + (int64_t)(n + 1) * K + k));
+        s2 += fabsf(__ldg(w + (int64_t)(n + 2) * K + k)), s3 += fabsf(__ldg(w + (int64_t)(n + 3) * K + k));
+      }
+      for (; n < N; ++n) s0 += fabsf(__ldg(w + (int64_t)n * K + k));
+    }
+    float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) atomicMax(out + WSTAT_COL_L1, __float_as_uint(s));
   }
-  (void)red;
 }
 
 // hi / lo [N, ld] and transposed hi_t / lo_t [K, ldt] halves of W [N, K] with the scale of stats[WSTAT_AMAX]; the padding
@@ -194,7 +206,7 @@ int cusrl_b200_split_f16(const float* x, int64_t ld, int64_t rows, int64_t width
   CUSRL_REQUIRE(rows > 0 && width > 0 && ld >= width && ldh >= width && (ldh % 8) == 0 && ldh < (1ll << 30), CUSRL_B200_EINVAL,
                 "split_f16: bad sizes (ldh must be a multiple of 8 halves covering the row)");
   CUSRL_REQUIRE(aligned_to(hi, 16) && aligned_to(lo, 16), CUSRL_B200_EALIGN, "split_f16: outputs must be 16-byte aligned");
-  int64_t blocks = (rows + 7) / 8;
+  int64_t blocks = (rows * (ldh / 8) + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, (int)width, bound, (__half*)hi, (__half*)lo, ldh);
@@ -208,7 +220,10 @@ int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float
   CUSRL_REQUIRE((hi_t == nullptr) == (lo_t == nullptr) && (!hi_t || (ldt >= N && (ldt % 8) == 0)), CUSRL_B200_EINVAL,
                 "weight_prep_f16: transposed outputs must be given together with ldt >= N, a multiple of 8");
   cudaStream_t s = (cudaStream_t)stream;
-  weight_stats_kernel<<<1, 1024, 0, s>>>(W, (int)N, (int)K, bias, stats);
+  cudaError_t me = cudaMemsetAsync(stats, 0, 4 * sizeof(float), s);
+  CUSRL_REQUIRE(me == cudaSuccess, (int)me, "weight_prep_f16: cudaMemsetAsync: %s", cudaGetErrorString(me));
+  const int row_blocks = (int)((N + 7) / 8), col_blocks = (int)((K + 255) / 256);
+  weight_stats_kernel<<<row_blocks + col_blocks, 256, 0, s>>>(W, (int)N, (int)K, bias, stats, row_blocks);
   if (int e = check_launch("weight_stats_kernel")) return e;
   if (ld > K) {  // zero the padding columns once per call (cheap: the matrices are tiny)
     cudaMemsetAsync(hi, 0, (size_t)N * ld * 2, s);

@@ -2,6 +2,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "f16x3_common.cuh"
 
 namespace cusrl_b200 {
 
@@ -51,6 +52,45 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
     case 4: gather_field<uint32_t>(f, a.index, a.n_index, a.n_src_rows); break;
     case 2: gather_field<uint16_t>(f, a.index, a.n_index, a.n_src_rows); break;
     default: gather_field<uint8_t>(f, a.index, a.n_index, a.n_src_rows); break;
+  }
+}
+
+// K8 for the f16x3 dense layers: dst pair[i] = split(src[index[i]]) -- the gathered minibatch rows of a wide fp32 leaf
+// (observation / state) emitted directly as the fp16 hi / lo pair the first trunk layer consumes, so the minibatch is not
+// re-read by a separate split pass.  One thread per 8 consecutive columns (two 16-byte loads, one 16-byte store per half).
+__global__ void __launch_bounds__(256) gather_split_f16_kernel(const float* __restrict__ src, int64_t lds, const int64_t* __restrict__ index,
+                                                               int64_t n, int64_t n_src_rows, int width, const float* __restrict__ bound,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldh) {
+  const float s = f16x3_scale(__ldg(bound));
+  const int units = (int)(ldh >> 3);
+  const int64_t total = n * units;
+  const bool vec = (lds & 3) == 0 && aligned_to(src, 16);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / units;
+    const int c = (int)(i - r * units) * 8;
+    int64_t row = __ldg(index + r);
+    row = row < 0 ? 0 : (row >= n_src_rows ? n_src_rows - 1 : row);
+    const float* p = src + row * lds + c;
+    float v[8];
+    if (vec && c + 8 <= width) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c + k < width ? __ldg(p + k) : 0.f;
+    }
+    uint4 h, l;
+    __half2* h2 = reinterpret_cast<__half2*>(&h);
+    __half2* l2 = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = v[2 * k] * s, b = v[2 * k + 1] * s;
+      h2[k] = __floats2half2_rn(a, b);
+      const float2 back = __half22float2(h2[k]);
+      l2[k] = __floats2half2_rn(a - back.x, b - back.y);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldh + c) = h;
+    *reinterpret_cast<uint4*>(lo + r * ldh + c) = l;
   }
 }
 
@@ -178,6 +218,21 @@ int cusrl_b200_gather_rows(const cusrl_b200_gather_field* fields_host, int n_fie
   dim3 grid((unsigned)blocks, (unsigned)n_fields);
   gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("gather_rows_kernel");
+}
+
+int cusrl_b200_gather_split_f16(const float* src, int64_t lds, const int64_t* index, int64_t n, int64_t n_src_rows, int64_t width,
+                                const float* bound, uint16_t* hi, uint16_t* lo, int64_t ldh, void* stream) {
+  CUSRL_REQUIRE(src && index && bound && hi && lo, CUSRL_B200_EINVAL, "gather_split_f16: null pointer");
+  CUSRL_REQUIRE(n >= 0 && n_src_rows > 0 && width > 0 && lds >= width && ldh >= width && (ldh % 8) == 0, CUSRL_B200_EINVAL,
+                "gather_split_f16: bad sizes (ldh must be a multiple of 8 halves covering the row)");
+  CUSRL_REQUIRE(aligned_to(hi, 16) && aligned_to(lo, 16), CUSRL_B200_EALIGN, "gather_split_f16: outputs must be 16-byte aligned");
+  if (n == 0) return 0;
+  int64_t blocks = (n * (ldh / 8) + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, index, n, n_src_rows, (int)width, bound,
+                                                                            (__half*)hi, (__half*)lo, ldh);
+  return check_launch("gather_split_f16_kernel");
 }
 
 int cusrl_b200_grad_sumsq_f32(const float* grad, int64_t n, double* sumsq_dev, void* stream) {

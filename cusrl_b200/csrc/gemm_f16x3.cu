@@ -20,7 +20,13 @@ namespace cusrl_b200 {
 
 constexpr int FBK = 64;            // halves per k-block = 128 bytes
 constexpr int F_UMMA_K = 16;       // halves per tcgen05.mma
-constexpr int kF16Threads = 384;   // warps: 0 TMA, 1 MMA, 2 TMEM, 3 idle, 4-11 epilogue
+// warps: 0 TMA, 1 MMA, 2 TMEM, 3 idle, 4.. epilogue.  The epilogue (TMEM -> activation -> fp16 split -> store) is what bounds
+// the layers with many outputs per reduction step: with 128 x 256 tiles only 8 epilogue warps fit (4 KB of staging each next
+// to two 96 KB stages) and the 235->512 layer takes 453 us at M = 393 216; 128 x 128 tiles leave room for 16.
+template <int BN>
+constexpr int f16_epi_warps() { return BN == 128 ? 16 : 8; }
+template <int BN>
+constexpr int f16_threads() { return 128 + 32 * f16_epi_warps<BN>(); }
 
 enum { OUT_F32 = 0, OUT_PAIR = 1 };
 
@@ -36,6 +42,7 @@ struct F16GemmParams {
   int M, N, K, act;
   int num_m_tiles, num_n_tiles, num_items;
   float* colsum;            // EPI_ACT_GRAD, optional: [gridDim.x][4][N] column sums of the fp32 output values
+  int prefetch;             // k-blocks the L2 prefetch of the A tiles runs ahead of the loads (0 = off)
 };
 
 template <int BN>
@@ -43,9 +50,11 @@ struct F16Cfg {
   static constexpr int A_BYTES = BM * FBK * 2;     // 16 KB
   static constexpr int B_BYTES = BN * FBK * 2;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi + lo of both operands
-  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 6 ? 6 : (kSmemBudget / STAGE_BYTES);
+  static constexpr int EPI_WARPS = f16_epi_warps<BN>();
+  static constexpr int EPI_BYTES = EPI_WARPS * kEpiWarpBytes;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiStageBytes + BAR_BYTES + 1024;
+  static constexpr int STAGES = ((226 * 1024 - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES) > 4 ? 4 : ((226 * 1024 - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static_assert(STAGES >= 2, "tile does not fit in shared memory");
 };
 
@@ -66,7 +75,23 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
-// One 32-row x 32-column chunk of the epilogue, one warp, lane = accumulator row within the chunk.
+// fp16 hi / lo split of two fp32 values with ONE conversion instruction per half2: hi = cvt.rn.f16x2(a, b); the fp32 value
+// of hi is rebuilt with integer arithmetic (round-to-nearest-even at mantissa bit 13) instead of converting back, which is
+// exact wherever hi is a normal fp16 number; below 2^-14 (2^-29 of the tensor's bound) it differs from the stored hi by at
+// most 2^-25, i.e. 2^-40 of the bound -- the same floor lo's gradual underflow has.
+__device__ __forceinline__ float f16_round_as_f32(float a) {
+  const uint32_t b = __float_as_uint(a);
+  return __uint_as_float((b + 0xfffu + ((b >> 13) & 1u)) & 0xffffe000u);
+}
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  lo = __floats2half2_rn(a - f16_round_as_f32(a), b - f16_round_as_f32(b));
+}
+
+// One 32-row x 32-column chunk of the epilogue, one warp, lane = accumulator row within the chunk.  Measured alternatives
+// to the bulk tensor stores on a B200 (us for the 235->512 / 512->256 / 256->128 layers at M = 393 216): bulk stores
+// 434 / 295 / 153, row-per-lane direct global stores 544 / 347 / 168, shared-memory transpose + coalesced global stores
+// 472 / 320 / 170 -- the epilogue is not what bounds the kernel (see the A-tile L2 prefetch in the producer).
 // Staging (4 KB per warp): OUT_F32  one 32 x 32 fp32 block, SWIZZLE_128B;
 //                          OUT_PAIR two 32 x 32 fp16 blocks (hi at +0, lo at +2048), 64-byte rows, SWIZZLE_64B.
 template <int EPI, int OUT>
@@ -95,15 +120,34 @@ __device__ __forceinline__ void f16_epilogue_chunk(const F16GemmParams& p, const
     }
   }
   tmem_ld_wait();
+  // From here on v holds the output ALREADY MULTIPLIED by the output scale s_out (1 for fp32 outputs): the epilogue is
+  // instruction-bound (ncu: ~1000 warp instructions per 32 x 32 chunk with two epilogue warps per scheduler, tensor pipe
+  // 31 % on the 235->512 layer), so every multiply that can be folded is.
   float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * inv_ab;
   if (EPI == EPI_BIAS_ACT) {
+    const float* ef = reinterpret_cast<const float*>(e);
+    const float neg_s = -s_out;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      v[4 * q + 0] = act_fwd(v[4 * q + 0] + e[q].x, p.act), v[4 * q + 1] = act_fwd(v[4 * q + 1] + e[q].y, p.act);
-      v[4 * q + 2] = act_fwd(v[4 * q + 2] + e[q].z, p.act), v[4 * q + 3] = act_fwd(v[4 * q + 3] + e[q].w, p.act);
+    for (int j = 0; j < 32; ++j) {
+      const float z = fmaf(__uint_as_float(r[j]), inv_ab, ef[j]);   // x W^T + b
+      const float t = OUT == OUT_PAIR ? z * s_out : z;
+      if (p.act == 1) {
+        // ELU: z <= 0 -> exp(z) - 1 with ex2.approx (2-ulp exponential: < 2.4e-7 ABSOLUTE on a value of magnitude < 1,
+        // i.e. fp32 rounding level of the O(1) sums it feeds; the 3xTF32 kernel's extra Taylor branch for |z| < 1/8
+        // would cost 8 more instructions per element here)
+        float ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * 1.4426950408889634f));
+        v[j] = z > 0.f ? t : fmaf(ex, s_out, neg_s);
+      } else if (p.act == 2) {
+        v[j] = fmaxf(t, 0.f);
+      } else {
+        v[j] = t;
+      }
     }
+  } else {
+    const float k = OUT == OUT_PAIR ? inv_ab * s_out : inv_ab;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * k;
   }
   if (lane == 0) tma_store_wait_read();  // the previous chunk's stores have finished reading the staging buffer
   __syncwarp();
@@ -146,12 +190,7 @@ __device__ __forceinline__ void f16_epilogue_chunk(const F16GemmParams& p, const
       __half2* h2 = reinterpret_cast<__half2*>(&h);
       __half2* l2 = reinterpret_cast<__half2*>(&l);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = v[8 * u + 2 * k] * s_out, b = v[8 * u + 2 * k + 1] * s_out;
-        const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-        h2[k] = __halves2half2(ha, hb);
-        l2[k] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
-      }
+      for (int k = 0; k < 4; ++k) split2(v[8 * u + 2 * k], v[8 * u + 2 * k + 1], h2[k], l2[k]);
       reinterpret_cast<uint4*>(stg + lane * 64)[u ^ sw] = h;
       reinterpret_cast<uint4*>(stg + 2048 + lane * 64)[u ^ sw] = l;
     }
@@ -166,7 +205,7 @@ __device__ __forceinline__ void f16_epilogue_chunk(const F16GemmParams& p, const
   if (EPI == EPI_ACT_GRAD && p.colsum) {
     // bias gradient of the layer below = column sums of this output (rows >= M hold exact zeros: their accumulators are
     // products of zero-filled A rows); one owner per (CTA, row quarter, column) slot, so plain read-modify-write
-    const float sum = warp_column_sums(v, lane);
+    const float sum = warp_column_sums(v, lane) * (OUT == OUT_PAIR ? 1.f / s_out : 1.f);  // v carries the output scale
     if (col0 + lane < p.N) {
       float* slot = p.colsum + ((int64_t)blockIdx.x * 4 + ((threadIdx.x >> 5) & 3)) * p.N + col0 + lane;
       *slot += sum;
@@ -175,7 +214,7 @@ __device__ __forceinline__ void f16_epilogue_chunk(const F16GemmParams& p, const
 }
 
 template <int BN, int EPI, int OUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF16Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(f16_threads<BN>(), 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutLo, const F16GemmParams p) {
@@ -189,7 +228,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   auto sBhi = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
   auto sBlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
   uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
   uint64_t* full = bars;                  // TMA bytes landed (own A pair + both halves of the B pair)
   uint64_t* empty = bars + STAGES;        // MMAs of BOTH CTAs reading the stage retired
   uint64_t* tfull = bars + 2 * STAGES;    // accumulator complete
@@ -216,7 +255,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
       // |(dz W) act'| <= bound(dz) max_k sum_n |W_nk|  (here B = W^T, so that is its row L1 norm = W's column norm; act' <= 1)
       b = bound_a * __ldg(p.wstats + WSTAT_COL_L1);
     }
-    b *= 1.0001f;  // the products above are rounded
+    b *= 1.001f;  // the L1 norms are rounded sums and the products above are rounded: stay an upper bound
     s_out = f16x3_scale(b);
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.bound_out) *p.bound_out = b;
   }
@@ -236,7 +275,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
+      mbar_init(&tempty[a], Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -255,9 +294,23 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      // The A tiles stream from HBM (~1 us away) while the B tiles come from L2, and two 96 KB stages keep only ~32 KB of A
+      // requests in flight per SM -- below the bandwidth-delay product of HBM (measured: 1.8 us per k-block against 0.83 us
+      // of tensor time).  A second cursor therefore runs p.prefetch k-blocks AHEAD of the loads and pulls the A tiles into
+      // L2 with bulk prefetches, so that the loads themselves see L2 latency.
+      int pf_item = cluster_id, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_item >= p.num_items) return;
+        const int pm0 = item_m0(pf_item);
+        tma_prefetch_2d(&tmAhi, pf_kb * FBK, pm0);
+        tma_prefetch_2d(&tmAlo, pf_kb * FBK, pm0);
+        if (++pf_kb == num_k_blocks) pf_kb = 0, pf_item += num_clusters;
+      };
+      for (int i = 0; i < p.prefetch; ++i) prefetch_next();
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const int m0 = item_m0(item), n0 = item_n0(item);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+          if (p.prefetch > 0) prefetch_next();
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
           tma_load_2d(sAhi(s), &tmAhi, kb * FBK, m0, &full[s]);
@@ -305,7 +358,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
     const int ew = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;   // which half of the tile's columns
+    constexpr int COLS = BN / (Cfg::EPI_WARPS / 4);   // columns of the tile this warp owns
+    const int part = (warp - 4) >> 2;
     uint8_t* stg = epi_stage + (warp - 4) * kEpiWarpBytes;
     int local = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++local) {
@@ -317,7 +371,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
       const uint32_t taddr = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(ew * 32) << 16);
       if (row0 < p.M) {
 #pragma unroll 1
-        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32)
+        for (int c0 = part * COLS; c0 < (part + 1) * COLS; c0 += 32)
           if (n0 + c0 < p.N)
             f16_epilogue_chunk<EPI, OUT>(p, &tmOut, &tmOutLo, stg, taddr + (uint32_t)c0, row0, n0 + c0, lane, inv_ab, inv_aux, s_out);
       }
@@ -340,6 +394,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
+int g_f16_prefetch = 0;  // measured on a B200: prefetching the A tiles into L2 never helps (0: 307 us, 4: 313, 16: 347 for 512->256)
+int g_f16_bn = 0;        // 0 = choose by N (256 when N > 128), 128 / 256 = force (cusrl_b200_f16x3_set_tile)
+;  // cusrl_b200_f16x3_set_prefetch; shared with gemm_wgrad_f16x3.cu
+
 int colsum_finalize(const float* partial, int nblocks, int N, float* db, int accumulate, cudaStream_t s);  // gemm_wgrad_tf32.cu
 
 template <int BN, int EPI, int OUT>
@@ -356,7 +414,7 @@ static int launch_f16_gemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const
     }
     configured = true;
   }
-  kern<<<gemm_grid_ctas(p.num_items), kF16Threads, Cfg::SMEM_BYTES, s>>>(tAh, tAl, tBh, tBl, tO, tOl, p);
+  kern<<<gemm_grid_ctas(p.num_items), f16_threads<BN>(), Cfg::SMEM_BYTES, s>>>(tAh, tAl, tBh, tBl, tO, tOl, p);
   return check_launch("gemm_f16x3_kernel");
 }
 
@@ -385,7 +443,7 @@ static int f16_gemm(const uint16_t* Ahi, const uint16_t* Alo, int64_t lda, const
                     (!out32 || aligned_to(out32, 16)) && (!pair || (aligned_to(out_hi, 16) && aligned_to(out_lo, 16))) &&
                     (!bias || aligned_to(bias, 16)) && (!aux_hi || (aligned_to(aux_hi, 16) && aligned_to(aux_lo, 16))),
                 CUSRL_B200_EALIGN, "linear_f16x3: pointers must be 16-byte aligned");
-  const int bn = N > 128 ? 256 : 128;
+  const int bn = g_f16_bn ? g_f16_bn : (N > 128 ? 256 : 128);
   const uint64_t Kp = (uint64_t)((K + 7) / 8 * 8);
   CUtensorMap tAh, tAl, tBh, tBl, tO, tOl;
   if (int e = encode_tmap_2d_f16(&tAh, Ahi, Kp, (uint64_t)M, (uint64_t)lda, FBK, BM, TMAP_SW128)) return e;
@@ -404,6 +462,7 @@ static int f16_gemm(const uint16_t* Ahi, const uint16_t* Alo, int64_t lda, const
   p.bias = bias, p.aux_hi = (const __half*)aux_hi, p.aux_lo = (const __half*)aux_lo, p.ldaux = ldaux;
   p.bound_a = bound_a, p.wstats = wstats, p.bound_aux = bound_aux, p.bound_out = bound_out;
   p.M = (int)M, p.N = (int)N, p.K = (int)K, p.act = act;
+  p.prefetch = g_f16_prefetch;
   p.num_m_tiles = (int)((M + BM - 1) / BM);
   p.num_n_tiles = (int)((N + bn - 1) / bn);
   p.num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
@@ -438,6 +497,18 @@ static int f16_gemm(const uint16_t* Ahi, const uint16_t* Alo, int64_t lda, const
 using namespace cusrl_b200;
 
 extern "C" {
+
+int cusrl_b200_f16x3_set_tile(int bn) {
+  if (bn != 0 && bn != 128 && bn != 256) return CUSRL_B200_EINVAL;
+  g_f16_bn = bn;
+  return 0;
+}
+
+int cusrl_b200_f16x3_set_prefetch(int k_blocks) {
+  if (k_blocks < 0 || k_blocks > 64) return CUSRL_B200_EINVAL;
+  g_f16_prefetch = k_blocks;
+  return 0;
+}
 
 int cusrl_b200_linear_fwd_f16x3(const uint16_t* Xhi, const uint16_t* Xlo, int64_t ldx, const float* x_bound, const uint16_t* Whi,
                                 const uint16_t* Wlo, int64_t ldw, const float* w_stats, const float* bias, float* Y, int64_t ldy,

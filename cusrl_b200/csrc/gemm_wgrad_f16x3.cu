@@ -16,6 +16,8 @@ namespace cusrl_b200 {
 
 using namespace tc;
 
+extern int g_f16_prefetch;  // gemm_f16x3.cu
+
 constexpr int WGF_BM = 128;        // output features per tile (UMMA M)
 constexpr int WGF_BKB = 64;        // batch rows per k-block
 constexpr int WGF_CHUNK = 64;      // features per 128-byte swizzle span
@@ -28,6 +30,7 @@ struct WgradF16Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits;
   int rows_per_split;    // multiple of WGF_BKB
+  int prefetch;          // k-blocks the L2 prefetch runs ahead of the loads (0 = off)
 };
 
 template <int BN>
@@ -99,8 +102,26 @@ wgrad_f16x3_kernel(const __grid_constant__ CUtensorMap tmDZhi, const __grid_cons
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      // both operands stream from HBM and two 96 KB stages keep too few requests in flight to cover its latency: a second
+      // cursor pulls the tiles of k-block kb + p.prefetch into L2 (see gemm_f16x3.cu)
+      auto prefetch_kb = [&](int kb) {
+        if (kb >= num_kb) return;
+        const int r0 = row_begin + kb * WGF_BKB;
+#pragma unroll
+        for (int c = 0; c < WGF_BM / WGF_CHUNK; ++c) {
+          tma_prefetch_2d(&tmDZhi, f0 + c * WGF_CHUNK, r0);
+          tma_prefetch_2d(&tmDZlo, f0 + c * WGF_CHUNK, r0);
+        }
+#pragma unroll
+        for (int c = 0; c < BN / WGF_CHUNK; ++c) {
+          tma_prefetch_2d(&tmXhi, k0 + c * WGF_CHUNK, r0);
+          tma_prefetch_2d(&tmXlo, k0 + c * WGF_CHUNK, r0);
+        }
+      };
+      for (int i = 0; i < p.prefetch; ++i) prefetch_kb(i);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int r0 = row_begin + kb * WGF_BKB;
+        if (p.prefetch > 0) prefetch_kb(kb + p.prefetch);
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         // rows beyond M are zero-filled by TMA and contribute nothing; a slab is a multiple of 64 rows, so a k-block never
@@ -291,6 +312,7 @@ int cusrl_b200_linear_wgrad_f16x3(const uint16_t* dZhi, const uint16_t* dZlo, in
   WgradF16Params p{};
   p.partial = (float*)workspace, p.ldp = ldp, p.M = (int)M, p.N = (int)N, p.K = (int)K;
   p.num_m_tiles = mt, p.num_n_tiles = nt, p.splits = splits, p.rows_per_split = rps;
+  p.prefetch = g_f16_prefetch;
   int e = bn == 256 ? launch_wgrad_f16<256>(tZh, tZl, tXh, tXl, p, s) : launch_wgrad_f16<128>(tZh, tZl, tXh, tXl, p, s);
   if (e) return e;
   const int64_t split_stride = (int64_t)mt * WGF_BM * ldp;

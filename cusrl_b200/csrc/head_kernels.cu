@@ -6,6 +6,7 @@
 //             dW[No,K] (+)= dY^T @ H ;  db[No] (+)= column sums of dY
 //             dbH[K]   (+)= column sums of dH        (optional: the bias gradient of the trunk's last layer)
 #include "common.cuh"
+#include "f16x3_common.cuh"
 
 namespace cusrl_b200 {
 
@@ -87,11 +88,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const float* __r
 
 // backward: lane l owns columns {128*v + 4*l .. +3} of every row its warp handles (W and the dW accumulators stay in
 // registers); the NO upstream gradients of a row are loaded by lanes 0..NO-1 and broadcast by shuffle.
-template <int NO, int KV>
+// PAIR: dH is written as the fp16 hi / lo pair the f16x3 dense-layer kernels consume (f16x3_common.cuh) instead of fp32.  Its
+// scale comes from the ANALYTIC bound |dH[m,k]| <= max|dY| * max_k sum_o |W[o,k]| (act' <= 1), formed here from the device
+// scalar *dy_amax and the head weights every lane already holds, and published through *bound_out for the consumers.
+struct HeadPairOut {
+  __half *hi, *lo;
+  int64_t ld;              // halves
+  const float* dy_amax;    // device scalar: max |dY|
+  float* bound_out;        // device scalar written by block 0
+};
+
+template <int NO, int KV, bool PAIR>
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ H,
                                                                 int64_t ldh, const float* __restrict__ W, int act,
                                                                 float* __restrict__ dH, int64_t lddh, int M,
-                                                                float* __restrict__ partial /*[blocks][NO*K + NO + K]*/) {
+                                                                float* __restrict__ partial /*[blocks][NO*K + NO + K]*/,
+                                                                const HeadPairOut po) {
   constexpr int K = 128 * KV;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -107,6 +119,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
       w[o][v] = __ldg(reinterpret_cast<const float4*>(W + o * K + 128 * v + 4 * lane));
       gw[o][v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  float s_out = 1.f;
+  if (PAIR) {
+    float col = 0.f;  // max over this lane's columns of sum_o |W[o,k]|
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NO; ++o) a.x += fabsf(w[o][v].x), a.y += fabsf(w[o][v].y), a.z += fabsf(w[o][v].z), a.w += fabsf(w[o][v].w);
+      col = fmaxf(col, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) col = fmaxf(col, __shfl_xor_sync(0xffffffffu, col, o));
+    const float bound = __ldg(po.dy_amax) * col * 1.001f;
+    s_out = f16x3_scale(bound);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *po.bound_out = bound;
   }
   // software pipeline: the loads of the next 8 rows are issued before the arithmetic on the current 8
   float4 h[kHeadRows][KV], hn[kHeadRows][KV];
@@ -140,12 +168,24 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const float* __r
           gw[o][v].x += g * h[r][v].x, gw[o][v].y += g * h[r][v].y, gw[o][v].z += g * h[r][v].z, gw[o][v].w += g * h[r][v].w;
         }
       }
-      if (dH && row < M) {
+      if ((PAIR || dH) && row < M) {
 #pragma unroll
         for (int v = 0; v < KV; ++v) {
           d[v].x *= head_act_grad(h[r][v].x, act), d[v].y *= head_act_grad(h[r][v].y, act);
           d[v].z *= head_act_grad(h[r][v].z, act), d[v].w *= head_act_grad(h[r][v].w, act);
-          *reinterpret_cast<float4*>(dH + row * lddh + 128 * v + 4 * lane) = d[v];
+          if (PAIR) {
+            const float a0 = d[v].x * s_out, a1 = d[v].y * s_out, a2 = d[v].z * s_out, a3 = d[v].w * s_out;
+            const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+            const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y), l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+            uint2 uh, ul;
+            uh.x = *reinterpret_cast<const uint32_t*>(&h01), uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+            ul.x = *reinterpret_cast<const uint32_t*>(&l01), ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(po.hi + row * po.ld + 128 * v + 4 * lane) = uh;
+            *reinterpret_cast<uint2*>(po.lo + row * po.ld + 128 * v + 4 * lane) = ul;
+          } else {
+            *reinterpret_cast<float4*>(dH + row * lddh + 128 * v + 4 * lane) = d[v];
+          }
           gd[v].x += d[v].x, gd[v].y += d[v].y, gd[v].z += d[v].z, gd[v].w += d[v].w;
         }
       }
@@ -244,9 +284,13 @@ struct HeadBwd {
   float *dH, *partial;
   unsigned grid;
   cudaStream_t s;
+  HeadPairOut po;
   template <int NO, int KV>
   int run() {
-    head_bwd_kernel<NO, KV><<<grid, kHeadThreads, 0, s>>>(dY, H, ldh, W, act, dH, lddh, M, partial);
+    if (po.hi)
+      head_bwd_kernel<NO, KV, true><<<grid, kHeadThreads, 0, s>>>(dY, H, ldh, W, act, dH, lddh, M, partial, po);
+    else
+      head_bwd_kernel<NO, KV, false><<<grid, kHeadThreads, 0, s>>>(dY, H, ldh, W, act, dH, lddh, M, partial, po);
     return check_launch("head_bwd_kernel");
   }
 };
@@ -295,7 +339,29 @@ int cusrl_b200_head_bwd_f32(const float* dY, const float* H, int64_t ldh, const 
   CUSRL_REQUIRE(!dbH || dH, CUSRL_B200_EINVAL, "head_bwd: dbH (column sums of dH) needs dH");
   CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_head_bwd_scratch_bytes(K, No), CUSRL_B200_ESCRATCH, "head_bwd: scratch too small");
   cudaStream_t s = (cudaStream_t)stream;
-  HeadBwd f{dY, H, W, ldh, lddh, act, (int)M, dH, (float*)scratch, head_grid(M, 2, kHeadMaxBlocks), s};  // 176 registers: 2 blocks per SM
+  HeadBwd f{dY, H, W, ldh, lddh, act, (int)M, dH, (float*)scratch, head_grid(M, 2, kHeadMaxBlocks), s, HeadPairOut{}};  // 176 registers: 2 blocks per SM
+  if (int e = head_dispatch((int)No, (int)K, f)) return e;
+  const int total = (int)(No * K + No + K);
+  head_bwd_final_kernel<<<(total + 255) / 256, 256, 0, s>>>((const float*)scratch, (int)f.grid, (int)No, (int)K, dW, db,
+                                                            accumulate, dbH, accumulate_dbh);
+  return check_launch("head_bwd_final_kernel");
+}
+
+int cusrl_b200_head_bwd_f16pair(const float* dY, const float* dy_amax, const float* H, int64_t ldh, const float* W, int act,
+                                uint16_t* dH_hi, uint16_t* dH_lo, int64_t lddh, float* dh_bound, float* dW, float* db, int64_t M,
+                                int64_t K, int64_t No, int accumulate, float* dbH, int accumulate_dbh, void* scratch,
+                                size_t scratch_bytes, void* stream) {
+  CUSRL_REQUIRE(dY && dy_amax && H && W && dW && scratch && dH_hi && dH_lo && dh_bound, CUSRL_B200_EINVAL, "head_bwd_f16pair: null pointer");
+  CUSRL_REQUIRE(M > 0 && K > 0 && No > 0 && M < (1ll << 31), CUSRL_B200_EINVAL, "head_bwd_f16pair: bad sizes");
+  CUSRL_REQUIRE((K % 128) == 0 && No <= kHeadMaxNo && No * K <= 2048, CUSRL_B200_EUNSUPPORTED, "head_bwd_f16pair: unsupported head shape");
+  CUSRL_REQUIRE((ldh % 4) == 0 && ldh >= K && (lddh % 8) == 0 && lddh >= K && aligned_to(H, 16) && aligned_to(W, 16) &&
+                    aligned_to(dH_hi, 16) && aligned_to(dH_lo, 16),
+                CUSRL_B200_EALIGN, "head_bwd_f16pair: alignment");
+  CUSRL_REQUIRE(act >= 0 && act <= 2, CUSRL_B200_EINVAL, "head_bwd_f16pair: unknown activation code");
+  CUSRL_REQUIRE(scratch_bytes >= cusrl_b200_head_bwd_scratch_bytes(K, No), CUSRL_B200_ESCRATCH, "head_bwd_f16pair: scratch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  HeadBwd f{dY, H, W, ldh, 0, act, (int)M, nullptr, (float*)scratch, head_grid(M, 2, kHeadMaxBlocks), s,
+            HeadPairOut{(__half*)dH_hi, (__half*)dH_lo, lddh, dy_amax, dh_bound}};
   if (int e = head_dispatch((int)No, (int)K, f)) return e;
   const int total = (int)(No * K + No + K);
   head_bwd_final_kernel<<<(total + 255) / 256, 256, 0, s>>>((const float*)scratch, (int)f.grid, (int)No, (int)K, dW, db,

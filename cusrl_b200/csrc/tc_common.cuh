@@ -94,6 +94,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of the box a later tma_load_2d with the same coordinates will fetch (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // Multicast variant: the box lands at the same shared-memory offset of every CTA in `cta_mask` and completes on the
 // mbarrier at the same offset in each of them.
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar,

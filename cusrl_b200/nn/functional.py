@@ -83,7 +83,9 @@ def f16_trunk_forward(x: torch.Tensor, linears, act_code: int, last_act: bool):
     """Forward of a Linear(+activation) stack on the f16x3 kernels: the input is split once (exact amax + split), hidden
     activations stay fp16 hi / lo pairs written by the GEMM epilogues (never materialised in fp32), the last layer's output
     is fp32.  Returns (x pair, [hidden pairs..., fp32 output])."""
-    xp = ops.split_f16(x if x.stride(-1) == 1 else x.contiguous())
+    xp = ops.attached_pair(x)   # the sampler may already have produced the pair while gathering the minibatch
+    if xp is None:
+        xp = ops.split_f16(x if x.stride(-1) == 1 else x.contiguous())
     h, acts = xp, []
     n = len(linears)
     for i, (w, b) in enumerate(linears):
@@ -123,8 +125,9 @@ def _f16_backward(ctx, grad_out):
         dw = hw_grad if arena else torch.empty_like(head_w)
         db = hb_grad if arena else (torch.empty_like(head_b) if head_b is not None else None)
         db_trunk, acc_trunk = _bias_target(weights[n - 1], biases[n - 1], grads, 2 * n - 1)
-        dz = ops.head_bwd(grad_out.contiguous(), latent, head_w, last_code, dw, db, need_dh=True, accumulate=arena,
-                          db_trunk=db_trunk, accumulate_trunk=acc_trunk)
+        # the head's backward emits the gradient entering the trunk directly as an fp16 pair (analytic bound)
+        dzp = ops.head_bwd_pair(grad_out.contiguous(), latent, head_w, last_code, dw, db, accumulate=arena,
+                                db_trunk=db_trunk, accumulate_trunk=acc_trunk)
         if not arena:
             grads[2 * n], grads[2 * n + 1] = dw, db
     else:
@@ -132,7 +135,7 @@ def _f16_backward(ctx, grad_out):
         db_last, acc_last = _bias_target(weights[n - 1], biases[n - 1], grads, 2 * n - 1)
         if db_last is not None:
             ops.colsum_(dz, db_last, accumulate=acc_last)
-    dzp = ops.split_f16(dz)   # the gradient entering the trunk: exact amax + split; below it stays in pairs
+        dzp = ops.split_f16(dz)   # exact amax + split; below it stays in pairs
     for i in range(n - 1, -1, -1):
         inp = hidden[i - 1] if i > 0 else xp
         w = weights[i]
@@ -308,7 +311,7 @@ class _HeadFunction(torch.autograd.Function):
             dy_p[:, :No].copy_(dy)
             dw_p = torch.empty(Np, K, device=dy.device)
             db_p = torch.empty(Np, device=dy.device) if bias is not None else None
-            ops.tc_linear_wgrad(dy_p, x, dw_p, db_p, ops.GEMM_PRECISION, accumulate=False)
+            ops.tc_linear_wgrad(dy_p, x, dw_p, db_p, ops.tf32_passes(), accumulate=False)
             grads = [dw_p[:No], None if db_p is None else db_p[:No]]
             dx = ops.tc_linear_dgrad(dy_p, ctx.padded, None, K, 0, ops.tf32_passes()) if need_dx else None
         return dx, grads[0], grads[1]

@@ -794,6 +794,59 @@ def f16_linear_dgrad(dy: Pair, wp: dict, x_act: Pair | None, act: int, out_pair:
     return dx
 
 
+def gather_split_f16(src: torch.Tensor, index: torch.Tensor, bound: torch.Tensor, out: Pair | None = None) -> Pair:
+    """pair[i] = split(src[index[i]]) for a 2-D fp32 source (unit inner stride), scale of `bound` (cusrl_b200_gather_split_f16)."""
+    sp, lds = _rows(src, "src")
+    n, width = index.numel(), src.shape[1]
+    out = pair_empty(n, width, src.device) if out is None else out
+    out.bound = bound
+    code = _lib.load().cusrl_b200_gather_split_f16(sp, lds, _ptr(index, torch.int64, "index"), n, src.shape[0], width,
+                                                   _ptr(bound, torch.float32, "bound"), out.data[0].data_ptr(),
+                                                   out.data[1].data_ptr(), out.ld, _stream())
+    _lib.check(code, "gather_split_f16")
+    return out
+
+
+# pairs that a producer (the sampler) prepared for a tensor a dense layer is about to consume: keyed by storage identity
+_attached_pairs: dict[int, tuple["weakref.ref", tuple, Pair]] = {}
+
+
+def attach_pair(tensor: torch.Tensor, pair: Pair) -> None:
+    """Remember that `pair` is the f16x3 split of `tensor` as it is NOW (same memory, shape and version counter)."""
+    if len(_attached_pairs) > 64:
+        for k in [k for k, v in _attached_pairs.items() if v[0]() is None]:
+            del _attached_pairs[k]
+    _attached_pairs[tensor.data_ptr()] = (weakref.ref(tensor), (tuple(tensor.shape), tuple(tensor.stride()), tensor._version), pair)
+
+
+def attached_pair(tensor: torch.Tensor) -> Pair | None:
+    hit = _attached_pairs.get(tensor.data_ptr())
+    if hit is None or hit[0]() is None:
+        return None
+    if hit[1] != (tuple(tensor.shape), tuple(tensor.stride()), tensor._version):
+        return None
+    return hit[2]
+
+
+def head_bwd_pair(dy: torch.Tensor, h: torch.Tensor, w: torch.Tensor, act: int, dw: torch.Tensor, db: torch.Tensor | None,
+                  accumulate: bool = False, db_trunk: torch.Tensor | None = None, accumulate_trunk: bool = False) -> Pair:
+    """:func:`head_bwd` with dH returned as an f16x3 :class:`Pair` (cusrl_b200_head_bwd_f16pair): no fp32 dH, no split pass."""
+    M, K = h.shape
+    No = w.shape[0]
+    hp, ldh = _rows(h, "h")
+    out = pair_empty(M, K, h.device)
+    dy_amax = amax(dy.reshape(M, No))
+    lib = _lib.load()
+    scratch = _get_scratch(h.device, "headbwd", lib.cusrl_b200_head_bwd_scratch_bytes(K, No))
+    code = lib.cusrl_b200_head_bwd_f16pair(
+        _ptr(dy, torch.float32, "dy"), dy_amax.data_ptr(), hp, ldh, _ptr(w.detach(), torch.float32, "weight"), act,
+        out.data[0].data_ptr(), out.data[1].data_ptr(), out.ld, out.bound.data_ptr(), _ptr(dw, torch.float32, "dw"),
+        _ptr(db, torch.float32, "db"), M, K, No, int(accumulate), _ptr(db_trunk, torch.float32, "db_trunk"),
+        int(accumulate_trunk), scratch.data_ptr(), scratch.numel(), _stream())
+    _lib.check(code, "head_bwd_f16pair", launches=2)
+    return out
+
+
 def colsum_(dz: torch.Tensor, db: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
     """db (+)= column sums of a 2-D fp32 tensor (the bias gradient of a dense layer)."""
     M, N = dz.shape

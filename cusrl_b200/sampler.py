@@ -48,6 +48,9 @@ class MiniBatchSampler(Sampler):
         self.shuffle = shuffle
         self.fields = None if fields is None else tuple(fields)
         self._dst: dict[tuple, torch.Tensor] = {}
+        self._pair_dst: dict[tuple, object] = {}
+        self._pair_bounds: dict[str, torch.Tensor] = {}
+        self._pair_bound_storage: dict[str, torch.Tensor] = {}
 
     # ---- index generation (pure torch, device agnostic: covered by the CPU tests) ----------------
     def _get_num_samples(self, buffer: Buffer) -> int:
@@ -124,10 +127,29 @@ class MiniBatchSampler(Sampler):
         for rows, pairs in groups.values():
             for i in range(0, len(pairs), 24):  # at most CUSRL_B200_MAX_GATHER_FIELDS (24) fields per launch
                 ops.gather_rows(pairs[i : i + 24], rows)
+        if not self.temporal and ops.GEMM_PRECISION == 2:
+            # f16x3 dense layers: the network inputs are ALSO emitted as fp16 hi / lo pairs by the gather itself (scale from
+            # the amax of the whole leaf, computed once per update), so the first layer does not re-read the minibatch to
+            # split it; the fp32 leaf stays in the batch for every other consumer
+            for key in ("observation", "state"):
+                if key not in out or buffer.storage[key].dim() != 3 or buffer.storage[key].dtype != torch.float32:
+                    continue
+                width = buffer.storage[key].shape[-1]
+                src = buffer.backing(key).reshape(T * N, -1)[:, :width]
+                bound = self._pair_bounds.get(key)
+                if bound is None:
+                    # a PERSISTENT device scalar: a captured train step has its address baked into the kernel arguments
+                    bound = self._pair_bounds[key] = ops.amax(src, out=self._pair_bound_storage.setdefault(
+                        key, torch.zeros(1, dtype=torch.float32, device=src.device)))
+                dst = self._pair_dst.get((key, idx.numel()))
+                pair = ops.gather_split_f16(src, idx, bound, out=dst)
+                self._pair_dst[(key, idx.numel())] = pair
+                ops.attach_pair(out[key], pair)
         return out
 
     def __call__(self, buffer: Buffer):
         keys = None
+        self._pair_bounds = {}   # per update: the leaves change every rollout
         for metadata, idx in self.indices(buffer):
             if keys is None:
                 keys = self._selected(buffer)

@@ -342,6 +342,22 @@ int cusrl_b200_split_f16(const float* x, int64_t ld, int64_t rows, int64_t width
                          int64_t ldh, void* stream);
 int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float* bias, uint16_t* hi, uint16_t* lo, int64_t ld,
                                uint16_t* hi_t, uint16_t* lo_t, int64_t ldt, float* stats, void* stream);
+/* K8 for precision 2: pair[i] = split(src[index[i]]) for a wide fp32 leaf (row pitch lds floats, `width` valid columns): the
+ * gathered minibatch rows emitted directly as the fp16 pair the first trunk layer consumes (scale of *bound, e.g. the amax
+ * of the whole leaf); out-of-range indices are clamped like cusrl_b200_gather_rows. */
+int cusrl_b200_gather_split_f16(const float* src, int64_t lds, const int64_t* index, int64_t n, int64_t n_src_rows, int64_t width,
+                                const float* bound, uint16_t* hi, uint16_t* lo, int64_t ldh, void* stream);
+/* cusrl_b200_head_bwd_f32 with dH emitted as the fp16 pair the f16x3 trunk kernels consume (no fp32 dH, no separate split
+ * pass): scale from the analytic bound max|dY| * max_k sum_o|W[o,k]| built from the device scalar *dy_amax (cusrl_b200_amax_f32
+ * of dY) and published in *dh_bound.  lddh in halves, a multiple of 8. */
+int cusrl_b200_head_bwd_f16pair(const float* dY, const float* dy_amax, const float* H, int64_t ldh, const float* W, int act,
+                                uint16_t* dH_hi, uint16_t* dH_lo, int64_t lddh, float* dh_bound, float* dW, float* db, int64_t M,
+                                int64_t K, int64_t No, int accumulate, float* dbH, int accumulate_dbh, void* scratch,
+                                size_t scratch_bytes, void* stream);
+/* k-blocks the L2 prefetch of the HBM-streamed operand tiles runs ahead of the TMA loads (0 = off; process-wide knob). */
+int cusrl_b200_f16x3_set_prefetch(int k_blocks);
+/* output-tile width of the forward / data-gradient kernels: 0 = by problem (256 when N > 128), 128 or 256 = forced. */
+int cusrl_b200_f16x3_set_tile(int bn);
 int cusrl_b200_linear_fwd_f16x3(const uint16_t* Xhi, const uint16_t* Xlo, int64_t ldx, const float* x_bound, const uint16_t* Whi,
                                 const uint16_t* Wlo, int64_t ldw, const float* w_stats, const float* bias, float* Y, int64_t ldy,
                                 uint16_t* Yhi, uint16_t* Ylo, int64_t ldyh, float* y_bound, int64_t M, int64_t N, int64_t K,

@@ -65,7 +65,9 @@ def test_linear_fwd(ops, M, K, N, act, out_pair):
     wp = ops.weight_prep_f16(w, b)
     stats = wp["stats"].cpu()
     assert stats[0].item() == pytest.approx(w.abs().max().item(), rel=1e-6)
-    assert stats[1].item() >= w.abs().sum(1).max().item() and stats[2].item() >= w.abs().sum(0).max().item()
+    # rounded sums: the kernels widen the bounds they build from the L1 norms by 1.001
+    assert stats[1].item() * 1.001 >= w.abs().sum(1).max().item() and stats[2].item() * 1.001 >= w.abs().sum(0).max().item()
+    assert stats[1].item() <= w.abs().sum(1).max().item() * 1.001 and stats[2].item() <= w.abs().sum(0).max().item() * 1.001
     assert stats[3].item() == pytest.approx(b.abs().max().item(), rel=1e-6)
     y = ops.f16_linear_fwd(ops.split_f16(x), wp, b, act, out_pair=out_pair)
     ref = _act(torch.nn.functional.linear(x.double(), w.double(), b.double()), act)
@@ -181,3 +183,39 @@ def test_network_node_f16x3_matches_fp64(ops, monkeypatch, B, has_head):
         f32 = (r32.grad.double() - r64.grad).abs().max().item()
         print(f"B={B} head={has_head} param {i}: rel err {err / scale:.2e}, torch fp32 {f32 / scale:.2e}")
         assert err <= max(8 * f32, 2e-5 * scale), (i, err, f32, scale)
+
+
+def test_head_bwd_pair_matches_fp32_head_bwd(ops):
+    g = torch.Generator().manual_seed(5)
+    M, K, No = 5000, 128, 12
+    h = torch.nn.functional.elu(torch.randn(M, K, generator=g)).to(DEV)
+    w = (torch.randn(No, K, generator=g) / K**0.5).to(DEV)
+    dy = (torch.randn(M, No, generator=g) / M).to(DEV)
+    dw0, db0, dbt0 = torch.zeros(No, K, device=DEV), torch.zeros(No, device=DEV), torch.zeros(K, device=DEV)
+    dh = ops.head_bwd(dy, h, w, 1, dw0, db0, db_trunk=dbt0)
+    dw1, db1, dbt1 = torch.zeros(No, K, device=DEV), torch.zeros(No, device=DEV), torch.zeros(K, device=DEV)
+    pair = ops.head_bwd_pair(dy, h, w, 1, dw1, db1, db_trunk=dbt1)
+    assert float(pair.bound) >= float(dh.abs().max())
+    scale = float(dh.abs().max())
+    assert (pair.float().double() - dh.double()).abs().max().item() <= 2.0**-20 * scale
+    assert torch.equal(dw0, dw1) and torch.equal(db0, db1) and torch.equal(dbt0, dbt1)
+
+
+def test_gather_split_matches_gather_then_split(ops):
+    g = torch.Generator().manual_seed(6)
+    E, K, B = 5000, 235, 1200
+    back = torch.zeros(E, 236)
+    back[:, :K] = torch.randn(E, K, generator=g)
+    back = back.to(DEV)
+    src = back[:, :K]
+    idx = torch.randperm(E, generator=g)[:B].to(DEV)
+    bound = ops.amax(src)
+    pair = ops.gather_split_f16(src, idx, bound)
+    ref = ops.split_f16(src[idx].contiguous(), bound=bound)
+    assert torch.equal(pair.data, ref.data) and pair.width == K and pair.ld == 240
+    # attach / lookup protocol used by the sampler
+    dst = src[idx].contiguous()
+    ops.attach_pair(dst, pair)
+    assert ops.attached_pair(dst) is pair
+    dst.add_(1.0)
+    assert ops.attached_pair(dst) is None   # a torch-level in-place change invalidates the attachment

@@ -41,6 +41,18 @@ for name, K, N in (("L1 235->512", 235, 512), ("L2 512->256", 512, 256), ("L3 25
     outs32 = [torch.empty(M, N, device=dev) for _ in range(sets)]
     dw = torch.zeros(N, K, device=dev)
     res = {"layer": name, "M": M}
+    from cusrl_b200 import _lib
+    sweep = {}
+    for bn in (256, 128):
+        _lib.load().cusrl_b200_f16x3_set_tile(bn)
+        row = [timeit([lambda i=i: ops.f16_linear_fwd(xps[i], wp16, b, 1, True, out=outs[i]) for i in range(sets)]),
+               timeit([lambda i=i: ops.f16_linear_fwd(xps[i], wp16, b, 1, False, out=outs32[i]) for i in range(sets)])]
+        if not name.startswith("L1"):
+            dbs = torch.zeros(K, device=dev)
+            row.append(timeit([lambda i=i: ops.f16_linear_dgrad(dzps[i], wp16, xps[i], 1, True, db_below=dbs, accumulate=True) for i in range(sets)]))
+        sweep[bn] = [round(v, 1) for v in row]
+    res["tile_sweep_fwdpair_fwdf32_dgrad_us"] = sweep
+    _lib.load().cusrl_b200_f16x3_set_tile(0)
     res["fwd_pair_us"] = timeit([lambda i=i: ops.f16_linear_fwd(xps[i], wp16, b, 1, True, out=outs[i]) for i in range(sets)])
     res["fwd_f32out_us"] = timeit([lambda i=i: ops.f16_linear_fwd(xps[i], wp16, b, 1, False, out=outs32[i]) for i in range(sets)])
     res["fwd_3xtf32_us"] = timeit([lambda i=i: ops.tc_linear_fwd(xs[i], wp32, b, N, 1, 3, out=outs32[i]) for i in range(sets)])
