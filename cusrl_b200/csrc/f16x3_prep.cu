@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restri
 }
 
 // hi / lo [N, ld] and transposed hi_t / lo_t [K, ldt] halves of W [N, K] with the scale of stats[WSTAT_AMAX]; the padding
-// columns (K..ld-1, N..ldt-1) are zeroed by the launcher's memsets.
+// columns (K..ld-1, N..ldt-1) are zero-initialised by the caller when it allocates the matrices.
 __global__ void __launch_bounds__(256) weight_split_f16_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ stats,
                                                                __half* __restrict__ hi, __half* __restrict__ lo, int ld,
                                                                __half* __restrict__ hi_t, __half* __restrict__ lo_t, int ldt) {
@@ -225,14 +225,8 @@ int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float
   const int row_blocks = (int)((N + 7) / 8), col_blocks = (int)((K + 255) / 256);
   weight_stats_kernel<<<row_blocks + col_blocks, 256, 0, s>>>(W, (int)N, (int)K, bias, stats, row_blocks);
   if (int e = check_launch("weight_stats_kernel")) return e;
-  if (ld > K) {  // zero the padding columns once per call (cheap: the matrices are tiny)
-    cudaMemsetAsync(hi, 0, (size_t)N * ld * 2, s);
-    cudaMemsetAsync(lo, 0, (size_t)N * ld * 2, s);
-  }
-  if (hi_t && ldt > N) {
-    cudaMemsetAsync(hi_t, 0, (size_t)K * ldt * 2, s);
-    cudaMemsetAsync(lo_t, 0, (size_t)K * ldt * 2, s);
-  }
+  // the padding columns (K..ld-1 of the pair, N..ldt-1 of the transposed pair) are never written: the CALLER zero-initialises
+  // the four matrices once, when it allocates them
   int blocks = (int)((N * K + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   weight_split_f16_kernel<<<blocks, 256, 0, s>>>(W, (int)N, (int)K, stats, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t,

@@ -86,6 +86,8 @@ def f16_trunk_forward(x: torch.Tensor, linears, act_code: int, last_act: bool):
     xp = ops.attached_pair(x)   # the sampler may already have produced the pair while gathering the minibatch
     if xp is None:
         xp = ops.split_f16(x if x.stride(-1) == 1 else x.contiguous())
+        if x.stride(-1) == 1:
+            ops.attach_pair(x, xp)   # actor and critic consume the same observations: split them once
     h, acts = xp, []
     n = len(linears)
     for i, (w, b) in enumerate(linears):
@@ -163,7 +165,7 @@ class _MlpHeadFunction(torch.autograd.Function):
         precision = ops.tf32_passes()
         n = (len(params) - (2 if has_head else 0)) // 2
         weights, biases = params[0 : 2 * n : 2], params[1 : 2 * n : 2]
-        ctx.f16 = ops.GEMM_PRECISION == 2 and f16x3_supported(weights, biases)
+        ctx.f16 = ops.GEMM_PRECISION == 2 and x.shape[0] >= ops.F16X3_MIN_ROWS and f16x3_supported(weights, biases)
         if ctx.f16:
             return _f16_forward(ctx, x, act_code, last_act, has_head, n, params)
         x = _rows_ok(x)

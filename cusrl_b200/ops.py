@@ -470,7 +470,13 @@ def adam_step_dev_(
 # ---------------------------------------------------------------------------------------------- K6
 # Dense layers on tcgen05 (csrc/gemm_tf32.cu, csrc/gemm_wgrad_tf32.cu) and SIMT heads (csrc/head_kernels.cu).
 # 3 = 3xTF32 (fp32-equivalent), 2 = f16x3 (fp16 hi / lo split, fp32-equivalent, half the tensor time), 1 = single-pass TF32
-GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "3"))
+GEMM_PRECISION = int(__import__("os").environ.get("CUSRL_B200_GEMM_PRECISION", "2"))
+
+
+# f16x3 pays a few extra small launches per layer (range statistics, splits of the trunk inputs): below this many rows the
+# 3xTF32 kernels (equally fp32-equivalent) are used instead.  Measured on a B200: 24 576-row minibatches (4096 envs) 27.1 ms
+# per iteration with f16x3 against 22.9 ms with 3xTF32; 98 304 rows (16 384 envs) 59.2 against 61.2; 393 216 rows 135 against 180.
+F16X3_MIN_ROWS = int(__import__("os").environ.get("CUSRL_B200_F16X3_MIN_ROWS", "49152"))
 
 
 def tf32_passes() -> int:

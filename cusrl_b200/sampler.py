@@ -127,7 +127,7 @@ class MiniBatchSampler(Sampler):
         for rows, pairs in groups.values():
             for i in range(0, len(pairs), 24):  # at most CUSRL_B200_MAX_GATHER_FIELDS (24) fields per launch
                 ops.gather_rows(pairs[i : i + 24], rows)
-        if not self.temporal and ops.GEMM_PRECISION == 2:
+        if not self.temporal and ops.GEMM_PRECISION == 2 and idx.numel() >= ops.F16X3_MIN_ROWS:
             # f16x3 dense layers: the network inputs are ALSO emitted as fp16 hi / lo pairs by the gather itself (scale from
             # the amax of the whole leaf, computed once per update), so the first layer does not re-read the minibatch to
             # split it; the fp32 leaf stays in the batch for every other consumer

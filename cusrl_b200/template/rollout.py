@@ -63,7 +63,7 @@ class _Net:
 
     def forward(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         pairs = [(lin.weight, lin.bias) for lin in self.linears]
-        if ops.GEMM_PRECISION == 2 and F.f16x3_supported(*zip(*pairs)):
+        if ops.GEMM_PRECISION == 2 and x.shape[0] >= ops.F16X3_MIN_ROWS and F.f16x3_supported(*zip(*pairs)):
             _, acts = F.f16_trunk_forward(x, pairs, self.act, True)
             self.acts[-1] = acts[-1]
             return ops.head_fwd(acts[-1], self.head.weight, self.head.bias, out=out)

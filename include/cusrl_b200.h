@@ -324,7 +324,7 @@ int cusrl_b200_sample_logp_f32(const float* mean, const float* sigma, const floa
  *   A "pair" is two dense fp16 matrices [rows, ld] (ld a multiple of 8 halves, columns >= width zero) plus one float bound.
  *   amax:            bound[0] = max|x| of an fp32 [rows, width] array (row pitch ld floats) -- the exact bound of an input.
  *   split_f16:       the pair of x with the scale of *bound.
- *   weight_prep_f16: pair of W[N,K] (+ transposed pair [K, ldt]) and stats[4] = { max|W|, max_n sum_k|W_nk|,
+ *   weight_prep_f16: pair of W[N,K] (+ transposed pair [K, ldt]; the caller zero-initialises the padding columns once) and stats[4] = { max|W|, max_n sum_k|W_nk|,
  *                    max_k sum_n|W_nk|, max|bias| }: the factors of the ANALYTIC output bounds
  *                    bound(act(x W^T + b)) <= bound(x) stats[1] + stats[3]   and   bound((dz W) act') <= bound(dz) stats[2],
  *                    which the GEMM kernels compute and publish (y_bound / dx_bound) without any extra pass.

@@ -32,6 +32,8 @@ for s in "$@"; do
     graphs_fps) step graphs_fps 200 bash -c "python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --no-graphs --no-fused-rollout; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2 --no-graphs; python tools/config_fps.py --only mlp_ppo_4096 --steps 3 --warmup 2" ;;
     f16tests)   step f16tests 400 python -u -m pytest tests/test_gemm_f16x3_gpu.py -q -m gpu --timeout 60 -x -rf -s ;;
     f16bench)   step f16bench 300 python tools/f16x3_bench.py ;;
+    tests_p3)   step tests_p3 900 env CUSRL_B200_GEMM_PRECISION=3 python -u -m pytest tests -q -m gpu --timeout 300 -rf ;;
+    bench_p3)   step bench_p3 600 env CUSRL_B200_GEMM_PRECISION=3 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-cuda ;;
     tests_p2)   step tests_p2 900 env CUSRL_B200_GEMM_PRECISION=2 python -u -m pytest tests -q -m gpu --timeout 300 -rf ;;
     bench_p2)   step bench_p2 600 env CUSRL_B200_GEMM_PRECISION=2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-cuda ;;
     configs_p2) step configs_p2 400 env CUSRL_B200_GEMM_PRECISION=2 python tools/config_fps.py ;;
