@@ -37,6 +37,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="mlp", choices=["mlp", "lstm", "rnd"],
+                    help="BASELINE.json configuration family: mlp = MLP 512-256-128 PPO (configs 2 and 5; the default 65536 envs "
+                         "is the headline), lstm = recurrent PPO, LSTM 2 x 256 (config 3: --envs 4096), rnd = MLP PPO + RND "
+                         "intrinsic reward (config 4: --envs 16384)")
     ap.add_argument("--envs", type=int, default=65536, help="global number of environments")
     ap.add_argument("--rollout", type=int, default=24)
     ap.add_argument("--cpu-envs", type=int, default=4096, help="environments of the bounded CPU-baseline sample")
@@ -160,22 +164,33 @@ def time_iterations(agent, data, steps: int, warmup: int, distributed: bool) -> 
 
 
 # ------------------------------------------------------------------------------------------------
-def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
+def gae_roofline(T: int, N: int, peaks: dict, which: str, chain: bool = False) -> dict:
     """Achieved HBM bandwidth of the GAE scan kernel, timed live: a CUDA graph of launches over rotating buffer
-    sets whose footprint exceeds L2, CUDA events on the launching stream."""
+    sets whose footprint exceeds L2, CUDA events on the launching stream.  chain=False: the separable K1 kernel (21 B per
+    element: reward, value, next_value, done in; advantage, return out).  chain=True: the kernel the pre-update actually
+    runs, K3 + K1 + K2 statistics in one launch (22 B: reward, value, terminated, truncated in; next_value, advantage,
+    return out) -- the same work the reference does in three stages moving 10 + 21 + 4 = 35 B per element."""
     from cusrl_b200 import _lib, ops
 
     E = T * N
-    n_sets = max(2, int(300e6 // (21 * E)) + 1)
+    bytes_per_elt = 22 if chain else 21
+    n_sets = max(2, int(300e6 // (bytes_per_elt * E)) + 1)
     sets = []
     for _ in range(n_sets):
         d = {k: torch.randn(T, N, 1, device="cuda") for k in ("reward", "value", "nv", "adv", "ret")}
         d["done"] = torch.rand(T, N, 1, device="cuda") < 0.011
+        d["trunc"] = torch.rand(T, N, 1, device="cuda") < 0.001
+        d["boot"] = torch.randn(N, 1, device="cuda")
+        d["mean_var"] = torch.empty(2, device="cuda")
         sets.append(d)
 
     def launch_all():
         for d in sets:
-            ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95, advantage=d["adv"], ret=d["ret"])
+            if chain:
+                ops.gae_chain(d["reward"], d["done"], d["trunc"], d["value"], d["boot"], 0.99, 0.95, None, 0.0, d["nv"], d["adv"],
+                              d["ret"], mean_var=d["mean_var"])
+            else:
+                ops.gae(d["reward"], d["done"], d["value"], d["nv"], 0.99, 0.95, advantage=d["adv"], ret=d["ret"])
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -198,8 +213,15 @@ def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b) * 1e-3 / n_sets)
     sec = sum(times) / len(times)
-    achieved = 21 * E / sec / 1e9
+    achieved = bytes_per_elt * E / sec / 1e9
     peak = float(peaks["hbm_gbs"])
+    if chain:
+        return {"kernel": "gae_chain_kernel (K3 next_value + K1 GAE scan + K2 statistics, one launch; includes its one-block "
+                          "finalisation)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(f"gae_chain_f32@T={T},N={N}"), "peak_source": which,
+                "bytes_per_launch": bytes_per_elt * E, "us_per_launch": round(sec * 1e6, 2),
+                "reference_stage_bytes_per_launch": 35 * E,
+                "vs_reference_stage_bytes": round(35 * E / sec / 1e9 / peak, 4)}
     return {"kernel": "gae_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4),
             "traffic": ncu_traffic(f"gae_f32@T={T},N={N},variant={_lib._gae_variant_from_env()[0]}"), "peak_source": which,
@@ -208,41 +230,41 @@ def gae_roofline(T: int, N: int, peaks: dict, which: str) -> dict:
 
 
 def gemm_roofline(rows: int, peaks: dict, which: str) -> dict:
-    """The dominant kernel of the step (29 % of device time, profiles/): the 3xTF32 tcgen05 dense-layer forward
-    `gemm_tf32_kernel<256,3,0>` on the 512 -> 256 trunk layer of one minibatch, timed live with CUDA events over
-    back-to-back launches on rotating activation buffers larger than L2.
-    achieved = ALGORITHMIC flops (2 M N K, fp32 semantics) / time; the tensor pipe executes 3x that in TF32.
-    peak = measured dense bf16 cuBLAS throughput / 2 (TF32 runs at half the bf16 rate); sustained figure because the
-    kernel runs inside a long step."""
+    """The dominant kernel of the step (profiles/r02_iter_profile.md): the f16x3 tcgen05 dense-layer forward
+    `gemm_f16x3_kernel<256,0,1>` (fp16 hi/lo split operands, pair output) on the 512 -> 256 trunk layer of one minibatch,
+    timed live with CUDA events over back-to-back launches on rotating activation buffers larger than L2.
+    achieved = ALGORITHMIC flops (2 M N K, fp32 semantics) / time; the tensor pipe executes 3x that as fp16 MMAs.
+    peak = measured dense bf16 cuBLAS throughput (fp16 and bf16 MMAs run at the same rate); the sustained figure because
+    the kernel runs inside a long step."""
     from cusrl_b200 import ops
 
     M, K, N = rows, 512, 256
     n_sets = max(2, int(300e6 // (M * (K + N) * 4)) + 1)
-    xs = [torch.randn(M, K, device="cuda") for _ in range(n_sets)]
-    ys = [torch.empty(M, N, device="cuda") for _ in range(n_sets)]
+    xs = [ops.split_f16(torch.randn(M, K, device="cuda")) for _ in range(n_sets)]
+    ys = [ops.pair_empty(M, N, "cuda") for _ in range(n_sets)]
     w = torch.randn(N, K, device="cuda") / K**0.5
     b = torch.randn(N, device="cuda")
-    wp = ops.weight_prep(w)
+    wp = ops.weight_prep_f16(w, b)
     for x, y in zip(xs, ys):
-        ops.tc_linear_fwd(x, wp, b, N, 1, 3, out=y)
+        ops.f16_linear_fwd(x, wp, b, 1, True, out=y)
     torch.cuda.synchronize()
     reps = 4
     a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
         for x, y in zip(xs, ys):
-            ops.tc_linear_fwd(x, wp, b, N, 1, 3, out=y)
+            ops.f16_linear_fwd(x, wp, b, 1, True, out=y)
     e.record()
     torch.cuda.synchronize()
     sec = a.elapsed_time(e) * 1e-3 / (reps * n_sets)
     flops = 2.0 * M * N * K
     achieved = flops / sec / 1e12
-    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])) / 2.0
-    return {"kernel": "gemm_tf32_kernel<256,3,0> (3xTF32 forward, 512->256)", "bound": "tensor", "achieved": round(achieved, 1),
-            "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-            "traffic": ncu_traffic(f"gemm_tf32_kernel<256,3,0>@M={M},K={K},N={N}"),
-            "peak_source": f"{which}: bf16_tflops_sustained / 2 (TF32 rate)", "flops_per_launch": flops,
-            "executed_tf32_flops_per_launch": 3 * flops, "executed_frac": round(3 * achieved / peak, 4),
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    return {"kernel": "gemm_f16x3_kernel<256,0,1> (f16x3 forward, 512->256, fp16 hi/lo pair in and out)", "bound": "tensor",
+            "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+            "traffic": ncu_traffic(f"gemm_f16x3_kernel<256,0,1>@M={M},K={K},N={N}"),
+            "peak_source": f"{which}: bf16_tflops_sustained (fp16 MMA rate)", "flops_per_launch": flops,
+            "executed_f16_flops_per_launch": 3 * flops, "executed_frac": round(3 * achieved / peak, 4),
             "hbm_gbs": round(M * (K + N) * 4 / sec / 1e9, 1), "us_per_launch": round(sec * 1e6, 2), "rows": M}
 
 
@@ -271,16 +293,23 @@ class ReferenceRun:
     """The reference agent on `device` ("cpu" or "cuda:0") with `envs` synthetic environments, same data recipe as
     :class:`RolloutData`."""
 
-    def __init__(self, device: str, envs: int, T: int, seed: int = 1000):
+    def __init__(self, device: str, envs: int, T: int, seed: int = 1000, config: str = "mlp"):
         cusrl = _import_reference()
         from cusrl.template.environment import EnvironmentSpec
 
         self.device, self.envs, self.T = torch.device(device), envs, T
         torch.manual_seed(42)
-        kwargs = dict(ANYMAL_C_ROUGH, num_steps_per_update=T)
         spec = EnvironmentSpec(num_instances=envs, observation_dim=OBS, action_dim=ACT, reward_dim=1, autoreset=True,
                                final_state_is_missing=True)
-        self.agent = cusrl.preset.ppo.PpoAgentFactory(device=device, **kwargs)(spec)
+        if config == "lstm":   # RecurrentPpoAgentFactory defaults: LSTM 2 x 256 both nets, lr 2e-4 (preset/ppo.py:185-245)
+            factory = cusrl.preset.ppo.RecurrentPpoAgentFactory(device=device, num_steps_per_update=T)
+        else:
+            factory = cusrl.preset.ppo.PpoAgentFactory(device=device, **dict(ANYMAL_C_ROUGH, num_steps_per_update=T))
+        if config == "rnd":    # cusrl_test/hook/auxiliary/test_rnd.py:12-19
+            factory = factory.to_underlying()
+            factory.register_hook(cusrl.hook.RandomNetworkDistillation(cusrl.Mlp.Factory([128, 128]), output_dim=16, reward_scale=0.1),
+                                  before="value_computation")
+        self.agent = factory(spec)
         self.data = RolloutData(T, envs, self.device, seed=seed, pinned_host=False)
 
     def iteration(self) -> dict:
@@ -315,11 +344,23 @@ class ReferenceRun:
         return self.T * self.envs / dt, dt, iters
 
 
-def pick_cpu_threads(T: int, max_threads: int, envs: int = 1024) -> tuple[int, dict]:
+def make_b200_agent(C, config: str, device, env):
+    """The agent of a BASELINE.json configuration family through this repository's public factories."""
+    if config == "lstm":
+        return C.RecurrentPpoAgentFactory(device=device).from_environment(env)
+    factory = C.anymal_c_rough_ppo(device=device)
+    if config == "rnd":
+        factory = factory.to_underlying()
+        factory.register_hook(C.RandomNetworkDistillation(C.Mlp.Factory([128, 128]), output_dim=16, reward_scale=0.1),
+                              before="value_computation")
+    return factory.from_environment(env)
+
+
+def pick_cpu_threads(T: int, max_threads: int, envs: int = 1024, config: str = "mlp") -> tuple[int, dict]:
     """PyTorch-CPU does not scale to every hardware thread on this workload (128 threads were 20x slower than 32 on the
     GPU box's host): calibrate on a small sample (one warm-up + three timed reference iterations per setting) and use the
     fastest setting, so the baseline is the CPU at its best."""
-    run = ReferenceRun("cpu", envs, T)
+    run = ReferenceRun("cpu", envs if config != "lstm" else min(envs, 256), T, config=config)
     rates = {}
     for th in (8, 16, 32, 64, max_threads):
         if th > max_threads or th in rates:
@@ -331,10 +372,11 @@ def pick_cpu_threads(T: int, max_threads: int, envs: int = 1024) -> tuple[int, d
     return best, {str(k): round(v, 1) for k, v in rates.items()}
 
 
-def reference_cpu_baseline(envs: int, T: int, iters: int, warmup: int, host_threads: int, budget_s: float | None):
+def reference_cpu_baseline(envs: int, T: int, iters: int, warmup: int, host_threads: int, budget_s: float | None,
+                           config: str = "mlp"):
     """`cpu_baseline` object: the reference's own CPU path on this box's host cores."""
-    threads, calib = pick_cpu_threads(T, host_threads)
-    run = ReferenceRun("cpu", envs, T)
+    threads, calib = pick_cpu_threads(T, host_threads, config=config)
+    run = ReferenceRun("cpu", envs, T, config=config)
     rate, dt, done = run.time(iters, warmup, budget_s)
     return {"value": round(rate, 1), "unit": "env-steps/s", "cores": threads, "kind": "reference",
             "sample": f"{envs} envs x {T} steps per iteration, {max(warmup, 1)} warm-up + {done} timed iterations "
@@ -358,7 +400,7 @@ def main():
         if rank != 0:
             return
         cpu, dt, done = reference_cpu_baseline(args.envs, T, iters=max(1, args.steps), warmup=1,
-                                               host_threads=host_threads, budget_s=args.ref_budget)
+                                               host_threads=host_threads, budget_s=args.ref_budget, config=args.config)
         rate = cpu["value"]
         line = {
             "impl": "reference", "metric": "ppo_env_steps_per_sec", "value": rate, "unit": "env-steps/s",
@@ -387,7 +429,7 @@ def main():
 
     torch.manual_seed(42 + rank)  # per-rank seed like the reference (utils/misc.py:163)
     env = C.SyntheticEnvironment(N, OBS, ACT, device=device, seed=42 + rank)
-    agent = C.anymal_c_rough_ppo(device=device).from_environment(env)
+    agent = make_b200_agent(C, args.config, device, env)
 
     # ---- value: inputs resident in HBM
     data = RolloutData(T, N, device, seed=1000 + rank, pinned_host=False)
@@ -421,6 +463,7 @@ def main():
         # launch shows the kernel's streaming rate without that fixed cost.  Context only: `frac` above is the metric.
         big = gae_roofline(T, 16 * N, peaks, which)
         roof_gae["same_kernel_16x_columns"] = {k: big[k] for k in ("achieved", "frac", "bytes_per_launch", "us_per_launch")}
+        roof_gae["pre_update_chain"] = gae_roofline(T, N, peaks, which, chain=True)
         roof = gemm_roofline(T * N // 4, peaks, which)  # one minibatch of this rank (4 minibatches per epoch)
         # ---- baselines (N = 1 only), both the UNMODIFIED reference from baseline/_ref, never on the product path
         ref_cuda = None
@@ -430,7 +473,7 @@ def main():
             del agent, env
             torch.cuda.empty_cache()
             try:
-                run = ReferenceRun("cuda:0", args.envs, T)
+                run = ReferenceRun("cuda:0", args.envs, T, config=args.config)
                 rate, dt, done = run.time(iters=3, warmup=2)
                 ref_cuda = {"value": round(rate, 1), "unit": "env-steps/s", "kind": "reference", "ms_per_step": round(dt * 1e3, 2),
                             "speedup_value": round(value / rate, 2),
@@ -445,7 +488,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                cpu, _, _ = reference_cpu_baseline(args.cpu_envs, T, iters=3, warmup=1, host_threads=host_threads, budget_s=30.0)
+                cpu_envs = min(args.cpu_envs, args.envs) if args.config != "lstm" else min(args.envs, 256)
+                cpu, _, _ = reference_cpu_baseline(cpu_envs, T, iters=3, warmup=1, host_threads=host_threads, budget_s=30.0,
+                                                   config=args.config)
             except Exception as error:
                 cpu = {"value": None, "error": f"{type(error).__name__}: {error}"[:300]}
         line = {
@@ -463,8 +508,10 @@ def main():
 
 
 def workload_config(args, world: int) -> dict:
+    model = {"mlp": "MLP 512-256-128 ELU actor-critic PPO", "lstm": "LSTM 2 x 256 recurrent actor-critic PPO (RecurrentPpoAgentFactory)",
+             "rnd": "MLP 512-256-128 ELU actor-critic PPO + RND intrinsic reward (235-128-128-16 nets)"}[args.config]
     return {
-        "workload": "synthetic Anymal-C-rough-shaped obs/act (235/12), MLP 512-256-128 ELU actor-critic PPO, "
+        "workload": f"synthetic Anymal-C-rough-shaped obs/act (235/12), {model}, "
                     f"{args.envs} envs x {args.rollout} steps, 5 epochs x 4 minibatches",
         "envs_global": args.envs, "envs_per_rank": args.envs // max(world, 1), "rollout_steps": args.rollout,
         "parallelism": f"dp{world} (env axis), NCCL flat-gradient allreduce per minibatch",

@@ -38,6 +38,7 @@ for s in "$@"; do
     bench_p2)   step bench_p2 600 env CUSRL_B200_GEMM_PRECISION=2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-cuda ;;
     configs_p2) step configs_p2 400 env CUSRL_B200_GEMM_PRECISION=2 python tools/config_fps.py ;;
     ncu_f16)    step ncu_f16 280 ncu --set full --clock-control none --import-source on -k regex:f16x3_kernel --launch-skip 4 --launch-count 4 -o "$out/f16x3" -f python tools/ncu_f16.py ;;
+    bench_cfgs) step bench_cfgs 900 bash -c "python bench.py --config mlp --envs 4096 --steps 5 --warmup 3; python bench.py --config lstm --envs 4096 --steps 3 --warmup 2; python bench.py --config rnd --envs 16384 --steps 5 --warmup 3" ;;
     fp16probe)  step fp16probe 300 python tools/fp16_split_probe.py ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
     launches)   step launches 230 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-reference-cuda ;;
