@@ -478,9 +478,13 @@ def main():
                 ref_cuda = {"value": round(rate, 1), "unit": "env-steps/s", "kind": "reference", "ms_per_step": round(dt * 1e3, 2),
                             "speedup_value": round(value / rate, 2),
                             "speedup_e2e": None if e2e is None else round(e2e["value"] / rate, 2),
-                            "note": "unmodified reference (baseline/_ref): cusrl.preset.ppo.PpoAgentFactory with the "
-                                    f"locomotion.py:48-59 values on cuda:0, {args.envs} envs x {T} steps, same act/step/update "
-                                    f"calls and data, 2 warm-up + {done} timed iterations, CUDA events"}
+                            "note": "unmodified reference (baseline/_ref): " + {
+                                "mlp": "cusrl.preset.ppo.PpoAgentFactory with the locomotion.py:48-59 values",
+                                "lstm": "cusrl.preset.ppo.RecurrentPpoAgentFactory defaults (nn.LSTM / cuDNN 2 x 256)",
+                                "rnd": "PpoAgentFactory (locomotion.py:48-59 values) + RandomNetworkDistillation before "
+                                       "value_computation"}[args.config]
+                                    + f" on cuda:0, {args.envs} envs x {T} steps, same act/step/update calls and data, "
+                                      f"2 warm-up + {done} timed iterations, CUDA events"}
                 del run
                 torch.cuda.empty_cache()
             except Exception as error:  # a baseline must never take the bench line down with it
