@@ -106,6 +106,10 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_wgrad_f16x3_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "cusrl_b200_linear_wgrad_f16x3": (
         c_int, [P, P, c_int64, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+    "cusrl_b200_column_stats_scratch_bytes": (c_size_t, [c_int64]),
+    "cusrl_b200_column_stats_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),
+    "cusrl_b200_rms_merge_f32": (c_int, [P, P, P, P, P, c_int64, c_double, c_double, c_float, P]),
+    "cusrl_b200_rms_normalize_f32": (c_int, [P, c_int64, P, c_int64, c_int64, c_int64, P, P, c_float, c_int, P]),
     "cusrl_b200_copy_rows_padded_f32": (c_int, [P, c_int64, P, c_int64, c_int64, c_int64, P]),
     "cusrl_b200_rollout_store_step_f32": (
         c_int, [P, c_int64, P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P, P, c_int64, P, P, P, P, P, c_int64, P]),

@@ -1,7 +1,9 @@
 from .auxiliary import RandomNetworkDistillation
+from .mdp import ObservationNanToNum, ObservationNormalization
 from .on_policy import (
     AdaptiveLRSchedule,
     AdvantageNormalization,
+    AdvantageReduction,
     EntropyLoss,
     GeneralizedAdvantageEstimation,
     GradientClipping,
@@ -16,10 +18,13 @@ from .on_policy import (
 __all__ = [
     "AdaptiveLRSchedule",
     "AdvantageNormalization",
+    "AdvantageReduction",
     "EntropyLoss",
     "GeneralizedAdvantageEstimation",
     "GradientClipping",
     "ModuleInitialization",
+    "ObservationNanToNum",
+    "ObservationNormalization",
     "OnPolicyPreparation",
     "OnPolicyStatistics",
     "PpoSurrogateLoss",

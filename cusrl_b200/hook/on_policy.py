@@ -33,6 +33,7 @@ from ..template.hook import Hook
 __all__ = [
     "AdaptiveLRSchedule",
     "AdvantageNormalization",
+    "AdvantageReduction",
     "EntropyLoss",
     "GeneralizedAdvantageEstimation",
     "GradientClipping",
@@ -200,6 +201,47 @@ class GeneralizedAdvantageEstimation(Hook):
             data["advantage"], data["return"] = advantage, ret
         ops.gae(data["reward"], data["done"], value, data["next_value"], self.gamma, self.lamda, self.lamda_value,
                 advantage=advantage, ret=ret)
+
+
+class AdvantageReduction(Hook):
+    """Reduces a vector advantage (one channel per reward term) to the scalar the surrogate needs: optional per-channel
+    weights, then sum or mean over the last dim, on the minibatch.  Reference: hook/on_policy/advantage.py:13-71.  The
+    Dv > 1 GAE scan that produces the vector advantage is K1 (bit-exact for every Dv); this reduction is a [B, Dv] -> [B, 1]
+    weighted row sum evaluated by the output-head kernel (a 1 x Dv "weight matrix"), so it needs no kernel of its own."""
+
+    def __init__(self, reduction: str = "sum", weight=None):
+        if reduction not in ("sum", "mean"):
+            raise ValueError(f"Unsupported reduction '{reduction}'")
+        super().__init__(training_only=True)
+        self.reduction = reduction
+        self.weight = None if weight is None else tuple(weight)
+        self.register_mutable("weight")
+        self._weight_tensor: Tensor | None = None
+
+    def init(self) -> None:
+        self._weight_tensor = None if self.weight is None else self.agent.to_tensor(self.weight).float()
+
+    def objective(self, metadata, batch):
+        advantage = batch["advantage"]
+        if self._weight_tensor is not None:
+            advantage = advantage * self._weight_tensor
+        if self.reduction == "sum":
+            advantage = advantage.sum(-1, keepdim=True)
+        elif self.reduction == "mean":
+            advantage = advantage.mean(-1, keepdim=True)
+        else:
+            raise ValueError(f"Unsupported reduction '{self.reduction}'")
+        batch["advantage"] = advantage
+        return None
+
+    def update_attribute(self, name: str, value) -> None:
+        super().update_attribute(name, value)
+        if name == "weight":
+            if value is None:
+                self.weight = self._weight_tensor = None
+            else:
+                self.weight = tuple(value)
+                self._weight_tensor = self.agent.to_tensor(self.weight).float()
 
 
 class AdvantageNormalization(Hook):

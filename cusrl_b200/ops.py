@@ -918,6 +918,42 @@ def sample_logp(mean: torch.Tensor, sigma: torch.Tensor, eps: torch.Tensor | Non
     _lib.check(code, "sample_logp")
 
 
+# ---------------------------------------------------------------------------------------------- observation normalisation (f2)
+def column_stats(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[mean(C) | population var(C)] over the rows of a 2-D fp32 tensor (normalization.py:15-49, correction=0)."""
+    xp, ld = _rows(x, "x")
+    rows, C = x.shape
+    lib = _lib.load()
+    scratch = _get_scratch(x.device, "colstats", lib.cusrl_b200_column_stats_scratch_bytes(C))
+    out = torch.empty(2 * C, dtype=torch.float32, device=x.device) if out is None else out
+    code = lib.cusrl_b200_column_stats_f32(xp, ld, rows, C, _ptr(out, torch.float32, "mean_var"), scratch.data_ptr(), scratch.numel(), _stream())
+    _lib.check(code, "column_stats", launches=2)
+    return out
+
+
+def rms_merge_(mean: torch.Tensor, var: torch.Tensor, std: torch.Tensor, batch_mean: torch.Tensor, batch_var: torch.Tensor,
+               w_old: float, w_new: float, eps: float) -> None:
+    """merge_mean_var_ + std refresh on the running statistics (normalization.py:78-93, rms.py:161-163)."""
+    f32 = torch.float32
+    code = _lib.load().cusrl_b200_rms_merge_f32(
+        _ptr(mean, f32, "mean"), _ptr(var, f32, "var"), _ptr(std, f32, "std"), _ptr(batch_mean, f32, "batch_mean"),
+        _ptr(batch_var, f32, "batch_var"), mean.numel(), float(w_old), float(w_new), float(eps), _stream())
+    _lib.check(code, "rms_merge")
+
+
+def rms_normalize(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, clamp: float | None, out: torch.Tensor | None = None,
+                  zero_padding: bool = False) -> torch.Tensor:
+    """(x - mean) / std, clamped (rms.py:202-214); x / out: 2-D fp32 with unit inner stride (out may alias x)."""
+    xp, ldx = _rows(x, "x")
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device) if out is None else out
+    op, ldo = _rows(out, "out")
+    f32 = torch.float32
+    code = _lib.load().cusrl_b200_rms_normalize_f32(xp, ldx, op, ldo, x.shape[0], x.shape[1], _ptr(mean, f32, "mean"), _ptr(std, f32, "std"),
+                                                    -1.0 if clamp is None else float(clamp), int(zero_padding), _stream())
+    _lib.check(code, "rms_normalize")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- K5
 def rnd_reward_(target: torch.Tensor, pred: torch.Tensor, reward: torch.Tensor, reward_scale: float
                 ) -> tuple[torch.Tensor, torch.Tensor]:

@@ -24,7 +24,7 @@ RECURRENT_PPO_MINIBATCH_FIELDS = PPO_MINIBATCH_FIELDS + ("actor_memory", "critic
 
 
 def ppo_hook_suite(
-    orthogonal_init: bool = True, gae_gamma: float = 0.99, gae_lamda: float = 0.95,
+    orthogonal_init: bool = True, normalize_observation: bool = False, gae_gamma: float = 0.99, gae_lamda: float = 0.95,
     gae_lamda_value: float | None = None, normalize_advantage: bool = True, value_loss_weight: float = 0.5,
     value_loss_clip: float | None = None, surrogate_clip_ratio: float = 0.2, surrogate_loss_weight: float = 1.0,
     entropy_loss_weight: float = 0.01, max_grad_norm: float | None = 1.0, grad_clip_groups: dict[str, float] | None = None,
@@ -33,6 +33,7 @@ def ppo_hook_suite(
     """Same order as the reference's ``ppo_hook_suite`` (preset/ppo.py:37-65)."""
     hooks = [
         H.ModuleInitialization(init_actor=orthogonal_init, init_critic=orthogonal_init),
+        H.ObservationNormalization() if normalize_observation else None,
         H.ValueComputation(),
         H.GeneralizedAdvantageEstimation(gamma=gae_gamma, lamda=gae_lamda, lamda_value=gae_lamda_value),
         H.AdvantageNormalization() if normalize_advantage else None,
@@ -84,8 +85,6 @@ class PpoAgentFactory:
     def to_underlying(self) -> ActorCriticFactory:
         if self.action_space_type != "continuous":
             raise ValueError("cusrl_b200 implements the continuous (NormalDist) policy head of the PPO preset")
-        if self.normalize_observation:
-            raise ValueError("ObservationNormalization is outside the B200 hot path (SURVEY.md section 2, row 22)")
         return ActorCriticFactory(
             num_steps_per_update=self.num_steps_per_update,
             actor_factory=Actor.Factory(
@@ -99,7 +98,7 @@ class PpoAgentFactory:
             sampler=AutoMiniBatchSampler(num_epochs=self.sampler_epochs, num_mini_batches=self.sampler_mini_batches,
                                          fields=PPO_MINIBATCH_FIELDS),
             hooks=ppo_hook_suite(
-                orthogonal_init=self.orthogonal_init, gae_gamma=self.gae_gamma, gae_lamda=self.gae_lamda,
+                orthogonal_init=self.orthogonal_init, normalize_observation=self.normalize_observation, gae_gamma=self.gae_gamma, gae_lamda=self.gae_lamda,
                 gae_lamda_value=self.gae_lamda_value, normalize_advantage=self.normalize_advantage,
                 value_loss_weight=self.value_loss_weight, value_loss_clip=self.value_loss_clip,
                 surrogate_clip_ratio=self.surrogate_clip_ratio, surrogate_loss_weight=self.surrogate_loss_weight,

@@ -374,6 +374,25 @@ int cusrl_b200_linear_wgrad_f16x3(const uint16_t* dZhi, const uint16_t* dZlo, in
                                   int64_t lddw, int64_t M, int64_t N, int64_t K, int accumulate, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Observation normalisation -- replaces the per-step arithmetic of RunningMeanStd
+ *     (nn/layer/rms.py:121-214, nn/utils/normalization.py:15-49,78-93) used by ObservationNormalization
+ *     (hook/mdp/observation.py:161-215):
+ *   column_stats:  mean_var[0:C] = column means, mean_var[C:2C] = POPULATION variances (torch.var_mean(dim=0, correction=0))
+ *                  of an fp32 [rows, C] array (row pitch ld); fp64 block partials, fixed-order finalisation.
+ *                  scratch: cusrl_b200_column_stats_scratch_bytes(C) bytes, 8-byte aligned.
+ *   rms_merge:     merge_mean_var_(mean, var, w_old, batch_mean, batch_var, w_new) in place (weights are host doubles, like
+ *                  the reference's python ints), then std = sqrt(var + eps).
+ *   rms_normalize: out = clamp((x - mean) / std, -clamp, clamp) (clamp <= 0: none); x / out may be pitched, zero_padding != 0
+ *                  also zeroes out's columns C..ldo-1 (padded rollout-buffer rows). */
+size_t cusrl_b200_column_stats_scratch_bytes(int64_t C);
+int cusrl_b200_column_stats_f32(const float* x, int64_t ld, int64_t rows, int64_t C, float* mean_var, void* scratch,
+                                size_t scratch_bytes, void* stream);
+int cusrl_b200_rms_merge_f32(float* mean, float* var, float* std_, const float* batch_mean, const float* batch_var, int64_t C,
+                             double w_old, double w_new, float eps, void* stream);
+int cusrl_b200_rms_normalize_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int64_t C, const float* mean,
+                                 const float* std_, float clamp, int zero_padding, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -464,9 +464,55 @@ def make_rnd_anymal(T: int = 24, N: int = 16384, D: int = 235):
     save("rnd_anymal", **out)
 
 
+def make_obsnorm():
+    """ObservationNormalization of the reference (hook/mdp/observation.py:161-215) over a few environment steps: the
+    normalised observations it hands to the agent and its running statistics after every step."""
+    from cusrl.hook.mdp.observation import ObservationNormalization
+
+    out = {}
+    for tag, (final_missing, state_dim) in {"a": (True, None), "b": (False, 7)}.items():
+        N, C, steps = 64, 19, 5
+        g = torch.Generator().manual_seed(41 if tag == "a" else 42)
+        hook = ObservationNormalization()
+        spec = SimpleNamespace(final_state_is_missing=final_missing, mirror_observation=None, mirror_state=None,
+                               observation_is_subset_of_state=None, observation_stat_groups=(), state_stat_groups=(),
+                               observation_normalization_excluded_indices=None, state_normalization_excluded_indices=None)
+        hook.agent = SimpleNamespace(environment_spec=spec, observation_dim=C, state_dim=state_dim, has_state=state_dim is not None,
+                                     inference_mode=False, setup_module=lambda m: m, to_tensor=torch.as_tensor)
+        hook.init()
+        obs = torch.randn(N, C, generator=g) * 3.0 + 1.0
+        state = None if state_dim is None else torch.randn(N, state_dim, generator=g) * 0.5 - 2.0
+        for t in range(steps):
+            tr = {"observation": obs.clone()}
+            if state is not None:
+                tr["state"] = state.clone()
+            hook.pre_act(tr)
+            out[f"{tag}_obs_in_{t}"], out[f"{tag}_obs_norm_{t}"] = obs, tr["observation"]
+            if state is not None:
+                out[f"{tag}_state_in_{t}"], out[f"{tag}_state_norm_{t}"] = state, tr["state"]
+            next_obs = torch.randn(N, C, generator=g) * (3.0 + t) + 1.0 - t
+            next_state = None if state_dim is None else torch.randn(N, state_dim, generator=g) * 0.5 - 2.0 + 0.3 * t
+            done = torch.rand(N, 1, generator=g) < 0.2
+            tr2 = {"next_observation": next_obs.clone(), "done": done}
+            if next_state is not None:
+                tr2["next_state"] = next_state.clone()
+            hook.post_step(tr2)
+            out[f"{tag}_next_obs_in_{t}"], out[f"{tag}_next_obs_norm_{t}"], out[f"{tag}_done_{t}"] = next_obs, tr2["next_observation"], done
+            if next_state is not None:
+                out[f"{tag}_next_state_in_{t}"], out[f"{tag}_next_state_norm_{t}"] = next_state, tr2["next_state"]
+            out[f"{tag}_mean_{t}"], out[f"{tag}_var_{t}"] = hook.observation_rms.mean.clone(), hook.observation_rms.var.clone()
+            out[f"{tag}_count_{t}"] = np.int64(hook.observation_rms.count)
+            obs, state = next_obs, next_state
+        if state_dim is not None:
+            out[f"{tag}_state_mean"], out[f"{tag}_state_var"] = hook.state_rms.mean.clone(), hook.state_rms.var.clone()
+            out[f"{tag}_state_count"] = np.int64(hook.state_rms.count)
+    save("obsnorm", **out)
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    big = {"iteration_anymal": make_iteration_anymal, "lstm_anymal": make_lstm_anymal, "rnd_anymal": make_rnd_anymal}
+    big = {"iteration_anymal": make_iteration_anymal, "lstm_anymal": make_lstm_anymal, "rnd_anymal": make_rnd_anymal,
+           "obsnorm": make_obsnorm}
     if only:
         for name in only:
             (big.get(name) or globals()[f"make_{name}"])()

@@ -40,6 +40,8 @@ for s in "$@"; do
     ncu_f16)    step ncu_f16 280 ncu --set full --clock-control none --import-source on -k regex:f16x3_kernel --launch-skip 4 --launch-count 4 -o "$out/f16x3" -f python tools/ncu_f16.py ;;
     bench_cfgs) step bench_cfgs 900 bash -c "python bench.py --config mlp --envs 4096 --steps 5 --warmup 3; python bench.py --config lstm --envs 4096 --steps 3 --warmup 2; python bench.py --config rnd --envs 16384 --steps 5 --warmup 3" ;;
     bench2)     step bench2 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    bench8)     step bench8 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 10 --warmup 5 ;;
+    bench4)     step bench4 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 10 --warmup 5 ;;
     bench2ref)  step bench2ref 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 1 --warmup 1 --impl reference --ref-budget 40 ;;
     fp16probe)  step fp16probe 300 python tools/fp16_split_probe.py ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
