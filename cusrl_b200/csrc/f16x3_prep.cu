@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 // ---- weights ---------------------------------------------------------------------------------------------------------
 // stats[4] = { max|W|, max_n sum_k |W[n,k]|, max_k sum_n |W[n,k]|, max|bias| }, zeroed by the launcher; combined across
 // blocks with integer atomicMax (non-negative floats order like their bit patterns).  Blocks 0 .. row_blocks-1 take 8 rows
-// each (one warp per row, lanes along the contiguous K axis); the remaining blocks take 256 columns each (one thread per
-// column, coalesced across the block).  The L1 norms are rounded sums: consumers widen the bounds they build from them.
+// each (one warp per row, lanes along the contiguous K axis); the remaining blocks take 32 columns each (8 row groups per
+// column).  The L1 norms are rounded sums: consumers widen the bounds they build from them.
 __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
                                                            float* __restrict__ stats, int row_blocks) {
   unsigned int* out = reinterpret_cast<unsigned int*>(stats);
@@ -106,20 +106,26 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restri
       if (bias) atomicMax(out + WSTAT_BIAS_MAX, __float_as_uint(fabsf(__ldg(bias + n))));
     }
   } else {
-    const int k = ((int)blockIdx.x - row_blocks) * 256 + threadIdx.x;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // 32 columns x 8 row groups per block: lanes along the contiguous K axis (128-byte segments), each thread sums every
+    // 8th row of its column, the 8 partial sums meet in shared memory
+    __shared__ float part[8][33];
+    const int k = ((int)blockIdx.x - row_blocks) * 32 + lane;
+    float s0 = 0.f, s1 = 0.f;
     if (k < K) {
-      int n = 0;
-      for (; n + 4 <= N; n += 4) {
-        s0 += fabsf(__ldg(w + (int64_t)n * K + k)), s1 += fabsf(__ldg(w + (int64_t)(n + 1) * K + k));
-        s2 += fabsf(__ldg(w + (int64_t)(n + 2) * K + k)), s3 += fabsf(__ldg(w + (int64_t)(n + 3) * K + k));
-      }
-      for (; n < N; ++n) s0 += fabsf(__ldg(w + (int64_t)n * K + k));
+      int n = warp;
+      for (; n + 8 < N; n += 16) s0 += fabsf(__ldg(w + (int64_t)n * K + k)), s1 += fabsf(__ldg(w + (int64_t)(n + 8) * K + k));
+      if (n < N) s0 += fabsf(__ldg(w + (int64_t)n * K + k));
     }
-    float s = (s0 + s1) + (s2 + s3);
+    part[warp][lane] = s0 + s1;
+    __syncthreads();
+    if (warp == 0) {
+      float s = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if (lane == 0) atomicMax(out + WSTAT_COL_L1, __float_as_uint(s));
+      for (int g = 0; g < 8; ++g) s += part[g][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
+      if (lane == 0) atomicMax(out + WSTAT_COL_L1, __float_as_uint(s));
+    }
   }
 }
 
@@ -222,7 +228,7 @@ int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t me = cudaMemsetAsync(stats, 0, 4 * sizeof(float), s);
   CUSRL_REQUIRE(me == cudaSuccess, (int)me, "weight_prep_f16: cudaMemsetAsync: %s", cudaGetErrorString(me));
-  const int row_blocks = (int)((N + 7) / 8), col_blocks = (int)((K + 255) / 256);
+  const int row_blocks = (int)((N + 7) / 8), col_blocks = (int)((K + 31) / 32);
   weight_stats_kernel<<<row_blocks + col_blocks, 256, 0, s>>>(W, (int)N, (int)K, bias, stats, row_blocks);
   if (int e = check_launch("weight_stats_kernel")) return e;
   // the padding columns (K..ld-1 of the pair, N..ldt-1 of the transposed pair) are never written: the CALLER zero-initialises
