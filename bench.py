@@ -127,14 +127,44 @@ class RolloutData:
         self.T, self.N = T, N
 
 
-def run_iteration(agent, data: RolloutData) -> dict:
-    """24 x (act, step) + update: the reference's "agent" timer sections."""
+def run_iteration(agent, data: RolloutData, phases: dict | None = None) -> dict:
+    """24 x (act, step) + update: the reference's "agent" timer sections.  `phases` (optional) accumulates where the time of
+    the iteration goes: CUDA-event time of the rollout and of the update, and the HOST time spent issuing each of them (up
+    to the metrics read-back, the one synchronisation point of an iteration) -- host time close to the event time means the
+    phase is bound by launch overhead, not by the GPU."""
+    if phases is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        t0 = time.perf_counter()
     for t in range(data.T):
         action = agent.act(data.obs[t])
         ready = agent.step(data.obs[t + 1], data.reward[t], data.terminated[t], data.truncated[t])
     assert ready
     del action
-    return agent.update()
+    if phases is None:
+        return agent.update()
+    t1 = time.perf_counter()
+    ev[1].record()
+    mark = {}
+    summary = agent.metrics.summary
+
+    def timed_summary(*a, **k):
+        mark["t"] = time.perf_counter()
+        return summary(*a, **k)
+
+    agent.metrics.summary = timed_summary
+    try:
+        out = agent.update()
+    finally:
+        agent.metrics.summary = summary
+    ev[2].record()
+    ev[2].synchronize()
+    phases["rollout_ms"] = phases.get("rollout_ms", 0.0) + ev[0].elapsed_time(ev[1])
+    phases["update_ms"] = phases.get("update_ms", 0.0) + ev[1].elapsed_time(ev[2])
+    phases["host_rollout_issue_ms"] = phases.get("host_rollout_issue_ms", 0.0) + (t1 - t0) * 1e3
+    phases["host_update_issue_ms"] = phases.get("host_update_issue_ms", 0.0) + (mark.get("t", t1) - t1) * 1e3
+    phases["iterations"] = phases.get("iterations", 0) + 1
+    return out
 
 
 def time_iterations(agent, data, steps: int, warmup: int, distributed: bool) -> tuple[float, dict]:
@@ -440,6 +470,7 @@ def main():
     value = args.steps * T * args.envs / seconds
 
     # ---- e2e: the same iterations driven through agent.act / agent.step with HOST (pinned) buffers
+    data_for_phases = data
     e2e = None
     if not args.no_e2e:
         del data
@@ -454,6 +485,19 @@ def main():
                "h2d_bytes_per_step": per_iter_in * world, "d2h_bytes_per_step": per_iter_out * world,
                "steps": e_steps, "note": "pinned host tensors through agent.act/agent.step; metrics read back per update"}
         del host
+
+    # ---- where the time goes (2 extra iterations, separately timed): device time per phase vs host issue time per phase
+    phases: dict = {}
+    if data_for_phases is not None:
+        for _ in range(2):
+            run_iteration(agent, data_for_phases, phases)
+        n_it = phases.pop("iterations")
+        phases = {k: round(v / n_it, 3) for k, v in phases.items()}
+        if distributed:   # the slowest rank per phase
+            t = torch.tensor([phases[k] for k in sorted(phases)], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            phases = {k: round(v, 3) for k, v in zip(sorted(phases), t.tolist())}
+        del data_for_phases
 
     line = None
     if rank == 0:
@@ -501,7 +545,7 @@ def main():
             "metric": "ppo_env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(seconds / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches), "phases": phases,
             "clocks": clocks.summary(), "roofline": roof, "roofline_gae": roof_gae, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
             "last_metrics": {k: round(v, 6) for k, v in metrics.items() if k.startswith("Agent/")},
         }
