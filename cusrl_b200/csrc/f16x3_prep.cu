@@ -14,12 +14,15 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  if (ld == width && (width & 3) == 0 && aligned_to(x, 16)) {
-    const int64_t n4 = rows * width / 4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+  if (ld == width && aligned_to(x, 16)) {
+    // dense rows: one flat array whatever the width (a [M, 1] value gradient is M consecutive floats, not M one-element rows)
+    const int64_t n = rows * width, n4 = n / 4;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n4; i += nthreads) {
       const float4 v = ldg_stream4(x + 4 * i);
       m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
+    for (int64_t i = 4 * n4 + tid; i < n; i += nthreads) m = fmaxf(m, fabsf(ldg_stream(x + i)));
   } else {
     for (int64_t r = warp; r < rows; r += nwarps)
       for (int c = lane; c < width; c += 32) m = fmaxf(m, fabsf(ldg_stream(x + r * ld + c)));

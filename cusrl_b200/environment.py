@@ -10,6 +10,7 @@ Isaac-Velocity-Rough-Anymal-C-v0 shapes (obs 235, act 12, reward 1) named in BAS
 
 from __future__ import annotations
 
+from collections.abc import Callable
 from dataclasses import dataclass
 
 import torch
@@ -28,6 +29,10 @@ class EnvironmentSpec:
     reward_dim: int = 1
     autoreset: bool = False
     final_state_is_missing: bool = False
+    # symmetry transforms read by the symmetry hooks and by ObservationNormalization (template/environment.py:130-132,156-158)
+    mirror_action: Callable[[torch.Tensor], torch.Tensor] | None = None
+    mirror_observation: Callable[[torch.Tensor], torch.Tensor] | None = None
+    mirror_state: Callable[[torch.Tensor], torch.Tensor] | None = None
 
 
 class SyntheticEnvironment:

@@ -1,5 +1,13 @@
 from .auxiliary import RandomNetworkDistillation
 from .mdp import ObservationNanToNum, ObservationNormalization
+from .symmetry import (
+    MirrorDef,
+    MirrorSymmetryLoss,
+    SymmetricActor,
+    SymmetricArchitecture,
+    SymmetricDataAugmentation,
+    TransitionMirroring,
+)
 from .on_policy import (
     AdaptiveLRSchedule,
     AdvantageNormalization,
@@ -22,6 +30,8 @@ __all__ = [
     "EntropyLoss",
     "GeneralizedAdvantageEstimation",
     "GradientClipping",
+    "MirrorDef",
+    "MirrorSymmetryLoss",
     "ModuleInitialization",
     "ObservationNanToNum",
     "ObservationNormalization",
@@ -29,6 +39,10 @@ __all__ = [
     "OnPolicyStatistics",
     "PpoSurrogateLoss",
     "RandomNetworkDistillation",
+    "SymmetricActor",
+    "SymmetricArchitecture",
+    "SymmetricDataAugmentation",
+    "TransitionMirroring",
     "ValueComputation",
     "ValueLoss",
 ]

@@ -63,6 +63,18 @@ def _active_neighbor(hook: Hook, offset: int):
     return None
 
 
+def _std_vector(std: Tensor, param: Tensor) -> Tensor:
+    """The state-independent std of the current action distribution as the ``[A]`` vector the fused kernels take, WITH its
+    autograd history.  For the plain ``NormalDist`` the distribution's std is an expanded view of the parameter vector and
+    the parameter itself is handed over (no extra autograd nodes on the hot path).  A wrapper that post-processes the std
+    (``SymmetricActor``: ``(std + |mirror(std)|) / 2``, symmetry.py:455-458) still yields identical rows, so row 0 carries
+    the value, and -- every row being the same function of the parameters -- the gradient of a sum over samples w.r.t. the
+    shared vector flows through row 0 exactly."""
+    if std.data_ptr() == param.data_ptr() and all(s == 0 for s in std.stride()[:-1]):
+        return param
+    return std.reshape(-1, std.shape[-1])[0]
+
+
 def _leaf(buffer: Buffer, name: str, like: Tensor) -> Tensor:
     """Persistent ``[T, N, Dv]`` leaf `name` in the buffer (allocated on first use, then overwritten in place)."""
     if name not in buffer:
@@ -329,7 +341,7 @@ class ValueLoss(Hook):
         if fused is None:
             raise RuntimeError("ValueLoss needs a PpoSurrogateLoss hook after it (fused objective, see cusrl_b200.hook)")
         curr_value = batch["curr_value"]
-        self.agent.metrics.record_mean("value", fused["metrics"][2], curr_value.shape[0])
+        self.agent.metrics.record_mean("value", fused["metrics"][2], curr_value.numel() // curr_value.shape[-1])
         if (dv := curr_value.size(-1)) != 1:
             with torch.no_grad():
                 self.agent.record(**{f"value.{i}": curr_value[..., i] for i in range(dv)})
@@ -356,7 +368,7 @@ class OnPolicyPreparation(Hook):
         fused = batch.get("_b200_fused")
         if fused is None:
             raise RuntimeError("OnPolicyPreparation needs a PpoSurrogateLoss hook after it (fused objective)")
-        n = batch["action_logp_ratio"].shape[0]
+        n = batch["action_logp_ratio"].numel()
         self.agent.metrics.record_mean("ratio", fused["metrics"][0], n)
         self.agent.metrics.record_mean("entropy", fused["metrics"][1], n)
 
@@ -387,7 +399,7 @@ class PpoSurrogateLoss(Hook):
         dist = batch.get("curr_action_dist")
         if dist is None:
             raise RuntimeError("PpoSurrogateLoss needs an OnPolicyPreparation hook before it")
-        std_param = self.agent.actor.distribution.std.param
+        std_param = _std_vector(dist["std"], self.agent.actor.distribution.std.param)
         mean = dist["mean"]
         lead = mean.shape[:-1]
         value_cfg = batch.get("_b200_value_loss")
@@ -512,7 +524,8 @@ class OnPolicyStatistics(Hook):
         # leaves whose rows the buffer pads to 16-byte multiples (action dims 17-19, 21-23, ...) are narrow views of the
         # padded storage: the statistics kernel takes dense rows, so those (and only those) are compacted first
         out = ops.policy_stats(old["mean"].contiguous(), old["std"].contiguous(), action_dist["mean"].contiguous(),
-                               actor.distribution.std.param.detach(), buffer["action"].contiguous(),
+                               _std_vector(action_dist["std"], actor.distribution.std.param).detach().contiguous(),
+                               buffer["action"].contiguous(),
                                buffer["action_logp"], buffer["advantage"])
         agent.metrics.record_mean("kl_divergence", out[0], E)
         agent.metrics.record_mean("importance_weighted_advantage", out[1], E)

@@ -247,6 +247,9 @@ class Actor(Module):
     def reset_memory(self, memory, done=None):
         return self.backbone.reset_memory(memory, done)
 
+    def step_memory(self, observation, memory=None, **kwargs):
+        return self.backbone.step_memory(observation, memory, **kwargs)
+
 
 @dataclass(slots=True)
 class ValueFactory:
@@ -293,3 +296,6 @@ class Value(Module):
 
     def reset_memory(self, memory, done=None):
         return self.backbone.reset_memory(memory, done)
+
+    def step_memory(self, state, memory=None, **kwargs):
+        return self.backbone.step_memory(state, memory, **kwargs)

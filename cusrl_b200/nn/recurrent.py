@@ -43,6 +43,15 @@ class _LstmFunction(torch.autograd.Function):
             cseq = torch.empty(T, Nb, H, device=dev)
             hin = torch.empty(T, Nb, H, device=dev)
             cin = torch.empty(T, Nb, H, device=dev)
+            if ops.lstm_seq_supported(H):
+                # sequence-resident kernel: all T steps of the layer in one launch (csrc/lstm_seq.cu)
+                ops.lstm_seq_fwd(xp, ops.prepared_weight_f16(w_hh, b_hh), b_hh, h0[layer], c0[layer], done, gates, cseq, out,
+                                 hin, cin)
+                h_n.append(out[T - 1])
+                c_n.append(cseq[T - 1])
+                saved_layers.append((inp2, gates, cseq, hin, cin))
+                layer_in = out
+                continue
             hin[0].copy_(h0[layer])
             cin[0].copy_(c0[layer])
             wp_hh = ops.prepared_weight(w_hh)
@@ -147,7 +156,7 @@ class Rnn(Module):
             z = torch.zeros(L, n_rows, H, device=device)
             return z, z.clone()
         hidden, cell = memory["hidden"], memory["cell"]
-        if tuple(hidden.shape[:-1]) == tuple(lead_shape) and hidden.dim() >= 3:  # sequence-aligned: take step 0 (recurrent.py:202-212)
+        if lead_shape is not None and tuple(hidden.shape[:-1]) == tuple(lead_shape) and hidden.dim() >= 3:  # sequence-aligned: take step 0 (recurrent.py:202-212)
             hidden, cell = hidden[0], cell[0]
         to_lnh = lambda m: m.reshape(n_rows, L, H).transpose(0, 1).contiguous()  # "n (k c) -> k n c"  # noqa: E731
         return to_lnh(hidden), to_lnh(cell)
@@ -164,8 +173,19 @@ class Rnn(Module):
         for d in batch_shape:
             n_rows *= d
         x = input.reshape(T, n_rows, input.shape[-1])
-        h0, c0 = self._initial(memory, input.shape[:-1], n_rows, input.device)
-        d = None if done is None else done.reshape(T, n_rows)
+        # only a SEQUENCE input can carry a per-step memory; a single step with extra batch dims ([N, V, C]) must not be cut
+        h0, c0 = self._initial(memory, input.shape[:-1] if (sequential and input.dim() >= 3) else None, n_rows, input.device)
+        if done is None:
+            d = None
+        elif done.numel() == T * n_rows:
+            d = done.reshape(T, n_rows)
+        else:
+            # batch dims the flags do not carry (SymmetricDataAugmentation: input [T, N, 1 + V, C], done [T, N, 1]): every
+            # variant of an environment shares its episode boundaries
+            d = done.squeeze(-1) if done.dim() >= 3 and done.shape[-1] == 1 else done
+            while d.dim() < 1 + len(batch_shape):
+                d = d.unsqueeze(-1)
+            d = d.expand(T, *batch_shape).reshape(T, n_rows)
         out, h_n, c_n = lstm_forward(x, h0, c0, d, self.rnn)
         out = out.reshape(*input.shape[:-1], H)
         if done is not None:

@@ -1011,3 +1011,90 @@ def lstm_cell_bwd(dh_above: torch.Tensor, dh_rec: torch.Tensor | None, dc_rec: t
         _ptr(c_in, torch.float32, "c_in"), _ptr(dgates, torch.float32, "dgates"), _ptr(dc_prev, torch.float32, "dc_prev"),
         Nb, H, _stream())
     _lib.check(code, "lstm_cell_bwd")
+
+
+LSTM_SEQ = __import__("os").environ.get("CUSRL_B200_LSTM_SEQ", "1") not in ("", "0")   # 0: per-step recurrence everywhere
+
+
+def lstm_seq_supported(H: int) -> bool:
+    """The sequence-resident LSTM kernels (csrc/lstm_seq.cu) cover hidden sizes that are multiples of 64 up to 256."""
+    return LSTM_SEQ and bool(_lib.load().cusrl_b200_lstm_seq_supported(H))
+
+
+def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torch.Tensor | None, c0: torch.Tensor | None,
+                 done: torch.Tensor | None, gates: torch.Tensor, cseq: torch.Tensor, out: torch.Tensor,
+                 hin: torch.Tensor | None, cin: torch.Tensor | None) -> None:
+    """All T steps of one LSTM layer in one launch (cusrl_b200_lstm_seq_fwd_f32).  xp [T*Nb, 4H] = input projection incl.
+    b_ih; `wp` = prepared_weight_f16(W_hh); gates / cseq / out / hin / cin [T, Nb, .] are written (the per-step path's saved
+    tensors); done [T, Nb] resets the carried state after the steps where it is set."""
+    T, Nb, H = out.shape
+    xpp, ldxp = _rows(xp, "xp")
+    lib = _lib.load()
+    need = lib.cusrl_b200_lstm_seq_workspace_bytes(T, Nb, H)
+    ws = _get_scratch(out.device, "lstm_seq", need)
+    w = wp["pair"]
+    if tuple(wp["shape"]) != (4 * H, H):
+        raise ValueError(f"lstm_seq_fwd: W_hh must be [{4 * H}, {H}], got {wp['shape']}")
+    if done is not None and (done.numel() != T * Nb or not done.is_contiguous()):
+        raise ValueError("lstm_seq_fwd: 'done' must be a contiguous [T, Nb] tensor")
+    code = lib.cusrl_b200_lstm_seq_fwd_f32(
+        xpp, ldxp, w[0].data_ptr(), w[1].data_ptr(), w.shape[2], wp["stats"].data_ptr(),
+        None if b_hh is None else _ptr(b_hh.detach(), torch.float32, "b_hh"), _ptr(h0, torch.float32, "h0"),
+        _ptr(c0, torch.float32, "c0"), None if done is None else _flag_ptr(done, "done"), _ptr(gates, torch.float32, "gates"),
+        _ptr(cseq, torch.float32, "cseq"), _ptr(out, torch.float32, "out"), _ptr(hin, torch.float32, "hin"),
+        _ptr(cin, torch.float32, "cin"), T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(code, "lstm_seq_fwd", launches=1)
+
+
+# ---------------------------------------------------------------------------------------------- symmetry (f3)
+def mirror_rows(x: torch.Tensor, dest: torch.Tensor, mult: torch.Tensor, layout: str = "same",
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """Index-permute + sign-flip transforms of the rows of `x` ([..., C] fp32) in one launch (symmetry.py:58-61,84-95,334-339).
+
+    `dest` int32 [V, C] / `mult` fp32 [V, C] are V transforms ``x[..., dest[v]] * mult[v]``.  Layouts of the result:
+      "same"      V must be 1: the shape of `x`                                    (MirrorDef.__call__)
+      "stacked"   [V, *x.shape]                                                    (_build_mirrored)
+      "augmented" [*x.shape[:-1], V, C] -- with an identity first table row this is torch.cat([x.unsqueeze(-2), mirrored], -2),
+                  the tensor SymmetricDataAugmentation stores                      (_build_augmented_tensor)
+    `out` (augmented layout only) may be a narrow view of 16-byte-padded rows: the padding columns are zeroed."""
+    _require_cuda(x, "x")
+    if x.dtype != torch.float32 or dest.dtype != torch.int32 or mult.dtype != torch.float32:
+        raise TypeError("mirror_rows: x / mult must be float32 and dest int32")
+    C = x.shape[-1]
+    V = dest.shape[0]
+    if dest.shape != (V, C) or mult.shape != (V, C):
+        raise ValueError(f"mirror_rows: transform tables must be [V, {C}], got {tuple(dest.shape)} / {tuple(mult.shape)}")
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < C):   # e.g. an expanded std vector (row stride 0)
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    pad_to = 0
+    if layout == "same":
+        if V != 1:
+            raise ValueError("mirror_rows: layout 'same' takes exactly one transform")
+        res = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        target, stride_r, stride_v = res, C, 0
+    elif layout == "stacked":
+        res = torch.empty((V, *x.shape), dtype=x.dtype, device=x.device)
+        target, stride_r, stride_v = res, C, rows * C
+    elif layout == "augmented":
+        if out is None:
+            res = torch.empty((*x.shape[:-1], V, C), dtype=x.dtype, device=x.device)
+            target, stride_r, stride_v = res, V * C, C
+        else:
+            if out.shape != (*x.shape[:-1], V, C) or out.stride(-1) != 1 or out.dtype != torch.float32:
+                raise ValueError("mirror_rows: `out` must be a float32 [..., V, C] tensor with a dense last dim")
+            ldo = out.stride(-2)
+            o2 = out.reshape(-1, V, C) if out.dim() != 3 else out
+            if o2.data_ptr() != out.data_ptr() or o2.stride(1) != ldo or (rows > 1 and o2.stride(0) != V * ldo):
+                raise ValueError("mirror_rows: `out` rows must be uniformly pitched")
+            res, target, stride_r, stride_v, pad_to = out, out, V * ldo, ldo, (ldo if ldo != C else 0)
+    else:
+        raise ValueError(f"mirror_rows: unknown layout '{layout}'")
+    if rows == 0:
+        return res
+    code = _lib.load().cusrl_b200_mirror_rows_f32(
+        x2.data_ptr(), x2.stride(0), rows, C, _ptr(dest, torch.int32, "dest"), _ptr(mult, torch.float32, "mult"), V,
+        target.data_ptr(), stride_r, stride_v, pad_to, _stream())
+    _lib.check(code, "mirror_rows")
+    return res

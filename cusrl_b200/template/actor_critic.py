@@ -149,8 +149,9 @@ class ActorCritic:
         self.actor_factory, self.critic_factory, self.optimizer_factory = actor_factory, critic_factory, optimizer_factory
         self.hook = HookComposite(hooks)
         self.hook.pre_init(self)
-        self.actor = actor_factory(self.observation_dim, self.action_dim)
-        self.critic = critic_factory(self.state_dim, self.value_dim)
+        # through the attributes: a hook's pre_init may have replaced a factory (SymmetricArchitecture, actor_critic.py:203-206)
+        self.actor = self.actor_factory(self.observation_dim, self.action_dim)
+        self.critic = self.critic_factory(self.state_dim, self.value_dim)
         self.buffer = Buffer(self.buffer_capacity, self.parallelism, device=self.device)
         self.sampler = sampler
         self.actor_memory = None

@@ -94,7 +94,7 @@ class FusedRollout:
         if agent.device.type != "cuda" and self.REQUIRE_CUDA:
             return False
         actor, critic = agent.actor, agent.critic
-        if not (isinstance(actor, M.Actor) and isinstance(critic, M.Value)):
+        if not (type(actor) is M.Actor and type(critic) is M.Value):   # wrappers (SymmetricActor) run their own forward
             return False
         if not (isinstance(actor.backbone, M.Mlp) and isinstance(critic.backbone, M.Mlp)):
             return False

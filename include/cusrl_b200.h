@@ -393,6 +393,36 @@ int cusrl_b200_rms_merge_f32(float* mean, float* var, float* std_, const float* 
 int cusrl_b200_rms_normalize_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int64_t C, const float* mean,
                                  const float* std_, float clamp, int zero_padding, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Symmetry transforms -- replaces MirrorDef.__call__ (hook/auxiliary/symmetry.py:58-61:
+ *     input[..., destination] * multiplier) and the per-step gather + multiply + movedim + cat behind `_build_mirrored`
+ *     (:84-95) and `_build_augmented_tensor` (:334-339):
+ *   out[r * stride_r + v * stride_v + j] = x[r * ldx + dest[v * width + j]] * mult[v * width + j],  0 <= v < variants.
+ *   An identity row in the tables makes variant 0 the original (the augmented [N, 1 + V, C] layout: stride_r = (1 + V) * ldo,
+ *   stride_v = ldo); stride_v = rows * width, stride_r = width gives the stacked [V, N, C] layout.  pad_to > width also zeroes
+ *   columns width..pad_to-1 of every output row (16-byte-padded rollout-buffer rows).  dest entries must lie in [0, width):
+ *   the caller validates them (they are a property of the environment spec, checked once).  Bit-identical to the reference. */
+int cusrl_b200_mirror_rows_f32(const float* x, int64_t ldx, int64_t rows, int64_t width, const int32_t* dest, const float* mult,
+                               int64_t variants, float* out, int64_t stride_r, int64_t stride_v, int64_t pad_to, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7, sequence-resident LSTM layer (csrc/lstm_seq.cu) -- replaces nn.LSTM's per-step recurrence over a whole
+ *     [T, Nb, .] sequence (cusrl/nn/module/rnn.py:62-97,264-299 driven by nn/utils/recurrent.py:160-272) in ONE launch:
+ *   xp [T*Nb, 4H] (pitch ldxp) = input projection of every step incl. b_ih;  W_hh as the fp16 pair + statistics of
+ *   cusrl_b200_weight_prep_f16 ([4H, H], pitch ldw halves);  b_hh [4H] nullable;  h0 / c0 [Nb, H] nullable (zeros);
+ *   done [T, Nb] nullable: the state handed to step t+1 is zeroed where done[t] (in-line episode reset).
+ *   Writes gates [T,Nb,4H] (activated i,f,g,o), cseq = c_t, out = h_t, and (nullable, together) hin / cin = the state that
+ *   ENTERED each step -- exactly the tensors the per-step path saves for the backward pass.
+ *   H must be a multiple of 64, at most 256 (cusrl_b200_lstm_seq_supported); workspace: cusrl_b200_lstm_seq_workspace_bytes
+ *   bytes, 256-byte aligned, contents irrelevant (cleared by the call).  All CTAs of the launch must be co-resident: the grid
+ *   is sized to the SM count; do not run it concurrently with another kernel that spins on it. */
+int cusrl_b200_lstm_seq_supported(int64_t H);
+size_t cusrl_b200_lstm_seq_workspace_bytes(int64_t T, int64_t Nb, int64_t H);
+int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* Whi, const uint16_t* Wlo, int64_t ldw,
+                                const float* w_stats, const float* b_hh, const float* h0, const float* c0, const uint8_t* done,
+                                float* gates, float* cseq, float* out, float* hin, float* cin, int64_t T, int64_t Nb, int64_t H,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -464,6 +464,89 @@ def make_rnd_anymal(T: int = 24, N: int = 16384, D: int = 235):
     save("rnd_anymal", **out)
 
 
+def make_symmetry():
+    """One whole reference PPO iteration per symmetry hook (hook/auxiliary/symmetry.py:98-360 + SymmetricArchitecture) at a
+    small shape, inputs regenerated from seeds on both sides (recipes.py): rollout outputs, the leaves the hook adds, the
+    per-minibatch objectives in order, post-update parameters, metrics, LR."""
+    import recipes as R
+    from cusrl.hook.auxiliary.symmetry import (MirrorDef, MirrorSymmetryLoss, SymmetricArchitecture,
+                                               SymmetricDataAugmentation, TransitionMirroring)
+    from cusrl.template.environment import EnvironmentSpec
+    import torch.distributions.normal as normal_mod
+
+    sh = R.SYMMETRY_SHAPE
+    N, T, obs_dim, act_dim, hidden = sh["N"], sh["T"], sh["obs"], sh["act"], sh["hidden"]
+    out = {}
+    for variant in R.SYMMETRY_VARIANTS:
+        factory = cusrl.preset.ppo.PpoAgentFactory(
+            num_steps_per_update=T, actor_hidden_dims=hidden, critic_hidden_dims=hidden, activation_fn="ELU", lr=1e-3,
+            sampler_epochs=3, sampler_mini_batches=2, orthogonal_init=False, entropy_loss_weight=0.005,
+            desired_kl_divergence=0.015, device="cpu").to_underlying()
+        if variant == "augmentation":
+            factory.register_hook(SymmetricDataAugmentation(), before="value_loss")
+        elif variant == "mirror_loss":
+            factory.register_hook(MirrorSymmetryLoss(0.5, symmetrize_action_std=True), after="ppo_surrogate_loss")
+        elif variant == "transition_mirroring":
+            factory.register_hook(TransitionMirroring(), index=0)
+        else:
+            factory.register_hook(SymmetricArchitecture(), after="module_initialization")
+        spec = EnvironmentSpec(num_instances=N, observation_dim=obs_dim, action_dim=act_dim, reward_dim=1, autoreset=True,
+                               final_state_is_missing=True,
+                               mirror_observation=MirrorDef(*R.mirror_tables(obs_dim, seed=21)),
+                               mirror_action=MirrorDef(*R.mirror_tables(act_dim, seed=22)))
+        agent = factory(spec)
+        R.set_seeded_parameters(agent.named_parameters(), seed=23)
+        stream = R.anymal_stream(T, N, seed=24, obs_dim=obs_dim, p_term=0.1, p_trunc=0.05)
+        noise = R.noise_stream(T, N, act_dim, seed=25)
+        step = {"t": 0}
+        real_normal = normal_mod._standard_normal
+        normal_mod._standard_normal = lambda shape, dtype, device: noise[step["t"]].to(dtype=dtype, device=device).reshape(shape)
+        actions = []
+        try:
+            for t in range(T):
+                step["t"] = t
+                actions.append(agent.act(stream["obs"][t]).clone())
+                ready = agent.step(stream["obs"][t + 1], stream["reward"][t], stream["terminated"][t], stream["truncated"][t])
+        finally:
+            normal_mod._standard_normal = real_normal
+        assert ready
+        pre = f"{variant}/"
+        out[pre + "returned_action"] = torch.stack(actions)
+        for key, leaf in agent.buffer.storage.items():
+            if key in ("observation", "action", "action_logp", "action_dist.mean", "value", "augmented_observation",
+                       "augmented_action"):
+                out[pre + f"buffer/{key}"] = leaf.clone()
+
+        logs, names = [], []
+        real_record = agent.record
+
+        def spy_record(metrics=None, /, **kwargs):
+            if "surrogate_loss" in kwargs:
+                if not names:
+                    names.extend(kwargs)
+                logs.append([float(kwargs[k]) for k in names])
+            return real_record(metrics, **kwargs)
+
+        real_randperm = torch.randperm
+        torch.randperm = R.SeededRandperm(seed=26)
+        agent.record = spy_record
+        try:
+            metrics = agent.update()
+        finally:
+            torch.randperm = real_randperm
+        out[pre + "objective_names"] = np.array(names)
+        out[pre + "minibatch_losses"] = np.array(logs, dtype=np.float64)
+        pnames = []
+        for name, p in agent.named_parameters():
+            pnames.append(name)
+            out[pre + f"param1/{name}"] = p.detach().clone()
+        out[pre + "param_names"] = np.array(pnames)
+        out[pre + "metric_names"] = np.array(sorted(metrics))
+        out[pre + "metric_values"] = np.array([metrics[k] for k in sorted(metrics)], dtype=np.float64)
+        out[pre + "lr_after"] = np.float64(agent.optimizer.param_groups[0]["lr"])
+    save("symmetry", **out)
+
+
 def make_obsnorm():
     """ObservationNormalization of the reference (hook/mdp/observation.py:161-215) over a few environment steps: the
     normalised observations it hands to the agent and its running statistics after every step."""
@@ -512,7 +595,7 @@ def make_obsnorm():
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     big = {"iteration_anymal": make_iteration_anymal, "lstm_anymal": make_lstm_anymal, "rnd_anymal": make_rnd_anymal,
-           "obsnorm": make_obsnorm}
+           "obsnorm": make_obsnorm, "symmetry": make_symmetry}
     if only:
         for name in only:
             (big.get(name) or globals()[f"make_{name}"])()

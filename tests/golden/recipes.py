@@ -77,3 +77,24 @@ def fingerprint(t: torch.Tensor, samples: int = 256) -> dict:
 
 def flatten_fingerprints(prefix: str, fp: dict) -> dict:
     return {f"{prefix}/{k}": v for k, v in fp.items()}
+
+
+def mirror_tables(dim: int, seed: int) -> tuple[list[int], list[int]]:
+    """A self-inverse index-permute + sign-flip transform of width `dim` (pairs swap places and share a sign, like the
+    reference's cusrl_test/_helpers.py:17-35): (destination_indices, flipped_indices) for ``MirrorDef``."""
+    g = torch.Generator().manual_seed(seed)
+    order = torch.randperm(dim, generator=g).tolist()
+    signs = (torch.rand(dim, generator=g) < 0.5).tolist()
+    dest, flipped = list(range(dim)), []
+    for i in range(dim // 2):
+        a, b = order[2 * i], order[2 * i + 1]
+        dest[a], dest[b] = b, a
+        if signs[i]:
+            flipped += [a, b]
+    if dim % 2 == 1 and signs[dim // 2]:
+        flipped.append(order[-1])
+    return dest, sorted(flipped)
+
+
+SYMMETRY_VARIANTS = ("augmentation", "mirror_loss", "transition_mirroring", "architecture")
+SYMMETRY_SHAPE = dict(N=32, T=6, obs=19, act=5, hidden=(64, 32, 128))

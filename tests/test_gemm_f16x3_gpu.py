@@ -219,3 +219,17 @@ def test_gather_split_matches_gather_then_split(ops):
     assert ops.attached_pair(dst) is pair
     dst.add_(1.0)
     assert ops.attached_pair(dst) is None   # a torch-level in-place change invalidates the attachment
+
+
+@pytest.mark.parametrize("rows,width,pitch", [(393216, 1, 1), (393216, 12, 12), (1001, 3, 3), (5, 1, 1), (4096, 235, 236), (77, 7, 7)])
+def test_amax_exact_for_dense_narrow_and_pitched_inputs(rows, width, pitch):
+    """The exact range of a tensor (scale of its fp16 pair): dense inputs of any width take the flat vector path (a [M, 1]
+    value gradient used to be reduced one element per warp), pitched rows the row path."""
+    from cusrl_b200 import build, ops
+
+    build.build()
+    g = torch.Generator().manual_seed(rows + width)
+    back = torch.randn(rows, pitch, generator=g).cuda()
+    x = back[:, :width]
+    back[rows // 2, width - 1] = -123.5
+    assert ops.amax(x).item() == x.abs().max().item() == 123.5

@@ -121,3 +121,42 @@ def test_recurrent_ppo_trainer_and_train_rollout_consistency(C):
         import numpy as np
 
         assert np.isfinite(history[-1][key]), key
+
+
+@pytest.mark.parametrize("T,Nb,I,H,L", [(24, 1024, 235, 256, 2), (6, 200, 19, 64, 1), (5, 2500, 40, 128, 2), (1, 4096, 235, 256, 2),
+                                        (3, 128, 16, 192, 1)])
+def test_sequence_resident_kernel_equals_per_step_path(C, monkeypatch, T, Nb, I, H, L):
+    """csrc/lstm_seq.cu (one launch per layer, recurrence on the SMs) against the per-step recurrence (one GEMM + one cell
+    kernel per step): outputs, final state, and every parameter gradient computed from the tensors it saves.  Shapes cover
+    the config-3 minibatch, a ragged last row tile, more row tiles than resident CTA groups, the single-step rollout call."""
+    from cusrl_b200 import ops
+    from cusrl_b200.nn.recurrent import Rnn
+
+    torch.manual_seed(T * 1000 + Nb)
+    rnn = Rnn.Factory("LSTM", hidden_size=H, num_layers=L)(I).to("cuda")
+    x = torch.randn(T, Nb, I, device="cuda")
+    done = (torch.rand(T, Nb, 1, device="cuda") < 0.1) if T > 1 else None
+    memory = {"hidden": torch.randn(Nb, L * H, device="cuda").tanh() * 0.9, "cell": torch.randn(Nb, L * H, device="cuda")}
+    gout = torch.randn(T, Nb, H, device="cuda") / (T * Nb) ** 0.5
+    results = {}
+    for mode in (True, False):
+        monkeypatch.setattr(ops, "LSTM_SEQ", mode)
+        assert ops.lstm_seq_supported(H) is mode
+        rnn.zero_grad(set_to_none=True)
+        ops.invalidate_weight_cache()
+        if T > 1:
+            out, mem = rnn(x, memory=memory, done=done)
+            assert mem is None
+            out2, mem2 = rnn(x, memory=memory)   # no episode cuts: the final state is returned
+        else:
+            out, mem2 = rnn(x[0], memory=memory, sequential=False)
+            out2 = out
+        (out * gout.reshape(out.shape)).sum().backward()
+        results[mode] = (out.detach().clone(), out2.detach().clone(), mem2["hidden"].clone(), mem2["cell"].clone(),
+                         {k: p.grad.clone() for k, p in rnn.named_parameters()})
+    a, b = results[True], results[False]
+    for i in range(4):
+        assert torch.allclose(a[i], b[i], rtol=1e-5, atol=2e-6), (i, (a[i] - b[i]).abs().max().item())
+    for k in a[4]:
+        scale = max(b[4][k].abs().max().item(), 1e-6)
+        assert torch.allclose(a[4][k], b[4][k], rtol=1e-4, atol=2e-5 * scale), (k, (a[4][k] - b[4][k]).abs().max().item(), scale)

@@ -46,6 +46,14 @@ for s in "$@"; do
     fp16probe)  step fp16probe 300 python tools/fp16_split_probe.py ;;
     iter)       step iter 70 python tools/iter_profile.py ;;
     launches)   step launches 230 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$out/launches.csv" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-reference-cuda ;;
+    bench_8k)   step bench_8k 300 python bench.py --envs 8192 --steps 10 --warmup 5 --no-cpu-baseline --no-reference-cuda ;;
+    bench_1x)   step bench_1x 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-cuda ;;
+    hostprof_8k) step hostprof_8k 200 python tools/host_profile.py 8192 ;;
+    iter_8k)    step iter_8k 100 python tools/iter_profile.py --envs 8192 --iters 2 ;;
+    sym_tests)  step sym_tests 600 python -u -m pytest tests/test_symmetry_gpu.py tests/test_gemm_f16x3_gpu.py tests/test_lstm_gpu.py -q -m gpu --timeout 200 -rf -x ;;
+    iter_lstm)  step iter_lstm 150 python tools/iter_profile.py --envs 4096 --iters 1 --config lstm ;;
+    lstm_tests) step lstm_tests 400 python -u -m pytest tests/test_lstm_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 120 -rf -x -k "lstm or sequence" ;;
+    bench_lstm) step bench_lstm 300 python bench.py --config lstm --envs 4096 --steps 3 --warmup 2 --no-cpu-baseline --no-reference-cuda ;;
     *) echo "unknown step $s" ;;
   esac
 done

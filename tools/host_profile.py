@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import cusrl_b200 as C
 from bench import RolloutData, run_iteration
 dev = torch.device("cuda", 0)
-envs = 2048
+envs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 env = C.SyntheticEnvironment(envs, device=dev, seed=42)
 agent = C.anymal_c_rough_ppo(device=dev).from_environment(env)
 data = RolloutData(24, envs, dev, seed=1000, pinned_host=False)

@@ -7,16 +7,17 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import cusrl_b200 as C
-from bench import RolloutData, run_iteration
+from bench import RolloutData, make_b200_agent, run_iteration
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=65536)
 ap.add_argument("--iters", type=int, default=1)
+ap.add_argument("--config", default="mlp", choices=["mlp", "lstm", "rnd"])
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(42)
 env = C.SyntheticEnvironment(args.envs, device=dev, seed=42)
-agent = C.anymal_c_rough_ppo(device=dev).from_environment(env)
+agent = make_b200_agent(C, args.config, dev, env)
 data = RolloutData(24, args.envs, dev, seed=1000, pinned_host=False)
 for _ in range(2):
     run_iteration(agent, data)
