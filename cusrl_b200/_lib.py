@@ -115,9 +115,13 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
         c_int, [P, c_int64, P, c_int64, c_int64, P, c_int64, P, c_int64, c_int64, P, P, c_int64, P, P, P, P, P, c_int64, P]),
     "cusrl_b200_sample_logp_f32": (c_int, [P, P, P, c_int64, c_int64, c_int, P, P, P, P]),
     "cusrl_b200_lstm_seq_supported": (c_int, [c_int64]),
+    "cusrl_b200_lstm_seq_set_debug": (c_int, [c_int]),
     "cusrl_b200_lstm_seq_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "cusrl_b200_lstm_seq_fwd_f32": (
         c_int, [P, c_int64, P, P, c_int64, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
+    "cusrl_b200_lstm_seq_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "cusrl_b200_lstm_seq_bwd_f32": (
+        c_int, [P, c_int64, P, P, P, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "cusrl_b200_mirror_rows_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int64, P]),
 }
 

@@ -16,10 +16,12 @@
 //                tcgen05.ld, + input projection (+ b_hh), gate nonlinearities, c_t (carried in REGISTERS across steps),
 //                h_t, in-line reset where done[t] (the reference's split / pad / scatter), all saved tensors of the
 //                backward pass, and h_t re-split into the exchange pair.
-//   hand-over    per (row tile, step) one counter in global memory: every slice's epilogue publishes its part of h_t
-//                (__threadfence, then one relaxed add), the TMA producers of the tile's CTAs acquire-poll it, order the
-//                generic-proxy writes before their async-proxy reads (fence.proxy.async) and load.  No cluster, no
-//                cooperative launch, no host involvement.
+//   hand-over    per (row tile, step) one counter in global memory: every slice's epilogue stores its part of h_t, meets at
+//                a named barrier and one thread adds to the counter with release semantics (the barrier makes the release
+//                cumulative over the CTA's writes); the TMA producers of the tile's CTAs acquire-poll the counter, order the
+//                generic-proxy writes before their async-proxy reads (fence.proxy.async) and load.  The tensors saved for
+//                the backward pass are written AFTER the hand-over, off the critical path.  No cluster, no cooperative
+//                launch, no host involvement.
 //
 // Numerics: fp32-equivalent recurrent product (three fp16 MMAs, fp32 accumulation), |h| < 1 fixes the scale of the h pair
 // (2^14), W_hh's scale comes from its exact amax (weight_prep_f16); everything else is the fp32 arithmetic of
@@ -35,7 +37,7 @@ constexpr int LS_N = 4 * LS_HS;           // gate columns per CTA = UMMA N
 constexpr int LS_KB = 64;                 // halves per k-block (one 128-byte swizzle span)
 constexpr int LS_UMMA_K = 16;             // halves per tcgen05.mma
 constexpr int LS_MAX_KB = 4;              // H <= 256
-constexpr int LS_EPI_WARPS = 8;
+constexpr int LS_EPI_WARPS = 16;
 constexpr int LS_THREADS = 128 + 32 * LS_EPI_WARPS;
 constexpr int LS_W_KB_BYTES = LS_N * LS_KB * 2;    // 8 KB per half per k-block
 constexpr int LS_A_KB_BYTES = BM * LS_KB * 2;      // 16 KB per half per k-block
@@ -57,6 +59,7 @@ struct LstmSeqFwdParams {
   const float* wstats;    // weight_prep_f16 statistics of W_hh
   unsigned int* flags;    // [tiles, T + 1], zeroed by the launcher
   int T, Nb, H, tiles, slices, groups, nbp;
+  int debug;
 };
 
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -72,6 +75,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 // generic-proxy writes (made visible to this thread by the acquire above) -> ordered before this thread's async-proxy reads
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the CTA's contribution to a hand-over counter: the epilogue barrier orders every epilogue thread's global writes before
+// this one thread's release (cumulative), as in CUTLASS's semaphore release
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * LS_EPI_WARPS) : "memory"); }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
@@ -91,7 +99,39 @@ __device__ __forceinline__ void store_pair8(__half* hi, __half* lo, const float 
   *reinterpret_cast<uint4*>(lo) = l;
 }
 
-__global__ void __launch_bounds__(LS_THREADS, 1)
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void store_pair4(__half* hi, __half* lo, const float (&v)[4], float s) {
+  uint2 h, l;
+  __half2* h2 = reinterpret_cast<__half2*>(&h);
+  __half2* l2 = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float a = v[2 * k] * s, b = v[2 * k + 1] * s;
+    h2[k] = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2[k]);
+    l2[k] = __floats2half2_rn(a - back.x, b - back.y);
+  }
+  *reinterpret_cast<uint2*>(hi) = h;
+  *reinterpret_cast<uint2*>(lo) = l;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+}
+
+// Clusters of LS_CLUSTER CTAs = consecutive slices of ONE row tile: the state tile every slice needs (128 KB, the same for
+// all of them) is read from L2 once per cluster -- CTA r of the cluster loads k-block r (and r + 4, ...) and multicasts it to
+// all four.  Without this the 16 slices of a tile pulled 16 x 128 KB = 2 MB per tile and step over the L2 fabric, 16 MB per
+// step at the minibatch shape, which alone cost ~3 us of an 11 us step (measured).
+constexpr int LS_CLUSTER = 4;
+
+__global__ void __cluster_dims__(LS_CLUSTER, 1, 1) __launch_bounds__(LS_THREADS, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                     const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                     const LstmSeqFwdParams p) {
@@ -104,12 +144,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   float* s_bias = reinterpret_cast<float*>(tail);            // [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
   uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* tfull = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* tfull = bars + 1;
+  uint64_t* a_full = bars + 2;             // one per k-block: the MMAs of a k-block start when ITS 32 KB have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + LS_MAX_KB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.slices, group = blockIdx.x / p.slices;
+  const uint32_t crank = cluster_ctarank();
   const int T = p.T, H = p.H;
 
   if (threadIdx.x < LS_N) {
@@ -124,13 +165,14 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
-    mbar_init(a_full, 1);
     mbar_init(tfull, 1);
+    for (int kb = 0; kb < LS_MAX_KB; ++kb) mbar_init(&a_full[kb], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // the peers' barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -144,19 +186,20 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           tma_load_2d(sW + (kb * 2 + 0) * LS_W_KB_BYTES + q * LS_HS * 128, &tmWhi, kb * LS_KB, q * H + slice * LS_HS, w_full);
           tma_load_2d(sW + (kb * 2 + 1) * LS_W_KB_BYTES + q * LS_HS * 128, &tmWlo, kb * LS_KB, q * H + slice * LS_HS, w_full);
         }
-      uint32_t it = 0;
       for (int tile = group; tile < p.tiles; tile += p.groups) {
         const unsigned int* flag = p.flags + (int64_t)tile * (T + 1);
-        for (int t = 0; t < T; ++t, ++it) {
+        for (int t = 0; t < T; ++t) {
           // every slice of this row tile has published the state entering step t -- which also means that every CTA of the
-          // tile, this one included, is done with step t - 1 (accumulator drained, operand tile no longer read)
-          while (ld_acquire_u32(flag + t) < (unsigned int)p.slices) __nanosleep(32);
+          // tile, the four of this cluster included, is done with step t - 1 (accumulator drained, operand tile no longer
+          // read, the k-block barriers in their next phase: a peer's multicast may land before this CTA arms them)
+          while (ld_acquire_u32(flag + t) < (unsigned int)p.slices) {
+          }
           fence_proxy_async_all();
-          mbar_expect_tx(a_full, (uint32_t)(nkb * 2 * LS_A_KB_BYTES));
+          for (int kb = 0; kb < nkb; ++kb) mbar_expect_tx(&a_full[kb], (uint32_t)(2 * LS_A_KB_BYTES));
           const int row = (t & 1) * p.nbp + tile * BM;
-          for (int kb = 0; kb < nkb; ++kb) {
-            tma_load_2d(sA + (kb * 2 + 0) * LS_A_KB_BYTES, &tmAhi, kb * LS_KB, row, a_full);
-            tma_load_2d(sA + (kb * 2 + 1) * LS_A_KB_BYTES, &tmAlo, kb * LS_KB, row, a_full);
+          for (int kb = (int)crank; kb < nkb; kb += LS_CLUSTER) {
+            tma_load_2d_mc(sA + (kb * 2 + 0) * LS_A_KB_BYTES, &tmAhi, kb * LS_KB, row, &a_full[kb], (uint16_t)((1u << LS_CLUSTER) - 1));
+            tma_load_2d_mc(sA + (kb * 2 + 1) * LS_A_KB_BYTES, &tmAlo, kb * LS_KB, row, &a_full[kb], (uint16_t)((1u << LS_CLUSTER) - 1));
           }
         }
       }
@@ -169,9 +212,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
       uint32_t it = 0;
       for (int tile = group; tile < p.tiles; tile += p.groups)
         for (int t = 0; t < T; ++t, ++it) {
-          mbar_wait(a_full, it & 1);
-          tc_fence_after();
           for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait_cluster(&a_full[kb], it & 1);
+            tc_fence_after();
             const uint32_t ahi = smem_u32(sA + (kb * 2 + 0) * LS_A_KB_BYTES), alo = smem_u32(sA + (kb * 2 + 1) * LS_A_KB_BYTES);
             const uint32_t bhi = smem_u32(sW + (kb * 2 + 0) * LS_W_KB_BYTES), blo = smem_u32(sW + (kb * 2 + 1) * LS_W_KB_BYTES);
 #pragma unroll
@@ -190,124 +233,106 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
     const int ew = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;        // which 8 of the CTA's 16 hidden units
-    const int u0 = slice * LS_HS + half * 8; // first hidden unit of this thread
+    const int part = (warp - 4) >> 2;        // which 4 of the CTA's 16 hidden units
+    const int u0 = slice * LS_HS + part * 4; // first hidden unit of this thread
     const float s_h = f16x3_scale(1.f);
     const float inv_ab = 1.f / (s_h * f16x3_scale(__ldg(p.wstats + WSTAT_AMAX)));
-    float bias[4][8];
+    float bias[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bias[q][j] = s_bias[q * LS_HS + half * 8 + j];
-    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * 8);
+      for (int j = 0; j < 4; ++j) bias[q][j] = s_bias[q * LS_HS + part * 4 + j];
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * 4);
+    const bool leader = threadIdx.x == 128;
     uint32_t it = 0;
     for (int tile = group; tile < p.tiles; tile += p.groups) {
       unsigned int* flag = p.flags + (int64_t)tile * (T + 1);
       const int row = tile * BM + ew * 32 + lane;
       const bool valid = row < p.Nb;
-      float c[8], h[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) c[j] = 0.f, h[j] = 0.f;
+      float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
         const int64_t o = (int64_t)row * H + u0;
-        if (p.c0) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.c0 + o)), b = __ldg(reinterpret_cast<const float4*>(p.c0 + o + 4));
-          c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
-        }
-        if (p.h0) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.h0 + o)), b = __ldg(reinterpret_cast<const float4*>(p.h0 + o + 4));
-          h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
-        }
-        if (p.hin) {
-          *reinterpret_cast<float4*>(p.hin + o) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(p.hin + o + 4) = make_float4(h[4], h[5], h[6], h[7]);
-          *reinterpret_cast<float4*>(p.cin + o) = make_float4(c[0], c[1], c[2], c[3]);
-          *reinterpret_cast<float4*>(p.cin + o + 4) = make_float4(c[4], c[5], c[6], c[7]);
-        }
-        const int64_t ox = (int64_t)row * H + u0;  // parity 0
-        store_pair8(p.hx_hi + ox, p.hx_lo + ox, h, s_h);
+        if (p.c0) ld4(p.c0 + o, c);
+        if (p.h0) ld4(p.h0 + o, h);
+        store_pair4(p.hx_hi + o, p.hx_lo + o, h, s_h);   // parity 0
       }
-      __threadfence();
       epi_bar_sync();
-      if (threadIdx.x == 128) atomicAdd(flag, 1u);
+      if (leader) red_release_add(flag, 1u);
+      if (valid && p.hin) {
+        const int64_t o = (int64_t)row * H + u0;
+        st4(p.hin + o, h);
+        st4(p.cin + o, c);
+      }
 
       for (int t = 0; t < T; ++t, ++it) {
         // operands that do not depend on the recurrence are requested before waiting for the accumulator
-        float4 x[4][2];
+        float x[4][4];
         uint8_t dn = 0;
         if (valid) {
           const float* xr = p.xp + ((int64_t)t * p.Nb + row) * p.ldxp + u0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            x[q][0] = __ldg(reinterpret_cast<const float4*>(xr + q * H));
-            x[q][1] = __ldg(reinterpret_cast<const float4*>(xr + q * H + 4));
-          }
+          for (int q = 0; q < 4; ++q) ld4(xr + q * H, x[q]);
           if (p.done) dn = p.done[(int64_t)t * p.Nb + row];
         }
         mbar_wait(tfull, it & 1);
         tc_fence_after();
-        uint32_t r[4][8];
+        uint32_t r[4][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld_32x8(taddr + (uint32_t)(q * LS_HS), r[q]);
+        for (int q = 0; q < 4; ++q) tmem_ld_32x4(taddr + (uint32_t)(q * LS_HS), r[q]);
         tmem_ld_wait();
         tc_fence_before();
+        float g[4][4], cs[4], hs[4];
+        const float m = dn ? 0.f : 1.f;   // the state handed to step t + 1 restarts where the episode ended
         if (valid) {
-          float g[4][8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float xv[8] = {x[q][0].x, x[q][0].y, x[q][0].z, x[q][0].w, x[q][1].x, x[q][1].y, x[q][1].z, x[q][1].w};
+          for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float pre = xv[j] + fmaf(__uint_as_float(r[q][j]), inv_ab, bias[q][j]);
+            for (int j = 0; j < 4; ++j) {
+              const float pre = x[q][j] + fmaf(__uint_as_float(r[q][j]), inv_ab, bias[q][j]);
               g[q][j] = q == 2 ? tanhf(pre) : sigmoid_acc(pre);
             }
-          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            c[j] = g[1][j] * c[j] + g[0][j] * g[2][j];
-            h[j] = g[3][j] * tanhf(c[j]);
+          for (int j = 0; j < 4; ++j) {
+            cs[j] = g[1][j] * c[j] + g[0][j] * g[2][j];
+            hs[j] = g[3][j] * tanhf(cs[j]);
+            c[j] = cs[j] * m, h[j] = hs[j] * m;
           }
+          if (t + 1 < T) {
+            const int64_t ox = ((int64_t)((t + 1) & 1) * p.nbp + row) * H + u0;
+            store_pair4(p.hx_hi + ox, p.hx_lo + ox, h, s_h);
+          }
+        }
+        // publish FIRST: this slice's part of the state entering step t + 1 is on its way to L2 and this CTA has drained its
+        // accumulator; the tensors saved for the backward pass are written after the hand-over, off the critical path
+        epi_bar_sync();
+        if (leader) red_release_add(flag + t + 1, 1u);
+        if (valid && !(p.debug & 1)) {
           const int64_t o = ((int64_t)t * p.Nb + row) * H + u0;
           float* gr = p.gates + ((int64_t)t * p.Nb + row) * 4 * H + u0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<float4*>(gr + q * H) = make_float4(g[q][0], g[q][1], g[q][2], g[q][3]);
-            *reinterpret_cast<float4*>(gr + q * H + 4) = make_float4(g[q][4], g[q][5], g[q][6], g[q][7]);
-          }
-          *reinterpret_cast<float4*>(p.cseq + o) = make_float4(c[0], c[1], c[2], c[3]);
-          *reinterpret_cast<float4*>(p.cseq + o + 4) = make_float4(c[4], c[5], c[6], c[7]);
-          *reinterpret_cast<float4*>(p.out + o) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(p.out + o + 4) = make_float4(h[4], h[5], h[6], h[7]);
-          if (t + 1 < T) {
-            const float m = dn ? 0.f : 1.f;   // the state handed to step t + 1 restarts where the episode ended
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] *= m, h[j] *= m;
-            if (p.hin) {
-              const int64_t on = o + (int64_t)p.Nb * H;
-              *reinterpret_cast<float4*>(p.hin + on) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(p.hin + on + 4) = make_float4(h[4], h[5], h[6], h[7]);
-              *reinterpret_cast<float4*>(p.cin + on) = make_float4(c[0], c[1], c[2], c[3]);
-              *reinterpret_cast<float4*>(p.cin + on + 4) = make_float4(c[4], c[5], c[6], c[7]);
-            }
-            const int64_t ox = ((int64_t)((t + 1) & 1) * p.nbp + row) * H + u0;
-            store_pair8(p.hx_hi + ox, p.hx_lo + ox, h, s_h);
+          for (int q = 0; q < 4; ++q) st4(gr + q * H, g[q]);
+          st4(p.cseq + o, cs);
+          st4(p.out + o, hs);
+          if (t + 1 < T && p.hin) {
+            const int64_t on = o + (int64_t)p.Nb * H;
+            st4(p.hin + on, h);
+            st4(p.cin + on, c);
           }
         }
-        // publish: this slice's part of the state entering step t + 1 is in L2, and this CTA has drained its accumulator
-        __threadfence();
-        epi_bar_sync();
-        if (threadIdx.x == 128) atomicAdd(flag + t + 1, 1u);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // no CTA leaves while a peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 64);
   }
 }
+
+int g_lstm_debug = 0;   // timing experiments only (cusrl_b200_lstm_seq_set_debug): results are wrong when non-zero
 
 constexpr int LS_SMEM_BYTES = LS_MAX_KB * 2 * (LS_W_KB_BYTES + LS_A_KB_BYTES) + 512 + 1024;
 
@@ -318,6 +343,11 @@ static bool lstm_seq_shape_ok(int64_t H) { return H > 0 && (H % LS_KB) == 0 && H
 using namespace cusrl_b200;
 
 extern "C" {
+
+int cusrl_b200_lstm_seq_set_debug(int bits) {
+  g_lstm_debug = bits;
+  return 0;
+}
 
 int cusrl_b200_lstm_seq_supported(int64_t H) { return lstm_seq_shape_ok(H) ? 1 : 0; }
 
@@ -348,7 +378,30 @@ int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* W
   LstmSeqFwdParams p{};
   p.tiles = (int)((Nb + BM - 1) / BM);
   p.slices = (int)(H / LS_HS);
-  const int max_groups = sm_count() / p.slices;
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM_BYTES);
+    CUSRL_REQUIRE(e == cudaSuccess, (int)e, "lstm_seq_fwd: cudaFuncSetAttribute(%d bytes): %s", LS_SMEM_BYTES, cudaGetErrorString(e));
+    // every CTA of a row tile spins on its peers: the whole grid must be co-resident, and clusters cannot straddle GPCs, so
+    // the grid is bounded by the number of clusters the device can hold at once, not by the SM count
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sm_count() / LS_CLUSTER * LS_CLUSTER));
+    cfg.blockDim = dim3(LS_THREADS);
+    cfg.dynamicSmemBytes = LS_SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = LS_CLUSTER, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_seq_fwd_kernel, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = (sm_count() - 24) / LS_CLUSTER;   // conservative: up to three SMs per GPC unusable by 4-CTA clusters
+    }
+    max_clusters = n;
+    configured = true;
+  }
+  const int max_groups = max_clusters * LS_CLUSTER / p.slices;
   CUSRL_REQUIRE(max_groups >= 1, CUSRL_B200_EUNSUPPORTED, "lstm_seq_fwd: not enough SMs for one row tile");
   p.groups = p.tiles < max_groups ? p.tiles : max_groups;
   p.nbp = p.tiles * BM;
@@ -356,25 +409,375 @@ int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* W
   p.flags = (unsigned int*)workspace;
   p.hx_hi = (__half*)((uint8_t*)workspace + flag_bytes);
   p.hx_lo = p.hx_hi + (size_t)2 * p.nbp * H;
-  // flags AND exchange rows are cleared: rows >= Nb of the last tile are read by TMA (their results are discarded)
-  cudaError_t me = cudaMemsetAsync(workspace, 0, need, s);
+  // only the counters are cleared: exchange rows >= Nb of the last tile are never written and hold whatever the workspace
+  // held, but a row of the product depends on its own row of the operand only, and those rows' results are discarded
+  cudaError_t me = cudaMemsetAsync(workspace, 0, flag_bytes, s);
   CUSRL_REQUIRE(me == cudaSuccess, (int)me, "lstm_seq_fwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
   p.xp = xp, p.ldxp = ldxp, p.b_hh = b_hh, p.h0 = h0, p.c0 = c0, p.done = done;
   p.gates = gates, p.cseq = cseq, p.out = out, p.hin = hin, p.cin = cin, p.wstats = w_stats;
-  p.T = (int)T, p.Nb = (int)Nb, p.H = (int)H;
+  p.T = (int)T, p.Nb = (int)Nb, p.H = (int)H, p.debug = g_lstm_debug;
   CUtensorMap tWh, tWl, tAh, tAl;
   if (int e = encode_tmap_2d_f16(&tWh, Whi, (uint64_t)H, (uint64_t)(4 * H), (uint64_t)ldw, LS_KB, LS_HS, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tWl, Wlo, (uint64_t)H, (uint64_t)(4 * H), (uint64_t)ldw, LS_KB, LS_HS, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tAh, p.hx_hi, (uint64_t)H, (uint64_t)(2 * p.nbp), (uint64_t)H, LS_KB, BM, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tAl, p.hx_lo, (uint64_t)H, (uint64_t)(2 * p.nbp), (uint64_t)H, LS_KB, BM, TMAP_SW128)) return e;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM_BYTES);
-    CUSRL_REQUIRE(e == cudaSuccess, (int)e, "lstm_seq_fwd: cudaFuncSetAttribute(%d bytes): %s", LS_SMEM_BYTES, cudaGetErrorString(e));
-    configured = true;
-  }
   lstm_seq_fwd_kernel<<<p.groups * p.slices, LS_THREADS, LS_SMEM_BYTES, s>>>(tWh, tWl, tAh, tAl, p);
   return check_launch("lstm_seq_fwd_kernel");
+}
+
+}  // extern "C"
+
+namespace cusrl_b200 {
+
+// =================================================================================================
+// Backward through time of one layer in ONE launch.
+//
+//   dgates_t = cell'(dh_above_t + mask_t * dh_rec_t, mask_t * dc_rec_t)          elementwise (lstm_cell_bwd_kernel's arithmetic)
+//   dh_rec_{t-1} = dgates_t @ W_hh                                               [Nb, 4H] x [4H, H]
+//
+// The reduction runs over the GATE axis, which the elementwise step produces, and the result is needed along the HIDDEN axis,
+// which the next elementwise step consumes: a CTA owning 32 hidden units (all 128 of their gate columns, 128 batch rows)
+// holds a K-slice of the product.  It multiplies its dgates slice [128 x 128] (split into an fp16 pair with a scale taken from
+// the slice's own maximum, written to shared memory in the K-major SWIZZLE_128B layout the MMA reads) by its rows of W_hh
+// (resident, [H x 128] pair, gate-interleaved copy made by lstm_wt_perm_kernel) into a [128 x H] fp32 partial product, and
+// hands it to the H/32 CTAs of its row tile through L2 (double-buffered by step parity, one counter per (tile, step) as in
+// the forward kernel).  Each consumer sums the H/32 partials of its 32 columns in a FIXED order: deterministic.
+// dc is carried in registers; dgates_t is written to HBM after the hand-over (the weight gradients and the gradient
+// w.r.t. the layer input are large GEMMs over all T * Nb rows afterwards).
+constexpr int LB_HS = 32;
+constexpr int LB_KS = 4 * LB_HS;           // 128 gate columns per CTA = K of its partial product
+constexpr int LB_NKB = LB_KS / LS_KB;      // 2 k-blocks
+constexpr int LB_EPI_WARPS = 16;
+constexpr int LB_THREADS = 128 + 32 * LB_EPI_WARPS;
+constexpr int LB_MAX_H = 256;
+constexpr int LB_B_KB_BYTES = LB_MAX_H * LS_KB * 2;   // 32 KB per half per k-block
+constexpr int LB_SMEM_BYTES = LB_NKB * 2 * (LB_B_KB_BYTES + LS_A_KB_BYTES) + 512 + 1024;
+
+struct LstmSeqBwdParams {
+  const float* dout;      // [T * Nb, H] gradient w.r.t. h_t from the layer above / the head, row pitch lddo
+  int64_t lddo;
+  const float* gates;     // [T, Nb, 4H] activated gates (forward)
+  const float* cseq;      // [T, Nb, H]
+  const float* cin;       // [T, Nb, H]
+  const uint8_t* done;    // [T, Nb] or null
+  float* dgates;          // [T, Nb, 4H] pre-activation gate gradients
+  float* part;            // [2, tiles, slices, 128, H] partial products
+  const float* wstats;
+  unsigned int* flags;    // [tiles, T + 1]
+  int T, Nb, H, tiles, slices, groups;
+  int debug;
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lb_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * LB_EPI_WARPS) : "memory"); }
+
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const LstmSeqBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;                                     // [2 kb][hi | lo][H rows x 128 B]
+  uint8_t* sA = smem + LB_NKB * 2 * LB_B_KB_BYTES;        // [2 kb][hi | lo][128 rows x 128 B]
+  uint8_t* tail = sA + LB_NKB * 2 * LS_A_KB_BYTES;
+  unsigned int* s_amax = reinterpret_cast<unsigned int*>(tail);   // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 64);
+  uint64_t* b_full = bars;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* tfull = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x % p.slices, group = blockIdx.x / p.slices;
+  const int T = p.T, H = p.H;
+
+  if (threadIdx.x == 0) s_amax[0] = 0u, s_amax[1] = 0u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmBhi);
+    tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(a_ready, 1);
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the CTA's rows of W_hh (as columns of the gate-interleaved transposed pair), once
+      mbar_expect_tx(b_full, (uint32_t)(LB_NKB * 2 * H * LS_KB * 2));
+      for (int kb = 0; kb < LB_NKB; ++kb) {
+        tma_load_2d(sB + (kb * 2 + 0) * LB_B_KB_BYTES, &tmBhi, slice * LB_KS + kb * LS_KB, 0, b_full);
+        tma_load_2d(sB + (kb * 2 + 1) * LB_B_KB_BYTES, &tmBlo, slice * LB_KS + kb * LS_KB, 0, b_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(BM, H, 0, 0);
+      mbar_wait(b_full, 0);
+      uint32_t it = 0;
+      for (int tile = group; tile < p.tiles; tile += p.groups)
+        for (int t = T - 1; t >= 1; --t, ++it) {
+          mbar_wait(a_ready, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < LB_NKB; ++kb) {
+            const uint32_t ahi = smem_u32(sA + (kb * 2 + 0) * LS_A_KB_BYTES), alo = smem_u32(sA + (kb * 2 + 1) * LS_A_KB_BYTES);
+            const uint32_t bhi = smem_u32(sB + (kb * 2 + 0) * LB_B_KB_BYTES), blo = smem_u32(sB + (kb * 2 + 1) * LB_B_KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < LS_KB / LS_UMMA_K; ++k) {
+              const uint32_t off = (uint32_t)k * LS_UMMA_K * 2;
+              const uint64_t dah = make_smem_desc_sw128(ahi + off, 16, 1024, 2);
+              const uint64_t dbh = make_smem_desc_sw128(bhi + off, 16, 1024, 2);
+              mma_f16_ss(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              mma_f16_ss(tmem_base, dah, make_smem_desc_sw128(blo + off, 16, 1024, 2), idesc, 1u);
+              mma_f16_ss(tmem_base, make_smem_desc_sw128(alo + off, 16, 1024, 2), dbh, idesc, 1u);
+            }
+          }
+          mma_commit(tfull);
+        }
+    }
+  } else if (warp >= 4) {
+    // ===================================== elementwise + hand-over ==========================
+    const int ew = warp & 3;                  // TMEM lane quarter
+    const int part = (warp - 4) >> 2;         // 0..3: which 8 of the CTA's 32 hidden units / which quarter of the H columns
+    const int u0 = slice * LB_HS + part * 8;
+    const int rloc = ew * 32 + lane;
+    const float s_w = f16x3_scale(__ldg(p.wstats + WSTAT_AMAX));
+    const int cols_per_part = H / 4;          // 16, 32, 48 or 64
+    const bool leader = threadIdx.x == 128;
+    uint32_t it = 0;
+    for (int tile = group; tile < p.tiles; tile += p.groups) {
+      unsigned int* flag = p.flags + (int64_t)tile * (T + 1);
+      const int row = tile * BM + rloc;
+      const bool valid = row < p.Nb;
+      float dc_carry[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dc_carry[j] = 0.f;
+      for (int t = T - 1; t >= 0; --t) {
+        float dh[8], g[4][8], cv[8], cpv[8];
+        float m = 1.f;
+        if (valid) {
+          const int64_t rt = (int64_t)t * p.Nb + row;
+          const float* dp = p.dout + rt * p.lddo + u0;
+          const float* gp = p.gates + rt * 4 * H + u0;
+          const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp + 4));
+          dh[0] = d0.x, dh[1] = d0.y, dh[2] = d0.z, dh[3] = d0.w, dh[4] = d1.x, dh[5] = d1.y, dh[6] = d1.z, dh[7] = d1.w;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(gp + q * H)), b = __ldg(reinterpret_cast<const float4*>(gp + q * H + 4));
+            g[q][0] = a.x, g[q][1] = a.y, g[q][2] = a.z, g[q][3] = a.w, g[q][4] = b.x, g[q][5] = b.y, g[q][6] = b.z, g[q][7] = b.w;
+          }
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.cseq + rt * H + u0)), c1 = __ldg(reinterpret_cast<const float4*>(p.cseq + rt * H + u0 + 4));
+          cv[0] = c0.x, cv[1] = c0.y, cv[2] = c0.z, cv[3] = c0.w, cv[4] = c1.x, cv[5] = c1.y, cv[6] = c1.z, cv[7] = c1.w;
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.cin + rt * H + u0)), e1 = __ldg(reinterpret_cast<const float4*>(p.cin + rt * H + u0 + 4));
+          cpv[0] = e0.x, cpv[1] = e0.y, cpv[2] = e0.z, cpv[3] = e0.w, cpv[4] = e1.x, cpv[5] = e1.y, cpv[6] = e1.z, cpv[7] = e1.w;
+          if (p.done && t < T - 1 && p.done[rt]) m = 0.f;
+        }
+        float dc[8];
+        if (t < T - 1) {
+          // the partial products of step t + 1 from every slice of this row tile
+          if (leader)
+            while (ld_acquire_u32(flag + t + 1) < (unsigned int)p.slices) {
+            }
+          lb_bar_sync();
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (valid) {
+            const float* base = p.part + ((((int64_t)((t + 1) & 1) * p.tiles + tile) * p.slices) * BM + rloc) * H + u0;
+            for (int src = 0; src < p.slices; ++src) {   // fixed order: deterministic
+              const float4 a = ld_cg4(base + (int64_t)src * BM * H), b = ld_cg4(base + (int64_t)src * BM * H + 4);
+              acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w, acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dh[j] += m * acc[j], dc[j] = m * dc_carry[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+        }
+        float dg[4][8];
+        float amax = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float iv = g[0][j], fv = g[1][j], gv = g[2][j], ov = g[3][j];
+            const float tc = tanhf(cv[j]);
+            const float dct = dc[j] + dh[j] * ov * (1.f - tc * tc);
+            dg[3][j] = dh[j] * tc * ov * (1.f - ov);
+            dg[0][j] = dct * gv * iv * (1.f - iv);
+            dg[1][j] = dct * cpv[j] * fv * (1.f - fv);
+            dg[2][j] = dct * iv * (1.f - gv * gv);
+            dc_carry[j] = dct * fv;
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(dg[0][j]), fabsf(dg[1][j]))), fmaxf(fabsf(dg[2][j]), fabsf(dg[3][j])));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dg[q][j] = 0.f;
+        }
+        if (t >= 1) {
+          // scale of this step's operand pair: the exact maximum of the CTA's slice
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+          unsigned int* slot = s_amax + (it & 1);
+          if (lane == 0) atomicMax(slot, __float_as_uint(amax));
+          lb_bar_sync();
+          const float s_a = f16x3_scale(__uint_as_float(*slot));
+          if (leader) s_amax[(it & 1) ^ 1] = 0u;   // the other slot is idle until the next step's barrier
+          // operand tile: k = gate * 32 + unit -> k-block gate / 2, 16-byte chunk (gate % 2) * 4 + part of the 128-byte row
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 hv, lv;
+            __half2* h2 = reinterpret_cast<__half2*>(&hv);
+            __half2* l2 = reinterpret_cast<__half2*>(&lv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = dg[q][2 * k] * s_a, b = dg[q][2 * k + 1] * s_a;
+              h2[k] = __floats2half2_rn(a, b);
+              const float2 back = __half22float2(h2[k]);
+              l2[k] = __floats2half2_rn(a - back.x, b - back.y);
+            }
+            const int kb = q >> 1, chunk = ((q & 1) * 4 + part) ^ (rloc & 7);
+            const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + chunk * 16;
+            *reinterpret_cast<uint4*>(sA + (kb * 2 + 0) * LS_A_KB_BYTES + off) = hv;
+            *reinterpret_cast<uint4*>(sA + (kb * 2 + 1) * LS_A_KB_BYTES + off) = lv;
+          }
+          fence_proxy_async_smem();
+          lb_bar_sync();
+          if (leader) mbar_arrive(a_ready);
+          // partial product -> L2
+          mbar_wait(tfull, it & 1);
+          tc_fence_after();
+          const float inv = 1.f / (s_a * s_w);
+          float* dst = p.part + ((((int64_t)(t & 1) * p.tiles + tile) * p.slices + slice) * BM + rloc) * H + part * cols_per_part;
+          const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * cols_per_part);
+          for (int c0 = 0; c0 < cols_per_part; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr + (uint32_t)c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              *reinterpret_cast<float4*>(dst + c0 + 4 * v) =
+                  make_float4(__uint_as_float(r[4 * v]) * inv, __uint_as_float(r[4 * v + 1]) * inv,
+                              __uint_as_float(r[4 * v + 2]) * inv, __uint_as_float(r[4 * v + 3]) * inv);
+          }
+          tc_fence_before();
+          lb_bar_sync();
+          if (leader) red_release_add(flag + t, 1u);
+          ++it;
+        }
+        if (valid && !(p.debug & 2)) {   // off the critical path
+          float* op = p.dgates + ((int64_t)t * p.Nb + row) * 4 * H + u0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<float4*>(op + q * H) = make_float4(dg[q][0], dg[q][1], dg[q][2], dg[q][3]);
+            *reinterpret_cast<float4*>(op + q * H + 4) = make_float4(dg[q][4], dg[q][5], dg[q][6], dg[q][7]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// W_hh^T pair [H, 4H] (weight_prep_f16's transposed pair) -> gate-interleaved copy: out[n][s * 128 + q * 32 + u] =
+// in[n][q * H + s * 32 + u], so that the 128 reduction indices a backward CTA owns are 128 consecutive columns.
+__global__ void __launch_bounds__(256) lstm_wt_perm_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int64_t ldi,
+                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H) {
+  const int chunks_per_row = 4 * H / 8;   // 16-byte chunks of 8 halves
+  const int total = H * chunks_per_row;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / chunks_per_row, c = i - n * chunks_per_row;
+    const int col = c * 8;                       // destination column
+    const int s = col / LB_KS, q = (col % LB_KS) / LB_HS, u = col % LB_HS;
+    const int64_t src = (int64_t)n * ldi + q * H + s * LB_HS + u;
+    const int64_t dst = (int64_t)n * 4 * H + col;
+    *reinterpret_cast<uint4*>(out_hi + dst) = *reinterpret_cast<const uint4*>(in_hi + src);
+    *reinterpret_cast<uint4*>(out_lo + dst) = *reinterpret_cast<const uint4*>(in_lo + src);
+  }
+}
+
+}  // namespace cusrl_b200
+
+extern "C" {
+
+size_t cusrl_b200_lstm_seq_bwd_workspace_bytes(int64_t T, int64_t Nb, int64_t H) {
+  if (T <= 0 || Nb <= 0 || !lstm_seq_shape_ok(H)) return 0;
+  const int64_t tiles = (Nb + BM - 1) / BM, slices = H / LB_HS;
+  const size_t flags = (size_t)((tiles * (T + 1) * 4 + 255) / 256 * 256);
+  const size_t perm = (size_t)(2 * H * 4 * H) * sizeof(uint16_t);                 // gate-interleaved W_hh^T pair
+  const size_t part = (size_t)(2 * tiles * slices * BM * H) * sizeof(float);
+  return flags + perm + part;
+}
+
+int cusrl_b200_lstm_seq_bwd_f32(const float* dout, int64_t lddo, const float* gates, const float* cseq, const float* cin,
+                                const uint8_t* done, const uint16_t* WThi, const uint16_t* WTlo, int64_t ldwt, const float* w_stats,
+                                float* dgates, int64_t T, int64_t Nb, int64_t H, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  CUSRL_REQUIRE(dout && gates && cseq && cin && WThi && WTlo && w_stats && dgates && workspace, CUSRL_B200_EINVAL,
+                "lstm_seq_bwd: null pointer");
+  CUSRL_REQUIRE(T > 0 && Nb > 0 && T < (1 << 20) && Nb < (1ll << 30), CUSRL_B200_EINVAL, "lstm_seq_bwd: bad sizes");
+  CUSRL_REQUIRE(lstm_seq_shape_ok(H), CUSRL_B200_EUNSUPPORTED, "lstm_seq_bwd: H must be a multiple of 64, at most 256 (got %lld)",
+                (long long)H);
+  CUSRL_REQUIRE((lddo % 4) == 0 && lddo >= H && ldwt >= 4 * H && (ldwt % 8) == 0, CUSRL_B200_EALIGN, "lstm_seq_bwd: leading dimensions");
+  CUSRL_REQUIRE(aligned_to(dout, 16) && aligned_to(gates, 16) && aligned_to(cseq, 16) && aligned_to(cin, 16) && aligned_to(WThi, 16) &&
+                    aligned_to(WTlo, 16) && aligned_to(dgates, 16) && aligned_to(workspace, 256),
+                CUSRL_B200_EALIGN, "lstm_seq_bwd: pointers must be 16-byte aligned (workspace: 256)");
+  const size_t need = cusrl_b200_lstm_seq_bwd_workspace_bytes(T, Nb, H);
+  CUSRL_REQUIRE(workspace_bytes >= need, CUSRL_B200_ESCRATCH, "lstm_seq_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  LstmSeqBwdParams p{};
+  p.tiles = (int)((Nb + BM - 1) / BM);
+  p.slices = (int)(H / LB_HS);
+  const int max_groups = sm_count() / p.slices;
+  CUSRL_REQUIRE(max_groups >= 1, CUSRL_B200_EUNSUPPORTED, "lstm_seq_bwd: not enough SMs for one row tile");
+  p.groups = p.tiles < max_groups ? p.tiles : max_groups;
+  const size_t flag_bytes = (size_t)(((int64_t)p.tiles * (T + 1) * 4 + 255) / 256 * 256);
+  p.flags = (unsigned int*)workspace;
+  __half* perm_hi = (__half*)((uint8_t*)workspace + flag_bytes);
+  __half* perm_lo = perm_hi + (size_t)H * 4 * H;
+  p.part = (float*)(perm_lo + (size_t)H * 4 * H);
+  cudaError_t me = cudaMemsetAsync(workspace, 0, flag_bytes, s);
+  CUSRL_REQUIRE(me == cudaSuccess, (int)me, "lstm_seq_bwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
+  lstm_wt_perm_kernel<<<(int)((H * 4 * H / 8 + 255) / 256), 256, 0, s>>>((const __half*)WThi, (const __half*)WTlo, ldwt, perm_hi, perm_lo, (int)H);
+  if (int e = check_launch("lstm_wt_perm_kernel")) return e;
+  p.dout = dout, p.lddo = lddo, p.gates = gates, p.cseq = cseq, p.cin = cin, p.done = done, p.dgates = dgates, p.wstats = w_stats;
+  p.T = (int)T, p.Nb = (int)Nb, p.H = (int)H, p.debug = g_lstm_debug;
+  CUtensorMap tBh, tBl;
+  if (int e = encode_tmap_2d_f16(&tBh, perm_hi, (uint64_t)(4 * H), (uint64_t)H, (uint64_t)(4 * H), LS_KB, (uint32_t)H, TMAP_SW128)) return e;
+  if (int e = encode_tmap_2d_f16(&tBl, perm_lo, (uint64_t)(4 * H), (uint64_t)H, (uint64_t)(4 * H), LS_KB, (uint32_t)H, TMAP_SW128)) return e;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES);
+    CUSRL_REQUIRE(e == cudaSuccess, (int)e, "lstm_seq_bwd: cudaFuncSetAttribute(%d bytes): %s", LB_SMEM_BYTES, cudaGetErrorString(e));
+    configured = true;
+  }
+  lstm_seq_bwd_kernel<<<p.groups * p.slices, LB_THREADS, LB_SMEM_BYTES, s>>>(tBh, tBl, p);
+  return check_launch("lstm_seq_bwd_kernel");
 }
 
 }  // extern "C"

@@ -89,19 +89,29 @@ class _LstmFunction(torch.autograd.Function):
             w_ih, w_hh, b_ih, b_hh = weights[4 * layer : 4 * layer + 4]
             inp2, gates, cseq, hin, cin = ctx.layers[layer]
             dgates = torch.empty(T, Nb, 4 * H, device=dev)
+            seq = ops.lstm_seq_supported(H)
+            if seq:
+                ops.lstm_seq_bwd(d_layer_out, gates, cseq, cin, done, ops.prepared_weight_f16(w_hh, b_hh), dgates)
             dc_buf = [torch.empty(Nb, H, device=dev), torch.empty(Nb, H, device=dev)]
             dh_rec = None
-            wp_hh = ops.prepared_weight(w_hh)
-            for t in range(T - 1, -1, -1):
+            wp_hh = None if seq else ops.prepared_weight(w_hh)
+            for t in range(T - 1, -1, -1) if not seq else ():
                 dc_rec = None if t == T - 1 else dc_buf[(t + 1) & 1]
                 ops.lstm_cell_bwd(d_layer_out[t], dh_rec, dc_rec, None if (done is None or t == T - 1) else done[t],
                                   gates[t], cseq[t], cin[t], dgates[t], dc_buf[t & 1])
                 if t > 0:
                     dh_rec = ops.tc_linear_dgrad(dgates[t], wp_hh, None, H, 0, precision)                   # dgates_t @ W_hh
             dg2 = dgates.reshape(T * Nb, 4 * H)
-            # weight gradients over all steps at once; both biases receive the column sums of dgates
-            _wgrad(dg2, inp2, w_ih, b_ih, grads, 4 * layer, 4 * layer + 2)
-            _wgrad(dg2, hin.reshape(T * Nb, H), w_hh, b_hh, grads, 4 * layer + 1, 4 * layer + 3)
+            # weight gradients over all steps at once; both biases receive the column sums of dgates: ONE reduction pass
+            # over dgates (it reads T * Nb * 4H floats), handed to both
+            db = ops.colsum_(dg2, torch.empty(4 * H, device=dev))
+            for bias, slot in ((b_ih, 4 * layer + 2), (b_hh, 4 * layer + 3)):
+                if bias.grad is not None:
+                    bias.grad.add_(db)
+                else:
+                    grads[slot] = db.clone()
+            _wgrad(dg2, inp2, w_ih, b_ih, grads, 4 * layer, 4 * layer + 2, bias_done=True)
+            _wgrad(dg2, hin.reshape(T * Nb, H), w_hh, b_hh, grads, 4 * layer + 1, 4 * layer + 3, bias_done=True)
             if layer > 0:
                 d_layer_out = ops.tc_linear_dgrad(dg2, ops.prepared_weight(w_ih), None, w_ih.shape[1], 0, precision).reshape(T, Nb, -1)
         ctx.layers = None

@@ -1046,6 +1046,24 @@ def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torc
     _lib.check(code, "lstm_seq_fwd", launches=1)
 
 
+def lstm_seq_bwd(dout: torch.Tensor, gates: torch.Tensor, cseq: torch.Tensor, cin: torch.Tensor, done: torch.Tensor | None,
+                 wp: dict, dgates: torch.Tensor) -> None:
+    """Backward through time of one LSTM layer in one launch (cusrl_b200_lstm_seq_bwd_f32): dgates [T, Nb, 4H] from dout
+    [T, Nb, H] and the forward's saved tensors; `wp` = prepared_weight_f16(W_hh) (its transposed pair is the operand)."""
+    T, Nb, H = cseq.shape
+    d2 = dout.reshape(T * Nb, H)
+    dp, lddo = _rows(d2, "dout")
+    lib = _lib.load()
+    need = lib.cusrl_b200_lstm_seq_bwd_workspace_bytes(T, Nb, H)
+    ws = _get_scratch(cseq.device, "lstm_seq_bwd", need)
+    wt = wp["pair_t"]
+    code = lib.cusrl_b200_lstm_seq_bwd_f32(
+        dp, lddo, _ptr(gates, torch.float32, "gates"), _ptr(cseq, torch.float32, "cseq"), _ptr(cin, torch.float32, "cin"),
+        None if done is None else _flag_ptr(done, "done"), wt[0].data_ptr(), wt[1].data_ptr(), wt.shape[2], wp["stats"].data_ptr(),
+        _ptr(dgates, torch.float32, "dgates"), T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(code, "lstm_seq_bwd", launches=2)
+
+
 # ---------------------------------------------------------------------------------------------- symmetry (f3)
 def mirror_rows(x: torch.Tensor, dest: torch.Tensor, mult: torch.Tensor, layout: str = "same",
                 out: torch.Tensor | None = None) -> torch.Tensor:

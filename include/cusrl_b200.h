@@ -417,11 +417,24 @@ int cusrl_b200_mirror_rows_f32(const float* x, int64_t ldx, int64_t rows, int64_
  *   bytes, 256-byte aligned, contents irrelevant (cleared by the call).  All CTAs of the launch must be co-resident: the grid
  *   is sized to the SM count; do not run it concurrently with another kernel that spins on it. */
 int cusrl_b200_lstm_seq_supported(int64_t H);
+/* timing experiments only: non-zero bits drop parts of the kernels' work (results are then wrong); default 0 */
+int cusrl_b200_lstm_seq_set_debug(int bits);
 size_t cusrl_b200_lstm_seq_workspace_bytes(int64_t T, int64_t Nb, int64_t H);
 int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* Whi, const uint16_t* Wlo, int64_t ldw,
                                 const float* w_stats, const float* b_hh, const float* h0, const float* c0, const uint8_t* done,
                                 float* gates, float* cseq, float* out, float* hin, float* cin, int64_t T, int64_t Nb, int64_t H,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward through time of the same layer in one launch: dgates [T,Nb,4H] = pre-activation gate gradients of every step,
+ * from dout [T*Nb, H] (pitch lddo; gradient w.r.t. h_t from above) and the forward's saved gates / cseq / cin; the recurrent
+ * term dgates_{t+1} @ W_hh is formed on the SMs from W_hh^T as the TRANSPOSED fp16 pair of cusrl_b200_weight_prep_f16
+ * ([H, 4H], pitch ldwt halves).  done[t] cuts the gradient flowing from step t+1 into step t.  Deterministic.  The weight
+ * gradients and the gradient w.r.t. the layer input follow as ordinary dense-layer calls on dgates. */
+size_t cusrl_b200_lstm_seq_bwd_workspace_bytes(int64_t T, int64_t Nb, int64_t H);
+int cusrl_b200_lstm_seq_bwd_f32(const float* dout, int64_t lddo, const float* gates, const float* cseq, const float* cin,
+                                const uint8_t* done, const uint16_t* WThi, const uint16_t* WTlo, int64_t ldwt, const float* w_stats,
+                                float* dgates, int64_t T, int64_t Nb, int64_t H, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 #ifdef __cplusplus
 }

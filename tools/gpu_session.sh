@@ -54,6 +54,7 @@ for s in "$@"; do
     iter_lstm)  step iter_lstm 150 python tools/iter_profile.py --envs 4096 --iters 1 --config lstm ;;
     lstm_tests) step lstm_tests 400 python -u -m pytest tests/test_lstm_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 120 -rf -x -k "lstm or sequence" ;;
     bench_lstm) step bench_lstm 300 python bench.py --config lstm --envs 4096 --steps 3 --warmup 2 --no-cpu-baseline --no-reference-cuda ;;
+    lstm_bench) step lstm_bench 200 python tools/lstm_bench.py --debug 3 ;;
     *) echo "unknown step $s" ;;
   esac
 done
