@@ -52,8 +52,10 @@ struct LstmSeqFwdParams {
   float* gates;           // [T, Nb, 4H] activated gates
   float* cseq;            // [T, Nb, H]  c_t
   float* out;             // [T, Nb, H]  h_t
-  float* hin;             // [T, Nb, H]  state entering step t: h0, then h_{t-1} (1 - done_{t-1})   (nullable together with cin)
-  float* cin;
+  float* hin;             // [T, Nb, H]  state entering step t: h0, then h_{t-1} (1 - done_{t-1})   (nullable)
+  float* cin;             // PRIVATE layout, like gates and cseq: [T][tiles][H/4][(4 gates)][128 rows][4] -- only the backward kernel
+                          // reads them, and in this layout the 32 rows of a warp are contiguous
+  float* c_last;          // [Nb, H] row-major c_{T-1} (nullable)
   __half* hx_hi;          // [2, Nbp, H] exchange pair (Nbp = tiles * 128), parity t & 1 holds the state entering step t
   __half* hx_lo;
   const float* wstats;    // weight_prep_f16 statistics of W_hh
@@ -134,19 +136,21 @@ constexpr int LS_CLUSTER = 4;
 __global__ void __cluster_dims__(LS_CLUSTER, 1, 1) __launch_bounds__(LS_THREADS, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                     const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-                    const LstmSeqFwdParams p) {
+                    const __grid_constant__ CUtensorMap tmX, const LstmSeqFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nkb = p.H / LS_KB;
   uint8_t* sW = smem;                                        // [nkb][hi | lo][64 rows x 128 B]
   uint8_t* sA = smem + LS_MAX_KB * 2 * LS_W_KB_BYTES;        // [nkb][hi | lo][128 rows x 128 B]
-  uint8_t* tail = sA + LS_MAX_KB * 2 * LS_A_KB_BYTES;
+  uint8_t* sX = sA + LS_MAX_KB * 2 * LS_A_KB_BYTES;          // [4 gates][128 rows x 64 B] input projection of one step
+  uint8_t* tail = sX + 4 * BM * LS_HS * 4;
   float* s_bias = reinterpret_cast<float*>(tail);            // [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
   uint64_t* w_full = bars;
   uint64_t* tfull = bars + 1;
-  uint64_t* a_full = bars + 2;             // one per k-block: the MMAs of a k-block start when ITS 32 KB have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + LS_MAX_KB);
+  uint64_t* x_full = bars + 2;
+  uint64_t* a_full = bars + 3;             // one per k-block: the MMAs of a k-block start when ITS 32 KB have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + LS_MAX_KB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.slices, group = blockIdx.x / p.slices;
@@ -162,10 +166,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
     tma_prefetch_desc(&tmWlo);
     tma_prefetch_desc(&tmAhi);
     tma_prefetch_desc(&tmAlo);
+    tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(w_full, 1);
     mbar_init(tfull, 1);
+    mbar_init(x_full, 1);
     for (int kb = 0; kb < LS_MAX_KB; ++kb) mbar_init(&a_full[kb], 1);
     fence_barrier_init();
   }
@@ -232,9 +238,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
+    // Thread = (accumulator row, quad of 4 hidden units): TMEM lanes are rows, so a warp's global accesses with this mapping
+    // touch 32 different rows -- 32 L1 wavefronts per instruction, which made the loads / stores of a step cost more LSU time
+    // than everything else together (measured: 7 000 wavefront cycles per step).  Hence: the input projection arrives by TMA
+    // (x_full), tensors only this kernel's backward twin reads (gates, c_t, c_in) use a layout in which a warp's 32 rows are
+    // contiguous, and row-major outputs (h_t, the state entering step t + 1 and its fp16 pair) are transposed through the
+    // idle operand tile in shared memory and written 16 bytes per thread along rows.
     const int ew = warp & 3;                 // TMEM lane quarter this warp may access
     const int part = (warp - 4) >> 2;        // which 4 of the CTA's 16 hidden units
-    const int u0 = slice * LS_HS + part * 4; // first hidden unit of this thread
+    const int quad = slice * (LS_HS / 4) + part;
+    const int rloc = ew * 32 + lane;
+    const int etid = threadIdx.x - 128;      // 0..511
     const float s_h = f16x3_scale(1.f);
     const float inv_ab = 1.f / (s_h * f16x3_scale(__ldg(p.wstats + WSTAT_AMAX)));
     float bias[4][4];
@@ -243,36 +257,66 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) bias[q][j] = s_bias[q * LS_HS + part * 4 + j];
     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * 4);
-    const bool leader = threadIdx.x == 128;
+    const bool leader = etid == 0;
+    const int nquads = H / 4;
+    // staging inside the operand tile (idle between the MMAs of a step and the next step's loads)
+    uint8_t* st_hx = sA;                      // [hi | lo][128 rows][16 halves]   8 KB
+    float* st_out = reinterpret_cast<float*>(sA + 8192);    // [128 rows][16]      8 KB
+    float* st_hin = reinterpret_cast<float*>(sA + 16384);   // [128 rows][16]      8 KB
     uint32_t it = 0;
+
+    // row-major copy-out of the staged tiles: 16 bytes per thread, a warp covers 8 (fp32) or 16 (fp16) whole row segments
+    auto flush = [&](int tile, int t_out, int par, bool with_out, bool with_hin) {
+      {  // exchange pair -> parity `par`
+        const int hl = etid >> 8, j = etid & 255, r = j >> 1, ch = j & 1;
+        const uint4 v = *reinterpret_cast<const uint4*>(st_hx + hl * 4096 + r * 32 + ch * 16);
+        __half* dst = (hl ? p.hx_lo : p.hx_hi) + ((int64_t)par * p.nbp + tile * BM + r) * H + slice * LS_HS + ch * 8;
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
+      const int r = etid >> 2, ch = etid & 3;
+      const int grow = tile * BM + r;
+      if (grow < p.Nb) {
+        if (with_out)
+          *reinterpret_cast<float4*>(p.out + ((int64_t)t_out * p.Nb + grow) * H + slice * LS_HS + ch * 4) =
+              *reinterpret_cast<const float4*>(st_out + r * 16 + ch * 4);
+        if (with_hin && p.hin)
+          *reinterpret_cast<float4*>(p.hin + ((int64_t)(t_out + 1) * p.Nb + grow) * H + slice * LS_HS + ch * 4) =
+              *reinterpret_cast<const float4*>(st_hin + r * 16 + ch * 4);
+      }
+    };
+    auto load_x = [&](int tile, int t) {   // leader only: this CTA's 4 x [128 rows x 16] slices of the input projection
+      mbar_expect_tx(x_full, 4 * BM * LS_HS * 4);
+      for (int q = 0; q < 4; ++q) tma_load_2d(sX + q * (BM * LS_HS * 4), &tmX, q * H + slice * LS_HS, t * p.Nb + tile * BM, x_full);
+    };
+
     for (int tile = group; tile < p.tiles; tile += p.groups) {
       unsigned int* flag = p.flags + (int64_t)tile * (T + 1);
-      const int row = tile * BM + ew * 32 + lane;
+      const int row = tile * BM + rloc;
       const bool valid = row < p.Nb;
+      if (leader && tile == group) load_x(tile, 0);   // later tiles: requested at the end of the previous tile
       float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
-        const int64_t o = (int64_t)row * H + u0;
+        const int64_t o = (int64_t)row * H + slice * LS_HS + part * 4;
         if (p.c0) ld4(p.c0 + o, c);
         if (p.h0) ld4(p.h0 + o, h);
-        store_pair4(p.hx_hi + o, p.hx_lo + o, h, s_h);   // parity 0
       }
+      store_pair4(reinterpret_cast<__half*>(st_hx) + rloc * 16 + part * 4, reinterpret_cast<__half*>(st_hx + 4096) + rloc * 16 + part * 4, h, s_h);
+      st4(st_hin + rloc * 16 + part * 4, h);
+      st4(p.cin + ((((int64_t)0 * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, c);
+      epi_bar_sync();
+      flush(tile, -1, 0, false, true);   // hin[0] = h0
       epi_bar_sync();
       if (leader) red_release_add(flag, 1u);
-      if (valid && p.hin) {
-        const int64_t o = (int64_t)row * H + u0;
-        st4(p.hin + o, h);
-        st4(p.cin + o, c);
-      }
 
       for (int t = 0; t < T; ++t, ++it) {
-        // operands that do not depend on the recurrence are requested before waiting for the accumulator
-        float x[4][4];
         uint8_t dn = 0;
-        if (valid) {
-          const float* xr = p.xp + ((int64_t)t * p.Nb + row) * p.ldxp + u0;
+        if (valid && p.done) dn = p.done[(int64_t)t * p.Nb + row];
+        mbar_wait(x_full, it & 1);
+        float x[4][4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ld4(xr + q * H, x[q]);
-          if (p.done) dn = p.done[(int64_t)t * p.Nb + row];
+        for (int q = 0; q < 4; ++q) {   // SWIZZLE_64B: 16-byte unit u of 64-byte row r lives at unit u ^ ((r >> 1) & 3)
+          const float4 v = *reinterpret_cast<const float4*>(sX + q * (BM * LS_HS * 4) + rloc * 64 + ((part ^ ((rloc >> 1) & 3)) * 16));
+          x[q][0] = v.x, x[q][1] = v.y, x[q][2] = v.z, x[q][3] = v.w;
         }
         mbar_wait(tfull, it & 1);
         tc_fence_after();
@@ -283,41 +327,38 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
         tc_fence_before();
         float g[4][4], cs[4], hs[4];
         const float m = dn ? 0.f : 1.f;   // the state handed to step t + 1 restarts where the episode ended
-        if (valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float pre = x[q][j] + fmaf(__uint_as_float(r[q][j]), inv_ab, bias[q][j]);
-              g[q][j] = q == 2 ? tanhf(pre) : sigmoid_acc(pre);
-            }
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            cs[j] = g[1][j] * c[j] + g[0][j] * g[2][j];
-            hs[j] = g[3][j] * tanhf(cs[j]);
-            c[j] = cs[j] * m, h[j] = hs[j] * m;
+            const float pre = x[q][j] + fmaf(__uint_as_float(r[q][j]), inv_ab, bias[q][j]);
+            g[q][j] = q == 2 ? tanhf(pre) : sigmoid_acc(pre);
           }
-          if (t + 1 < T) {
-            const int64_t ox = ((int64_t)((t + 1) & 1) * p.nbp + row) * H + u0;
-            store_pair4(p.hx_hi + ox, p.hx_lo + ox, h, s_h);
-          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cs[j] = g[1][j] * c[j] + g[0][j] * g[2][j];
+          hs[j] = g[3][j] * tanhf(cs[j]);
+          c[j] = cs[j] * m, h[j] = hs[j] * m;
         }
-        // publish FIRST: this slice's part of the state entering step t + 1 is on its way to L2 and this CTA has drained its
-        // accumulator; the tensors saved for the backward pass are written after the hand-over, off the critical path
+        const bool more = t + 1 < T;
+        // stage the row-major outputs (the operand tile is idle: this step's MMAs have completed)
+        store_pair4(reinterpret_cast<__half*>(st_hx) + rloc * 16 + part * 4, reinterpret_cast<__half*>(st_hx + 4096) + rloc * 16 + part * 4, h, s_h);
+        st4(st_out + rloc * 16 + part * 4, hs);
+        st4(st_hin + rloc * 16 + part * 4, h);
+        epi_bar_sync();   // staged tiles complete; every thread has consumed the input-projection tile
+        if (leader && (more || tile + p.groups < p.tiles)) load_x(more ? tile : tile + p.groups, more ? t + 1 : 0);
+        flush(tile, t, (t + 1) & 1, !(p.debug & 1), more && !(p.debug & 1));
+        // publish: this slice's part of the state entering step t + 1 is on its way to L2, this CTA has drained its
+        // accumulator and no longer reads its operand tile
         epi_bar_sync();
         if (leader) red_release_add(flag + t + 1, 1u);
-        if (valid && !(p.debug & 1)) {
-          const int64_t o = ((int64_t)t * p.Nb + row) * H + u0;
-          float* gr = p.gates + ((int64_t)t * p.Nb + row) * 4 * H + u0;
+        if (!(p.debug & 1)) {   // private layouts (rows of a warp contiguous), after the hand-over
+          float* gr = p.gates + ((((int64_t)t * p.tiles + tile) * nquads + quad) * 4 * BM + rloc) * 4;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) st4(gr + q * H, g[q]);
-          st4(p.cseq + o, cs);
-          st4(p.out + o, hs);
-          if (t + 1 < T && p.hin) {
-            const int64_t on = o + (int64_t)p.Nb * H;
-            st4(p.hin + on, h);
-            st4(p.cin + on, c);
-          }
+          for (int q = 0; q < 4; ++q) st4(gr + q * BM * 4, g[q]);
+          st4(p.cseq + ((((int64_t)t * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, cs);
+          if (more) st4(p.cin + ((((int64_t)(t + 1) * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, c);
+          if (!more && valid && p.c_last) st4(p.c_last + (int64_t)row * H + slice * LS_HS + part * 4, cs);
         }
       }
     }
@@ -334,7 +375,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
 
 int g_lstm_debug = 0;   // timing experiments only (cusrl_b200_lstm_seq_set_debug): results are wrong when non-zero
 
-constexpr int LS_SMEM_BYTES = LS_MAX_KB * 2 * (LS_W_KB_BYTES + LS_A_KB_BYTES) + 512 + 1024;
+constexpr int LS_SMEM_BYTES = LS_MAX_KB * 2 * (LS_W_KB_BYTES + LS_A_KB_BYTES) + 4 * BM * LS_HS * 4 + 512 + 1024;
 
 static bool lstm_seq_shape_ok(int64_t H) { return H > 0 && (H % LS_KB) == 0 && H <= LS_MAX_KB * LS_KB; }
 
@@ -360,17 +401,16 @@ size_t cusrl_b200_lstm_seq_workspace_bytes(int64_t T, int64_t Nb, int64_t H) {
 
 int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* Whi, const uint16_t* Wlo, int64_t ldw,
                                 const float* w_stats, const float* b_hh, const float* h0, const float* c0, const uint8_t* done,
-                                float* gates, float* cseq, float* out, float* hin, float* cin, int64_t T, int64_t Nb, int64_t H,
-                                void* workspace, size_t workspace_bytes, void* stream) {
-  CUSRL_REQUIRE(xp && Whi && Wlo && w_stats && gates && cseq && out && workspace, CUSRL_B200_EINVAL, "lstm_seq_fwd: null pointer");
-  CUSRL_REQUIRE((hin == nullptr) == (cin == nullptr), CUSRL_B200_EINVAL, "lstm_seq_fwd: hin / cin go together");
+                                float* gates, float* cseq, float* out, float* hin, float* cin, float* c_last, int64_t T, int64_t Nb,
+                                int64_t H, void* workspace, size_t workspace_bytes, void* stream) {
+  CUSRL_REQUIRE(xp && Whi && Wlo && w_stats && gates && cseq && out && cin && workspace, CUSRL_B200_EINVAL, "lstm_seq_fwd: null pointer");
   CUSRL_REQUIRE(T > 0 && Nb > 0 && T < (1 << 20) && Nb < (1ll << 30), CUSRL_B200_EINVAL, "lstm_seq_fwd: bad sizes");
   CUSRL_REQUIRE(lstm_seq_shape_ok(H), CUSRL_B200_EUNSUPPORTED, "lstm_seq_fwd: H must be a multiple of 64, at most 256 (got %lld)",
                 (long long)H);
   CUSRL_REQUIRE((ldxp % 4) == 0 && ldxp >= 4 * H && ldw >= H && (ldw % 8) == 0, CUSRL_B200_EALIGN, "lstm_seq_fwd: leading dimensions");
   CUSRL_REQUIRE(aligned_to(xp, 16) && aligned_to(Whi, 16) && aligned_to(Wlo, 16) && aligned_to(gates, 16) && aligned_to(cseq, 16) &&
-                    aligned_to(out, 16) && (!hin || (aligned_to(hin, 16) && aligned_to(cin, 16))) && (!h0 || aligned_to(h0, 16)) &&
-                    (!c0 || aligned_to(c0, 16)) && aligned_to(workspace, 256),
+                    aligned_to(out, 16) && (!hin || aligned_to(hin, 16)) && aligned_to(cin, 16) && (!h0 || aligned_to(h0, 16)) &&
+                    (!c0 || aligned_to(c0, 16)) && (!c_last || aligned_to(c_last, 16)) && aligned_to(workspace, 256),
                 CUSRL_B200_EALIGN, "lstm_seq_fwd: pointers must be 16-byte aligned (workspace: 256)");
   const size_t need = cusrl_b200_lstm_seq_workspace_bytes(T, Nb, H);
   CUSRL_REQUIRE(workspace_bytes >= need, CUSRL_B200_ESCRATCH, "lstm_seq_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -414,14 +454,15 @@ int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* W
   cudaError_t me = cudaMemsetAsync(workspace, 0, flag_bytes, s);
   CUSRL_REQUIRE(me == cudaSuccess, (int)me, "lstm_seq_fwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
   p.xp = xp, p.ldxp = ldxp, p.b_hh = b_hh, p.h0 = h0, p.c0 = c0, p.done = done;
-  p.gates = gates, p.cseq = cseq, p.out = out, p.hin = hin, p.cin = cin, p.wstats = w_stats;
+  p.gates = gates, p.cseq = cseq, p.out = out, p.hin = hin, p.cin = cin, p.c_last = c_last, p.wstats = w_stats;
   p.T = (int)T, p.Nb = (int)Nb, p.H = (int)H, p.debug = g_lstm_debug;
-  CUtensorMap tWh, tWl, tAh, tAl;
+  CUtensorMap tWh, tWl, tAh, tAl, tX;
+  if (int e = encode_tmap_2d_f32(&tX, xp, (uint64_t)(4 * H), (uint64_t)(T * Nb), (uint64_t)ldxp, LS_HS, BM, TMAP_SW64)) return e;
   if (int e = encode_tmap_2d_f16(&tWh, Whi, (uint64_t)H, (uint64_t)(4 * H), (uint64_t)ldw, LS_KB, LS_HS, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tWl, Wlo, (uint64_t)H, (uint64_t)(4 * H), (uint64_t)ldw, LS_KB, LS_HS, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tAh, p.hx_hi, (uint64_t)H, (uint64_t)(2 * p.nbp), (uint64_t)H, LS_KB, BM, TMAP_SW128)) return e;
   if (int e = encode_tmap_2d_f16(&tAl, p.hx_lo, (uint64_t)H, (uint64_t)(2 * p.nbp), (uint64_t)H, LS_KB, BM, TMAP_SW128)) return e;
-  lstm_seq_fwd_kernel<<<p.groups * p.slices, LS_THREADS, LS_SMEM_BYTES, s>>>(tWh, tWl, tAh, tAl, p);
+  lstm_seq_fwd_kernel<<<p.groups * p.slices, LS_THREADS, LS_SMEM_BYTES, s>>>(tWh, tWl, tAh, tAl, tX, p);
   return check_launch("lstm_seq_fwd_kernel");
 }
 
@@ -559,7 +600,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
     const int ew = warp & 3;                  // TMEM lane quarter
     const int part = (warp - 4) >> 2;         // 0..3: which 8 of the CTA's 32 hidden units / which quarter of the H columns
     const int u0 = slice * LB_HS + part * 8;
+    const int quad0 = u0 / 4;
     const int rloc = ew * 32 + lane;
+    const int etid = threadIdx.x - 128;
     const float s_w = f16x3_scale(__ldg(p.wstats + WSTAT_AMAX));
     const int cols_per_part = H / 4;          // 16, 32, 48 or 64
     const bool leader = threadIdx.x == 128;
@@ -574,21 +617,30 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
       for (int t = T - 1; t >= 0; --t) {
         float dh[8], g[4][8], cv[8], cpv[8];
         float m = 1.f;
+        {
+          // tensors written by the forward kernel in its private layout: the 32 rows of a warp are contiguous
+          const int64_t qb = ((int64_t)t * p.tiles + tile) * (H / 4) + quad0;
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const float* gp = p.gates + (((qb + hq) * 4) * BM + rloc) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(gp + q * BM * 4));
+              g[q][4 * hq] = a.x, g[q][4 * hq + 1] = a.y, g[q][4 * hq + 2] = a.z, g[q][4 * hq + 3] = a.w;
+            }
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cseq + ((qb + hq) * BM + rloc) * 4));
+            cv[4 * hq] = cc.x, cv[4 * hq + 1] = cc.y, cv[4 * hq + 2] = cc.z, cv[4 * hq + 3] = cc.w;
+            const float4 ce = __ldg(reinterpret_cast<const float4*>(p.cin + ((qb + hq) * BM + rloc) * 4));
+            cpv[4 * hq] = ce.x, cpv[4 * hq + 1] = ce.y, cpv[4 * hq + 2] = ce.z, cpv[4 * hq + 3] = ce.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dh[j] = 0.f;
         if (valid) {
           const int64_t rt = (int64_t)t * p.Nb + row;
           const float* dp = p.dout + rt * p.lddo + u0;
-          const float* gp = p.gates + rt * 4 * H + u0;
           const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp + 4));
           dh[0] = d0.x, dh[1] = d0.y, dh[2] = d0.z, dh[3] = d0.w, dh[4] = d1.x, dh[5] = d1.y, dh[6] = d1.z, dh[7] = d1.w;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(gp + q * H)), b = __ldg(reinterpret_cast<const float4*>(gp + q * H + 4));
-            g[q][0] = a.x, g[q][1] = a.y, g[q][2] = a.z, g[q][3] = a.w, g[q][4] = b.x, g[q][5] = b.y, g[q][6] = b.z, g[q][7] = b.w;
-          }
-          const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.cseq + rt * H + u0)), c1 = __ldg(reinterpret_cast<const float4*>(p.cseq + rt * H + u0 + 4));
-          cv[0] = c0.x, cv[1] = c0.y, cv[2] = c0.z, cv[3] = c0.w, cv[4] = c1.x, cv[5] = c1.y, cv[6] = c1.z, cv[7] = c1.w;
-          const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.cin + rt * H + u0)), e1 = __ldg(reinterpret_cast<const float4*>(p.cin + rt * H + u0 + 4));
-          cpv[0] = e0.x, cpv[1] = e0.y, cpv[2] = e0.z, cpv[3] = e0.w, cpv[4] = e1.x, cpv[5] = e1.y, cpv[6] = e1.z, cpv[7] = e1.w;
           if (p.done && t < T - 1 && p.done[rt]) m = 0.f;
         }
         float dc[8];
@@ -599,10 +651,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
             }
           lb_bar_sync();
           float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const float* base = p.part + ((((int64_t)((t + 1) & 1) * p.tiles + tile) * p.slices) * BM + rloc) * H + u0;
+          {
+            // [parity][tile][source slice][H/4 quads][128 rows][4]: a warp reads 512 contiguous bytes per quad
+            const float* base = p.part + ((((int64_t)((t + 1) & 1) * p.tiles + tile) * p.slices) * (H / 4) + quad0) * BM * 4 + rloc * 4;
             for (int src = 0; src < p.slices; ++src) {   // fixed order: deterministic
-              const float4 a = ld_cg4(base + (int64_t)src * BM * H), b = ld_cg4(base + (int64_t)src * BM * H + 4);
+              const float4 a = ld_cg4(base + (int64_t)src * H * BM), b = ld_cg4(base + (int64_t)src * H * BM + BM * 4);
               acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w, acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
             }
           }
@@ -667,7 +720,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
           mbar_wait(tfull, it & 1);
           tc_fence_after();
           const float inv = 1.f / (s_a * s_w);
-          float* dst = p.part + ((((int64_t)(t & 1) * p.tiles + tile) * p.slices + slice) * BM + rloc) * H + part * cols_per_part;
+          float* dst = p.part + (((((int64_t)(t & 1) * p.tiles + tile) * p.slices + slice) * (H / 4)) + part * (cols_per_part / 4)) * BM * 4 + rloc * 4;
           const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(part * cols_per_part);
           for (int c0 = 0; c0 < cols_per_part; c0 += 16) {
             uint32_t r[16];
@@ -675,7 +728,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
             tmem_ld_wait();
 #pragma unroll
             for (int v = 0; v < 4; ++v)
-              *reinterpret_cast<float4*>(dst + c0 + 4 * v) =
+              *reinterpret_cast<float4*>(dst + (c0 / 4 + v) * BM * 4) =
                   make_float4(__uint_as_float(r[4 * v]) * inv, __uint_as_float(r[4 * v + 1]) * inv,
                               __uint_as_float(r[4 * v + 2]) * inv, __uint_as_float(r[4 * v + 3]) * inv);
           }
@@ -684,13 +737,29 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
           if (leader) red_release_add(flag + t, 1u);
           ++it;
         }
-        if (valid && !(p.debug & 2)) {   // off the critical path
-          float* op = p.dgates + ((int64_t)t * p.Nb + row) * 4 * H + u0;
+        if (!(p.debug & 2)) {
+          // off the critical path: dgates_t is consumed row-major by the weight-gradient / input-gradient GEMMs.  It is
+          // transposed through the operand tile (idle: this step's MMAs are complete, the next step's operand is written two
+          // barriers from here): [128 rows][4 gates][32 units] fp32, 16-byte units XOR-swizzled by the row within each
+          // 128-byte gate segment, then written 16 bytes per thread along rows (a warp covers one row's four segments)
+          float* stg = reinterpret_cast<float*>(sA);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<float4*>(op + q * H) = make_float4(dg[q][0], dg[q][1], dg[q][2], dg[q][3]);
-            *reinterpret_cast<float4*>(op + q * H + 4) = make_float4(dg[q][4], dg[q][5], dg[q][6], dg[q][7]);
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq)
+              *reinterpret_cast<float4*>(stg + rloc * 128 + q * 32 + (((part * 2 + hq) ^ (rloc & 7)) * 4)) =
+                  make_float4(dg[q][4 * hq], dg[q][4 * hq + 1], dg[q][4 * hq + 2], dg[q][4 * hq + 3]);
+          lb_bar_sync();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int idx = k * (32 * LB_EPI_WARPS) + etid;
+            const int r = idx >> 5, unit = idx & 31, q = unit >> 3, ch = unit & 7;
+            const int grow = tile * BM + r;
+            if (grow < p.Nb)
+              *reinterpret_cast<float4*>(p.dgates + ((int64_t)t * p.Nb + grow) * 4 * H + q * H + slice * LB_HS + ch * 4) =
+                  *reinterpret_cast<const float4*>(stg + r * 128 + q * 32 + ((ch ^ (r & 7)) * 4));
           }
+          lb_bar_sync();   // the staging tile is free again before anyone writes the next operand into it
         }
       }
     }

@@ -38,20 +38,22 @@ class _LstmFunction(torch.autograd.Function):
             w_ih, w_hh, b_ih, b_hh = weights[4 * layer : 4 * layer + 4]
             inp2 = ops_rows(layer_in.reshape(T * Nb, layer_in.shape[-1]))
             xp = ops.tc_linear_fwd(inp2, ops.prepared_weight(w_ih), b_ih, 4 * H, 0, precision)            # [T*Nb, 4H]
-            gates = torch.empty(T, Nb, 4 * H, device=dev)
             out = torch.empty(T, Nb, H, device=dev)
-            cseq = torch.empty(T, Nb, H, device=dev)
             hin = torch.empty(T, Nb, H, device=dev)
-            cin = torch.empty(T, Nb, H, device=dev)
             if ops.lstm_seq_supported(H):
-                # sequence-resident kernel: all T steps of the layer in one launch (csrc/lstm_seq.cu)
-                ops.lstm_seq_fwd(xp, ops.prepared_weight_f16(w_hh, b_hh), b_hh, h0[layer], c0[layer], done, gates, cseq, out,
-                                 hin, cin)
+                # sequence-resident kernel: all T steps of the layer in one launch (csrc/lstm_seq.cu); gates / c_t / c_in stay
+                # in the kernels' private layout for the backward twin
+                private = ops.lstm_seq_private(T, Nb, H, dev)
+                c_last = torch.empty(Nb, H, device=dev)
+                ops.lstm_seq_fwd(xp, ops.prepared_weight_f16(w_hh, b_hh), b_hh, h0[layer], c0[layer], done, private, out, hin, c_last)
                 h_n.append(out[T - 1])
-                c_n.append(cseq[T - 1])
-                saved_layers.append((inp2, gates, cseq, hin, cin))
+                c_n.append(c_last)
+                saved_layers.append((inp2, private, None, hin, None))
                 layer_in = out
                 continue
+            gates = torch.empty(T, Nb, 4 * H, device=dev)
+            cseq = torch.empty(T, Nb, H, device=dev)
+            cin = torch.empty(T, Nb, H, device=dev)
             hin[0].copy_(h0[layer])
             cin[0].copy_(c0[layer])
             wp_hh = ops.prepared_weight(w_hh)
@@ -89,9 +91,9 @@ class _LstmFunction(torch.autograd.Function):
             w_ih, w_hh, b_ih, b_hh = weights[4 * layer : 4 * layer + 4]
             inp2, gates, cseq, hin, cin = ctx.layers[layer]
             dgates = torch.empty(T, Nb, 4 * H, device=dev)
-            seq = ops.lstm_seq_supported(H)
+            seq = cseq is None   # the forward pass ran the sequence-resident kernel: `gates` holds its private buffers
             if seq:
-                ops.lstm_seq_bwd(d_layer_out, gates, cseq, cin, done, ops.prepared_weight_f16(w_hh, b_hh), dgates)
+                ops.lstm_seq_bwd(d_layer_out, gates, done, ops.prepared_weight_f16(w_hh, b_hh), dgates)   # gates = private buffers
             dc_buf = [torch.empty(Nb, H, device=dev), torch.empty(Nb, H, device=dev)]
             dh_rec = None
             wp_hh = None if seq else ops.prepared_weight(w_hh)

@@ -1021,13 +1021,22 @@ def lstm_seq_supported(H: int) -> bool:
     return LSTM_SEQ and bool(_lib.load().cusrl_b200_lstm_seq_supported(H))
 
 
+def lstm_seq_private(T: int, Nb: int, H: int, device) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(gates, cseq, cin) buffers of the sequence-resident LSTM kernels: opaque, in the kernels' private tiled layout
+    [T][ceil(Nb/128)][H/4][(4 gates)][128 rows][4] (include/cusrl_b200.h) -- written by lstm_seq_fwd, read by lstm_seq_bwd."""
+    nbp = (Nb + 127) // 128 * 128
+    return (torch.empty(T, nbp, 4 * H, device=device), torch.empty(T, nbp, H, device=device), torch.empty(T, nbp, H, device=device))
+
+
 def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torch.Tensor | None, c0: torch.Tensor | None,
-                 done: torch.Tensor | None, gates: torch.Tensor, cseq: torch.Tensor, out: torch.Tensor,
-                 hin: torch.Tensor | None, cin: torch.Tensor | None) -> None:
+                 done: torch.Tensor | None, private: tuple[torch.Tensor, torch.Tensor, torch.Tensor], out: torch.Tensor,
+                 hin: torch.Tensor | None, c_last: torch.Tensor | None) -> None:
     """All T steps of one LSTM layer in one launch (cusrl_b200_lstm_seq_fwd_f32).  xp [T*Nb, 4H] = input projection incl.
-    b_ih; `wp` = prepared_weight_f16(W_hh); gates / cseq / out / hin / cin [T, Nb, .] are written (the per-step path's saved
-    tensors); done [T, Nb] resets the carried state after the steps where it is set."""
+    b_ih; `wp` = prepared_weight_f16(W_hh); writes out = h_t and hin = the hidden state entering each step ([T, Nb, H],
+    row-major), c_last = c_{T-1} [Nb, H], and the `private` buffers of lstm_seq_private for the backward kernel; done [T, Nb]
+    resets the carried state after the steps where it is set."""
     T, Nb, H = out.shape
+    gates, cseq, cin = private
     xpp, ldxp = _rows(xp, "xp")
     lib = _lib.load()
     need = lib.cusrl_b200_lstm_seq_workspace_bytes(T, Nb, H)
@@ -1037,25 +1046,31 @@ def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torc
         raise ValueError(f"lstm_seq_fwd: W_hh must be [{4 * H}, {H}], got {wp['shape']}")
     if done is not None and (done.numel() != T * Nb or not done.is_contiguous()):
         raise ValueError("lstm_seq_fwd: 'done' must be a contiguous [T, Nb] tensor")
+    nbp = (Nb + 127) // 128 * 128
+    if gates.numel() != T * nbp * 4 * H or cseq.numel() != T * nbp * H or cin.numel() != T * nbp * H:
+        raise ValueError("lstm_seq_fwd: private buffers must come from lstm_seq_private(T, Nb, H)")
     code = lib.cusrl_b200_lstm_seq_fwd_f32(
         xpp, ldxp, w[0].data_ptr(), w[1].data_ptr(), w.shape[2], wp["stats"].data_ptr(),
         None if b_hh is None else _ptr(b_hh.detach(), torch.float32, "b_hh"), _ptr(h0, torch.float32, "h0"),
         _ptr(c0, torch.float32, "c0"), None if done is None else _flag_ptr(done, "done"), _ptr(gates, torch.float32, "gates"),
         _ptr(cseq, torch.float32, "cseq"), _ptr(out, torch.float32, "out"), _ptr(hin, torch.float32, "hin"),
-        _ptr(cin, torch.float32, "cin"), T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
+        _ptr(cin, torch.float32, "cin"), _ptr(c_last, torch.float32, "c_last"), T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(code, "lstm_seq_fwd", launches=1)
 
 
-def lstm_seq_bwd(dout: torch.Tensor, gates: torch.Tensor, cseq: torch.Tensor, cin: torch.Tensor, done: torch.Tensor | None,
+def lstm_seq_bwd(dout: torch.Tensor, private: tuple[torch.Tensor, torch.Tensor, torch.Tensor], done: torch.Tensor | None,
                  wp: dict, dgates: torch.Tensor) -> None:
-    """Backward through time of one LSTM layer in one launch (cusrl_b200_lstm_seq_bwd_f32): dgates [T, Nb, 4H] from dout
-    [T, Nb, H] and the forward's saved tensors; `wp` = prepared_weight_f16(W_hh) (its transposed pair is the operand)."""
-    T, Nb, H = cseq.shape
+    """Backward through time of one LSTM layer in one launch (cusrl_b200_lstm_seq_bwd_f32): dgates [T, Nb, 4H] (row-major)
+    from dout [T, Nb, H] and the forward's `private` buffers; `wp` = prepared_weight_f16(W_hh) (its transposed pair is the
+    operand)."""
+    T, Nb, H4 = dgates.shape
+    H = H4 // 4
+    gates, cseq, cin = private
     d2 = dout.reshape(T * Nb, H)
     dp, lddo = _rows(d2, "dout")
     lib = _lib.load()
     need = lib.cusrl_b200_lstm_seq_bwd_workspace_bytes(T, Nb, H)
-    ws = _get_scratch(cseq.device, "lstm_seq_bwd", need)
+    ws = _get_scratch(dgates.device, "lstm_seq_bwd", need)
     wt = wp["pair_t"]
     code = lib.cusrl_b200_lstm_seq_bwd_f32(
         dp, lddo, _ptr(gates, torch.float32, "gates"), _ptr(cseq, torch.float32, "cseq"), _ptr(cin, torch.float32, "cin"),

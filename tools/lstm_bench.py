@@ -40,15 +40,16 @@ for debug in sorted({0, args.debug}):
         h0 = torch.randn(Nb, H, device=dev).tanh()
         c0 = torch.randn(Nb, H, device=dev)
         done = torch.rand(T, Nb, device=dev) < 0.02
-        gates = torch.empty(T, Nb, 4 * H, device=dev)
-        cseq, out, hin, cin = (torch.empty(T, Nb, H, device=dev) for _ in range(4))
-        fwd = lambda: ops.lstm_seq_fwd(xp, wp, b_hh, h0, c0, done, gates, cseq, out, hin, cin)
+        private = ops.lstm_seq_private(T, Nb, H, dev)
+        out, hin = (torch.empty(T, Nb, H, device=dev) for _ in range(2))
+        c_last = torch.empty(Nb, H, device=dev)
+        fwd = lambda: ops.lstm_seq_fwd(xp, wp, b_hh, h0, c0, done, private, out, hin, c_last)
         us_f = timeit(fwd, args.reps)
         line = {"debug": debug, "T": T, "Nb": Nb, "H": H, "fwd_us": round(us_f, 1), "fwd_us_per_step": round(us_f / T, 2)}
         if T > 1:
             dout = torch.randn(T, Nb, H, device=dev) / (T * Nb) ** 0.5
             dgates = torch.empty(T, Nb, 4 * H, device=dev)
-            bwd = lambda: ops.lstm_seq_bwd(dout, gates, cseq, cin, done, wp, dgates)
+            bwd = lambda: ops.lstm_seq_bwd(dout, private, done, wp, dgates)
             us_b = timeit(bwd, args.reps)
             line.update(bwd_us=round(us_b, 1), bwd_us_per_step=round(us_b / (T - 1), 2))
         print(json.dumps(line), flush=True)
