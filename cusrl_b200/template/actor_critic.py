@@ -349,6 +349,16 @@ class ActorCritic:
         if keys:
             self.warn(f"Unused state_dict keys: {keys}.")
 
+    def export(self, output_dir: str, *, target_format: str = "onnx", with_environment_normalization: bool = True,
+               optimize: bool = True, sequence_len: int = 1, batch_size: int = 1, opset_version: int | None = None,
+               dynamo: bool = False, verbose: bool = True, **kwargs) -> None:
+        """actor_critic.py:332-418: the deployed (deterministic) policy as ONNX / TorchScript (template/export.py)."""
+        from .export import export_agent
+
+        export_agent(self, output_dir, target_format=target_format, with_environment_normalization=with_environment_normalization,
+                     optimize=optimize, sequence_len=sequence_len, batch_size=batch_size, opset_version=opset_version,
+                     dynamo=dynamo, verbose=verbose, **kwargs)
+
     @classmethod
     def warn(cls, message: str) -> None:
         if distributed.is_main_process():

@@ -134,3 +134,92 @@ def test_reference_side_schedule_hooks_drive_the_b200_hooks(reference):
     # non-hooks are still refused
     with pytest.raises(TypeError, match="Expected a Hook instance"):
         C.HookComposite([object()])
+
+
+@pytest.mark.parametrize("recurrent", [False, True])
+def test_export_goes_through_the_reference_exporter_and_matches_the_reference_policy(reference, tmp_path, recurrent):
+    """SURVEY.md section 8(f) rank 4, export half: `agent.export(dir, target_format="jit")` hands a plain-torch twin of the
+    B200 actor (shared parameters, reference module names) to the REFERENCE's own FlowGraph exporter
+    (cusrl/nn/layer/export.py:130-171: actor.pt, actor_stateless.pt, actor.yml); the exported policy equals the reference's
+    own actor loaded with the same state_dict.  (ONNX takes the same route; the `onnx` package is not in this image, which
+    the reference's exporter itself imports.)"""
+    import torch
+    import yaml
+
+    import cusrl_b200 as C
+
+    obs_dim, act_dim = 19, 5
+    if recurrent:
+        ours = C.RecurrentPpoAgentFactory(num_steps_per_update=4, actor_hidden_size=64, critic_hidden_size=64, actor_num_layers=2,
+                                          critic_num_layers=1, device="cpu")
+        theirs = reference.preset.ppo.RecurrentPpoAgentFactory(num_steps_per_update=4, actor_hidden_size=64, critic_hidden_size=64,
+                                                               actor_num_layers=2, critic_num_layers=1, device="cpu")
+    else:
+        ours = C.PpoAgentFactory(num_steps_per_update=4, actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128),
+                                 activation_fn="ELU", device="cpu")
+        theirs = reference.preset.ppo.PpoAgentFactory(num_steps_per_update=4, actor_hidden_dims=(64, 128),
+                                                      critic_hidden_dims=(64, 128), activation_fn="ELU", device="cpu")
+    torch.manual_seed(5)
+    agent = ours(C.EnvironmentSpec(4, obs_dim, act_dim, autoreset=True, final_state_is_missing=True))
+    from cusrl.template.environment import EnvironmentSpec as RefSpec
+
+    ref_agent = theirs(RefSpec(num_instances=4, observation_dim=obs_dim, action_dim=act_dim, autoreset=True,
+                               final_state_is_missing=True))
+    ref_agent.actor.load_state_dict(agent.actor.state_dict())
+    out = tmp_path / ("lstm" if recurrent else "mlp")
+    agent.export(str(out), target_format="jit", verbose=False)
+    assert (out / "actor.pt").exists() and (out / "actor_stateless.pt").exists() and (out / "actor.yml").exists()
+    info = yaml.safe_load((out / "actor.yml").read_text())
+    assert info["observation_dim"] == obs_dim and info["action_dim"] == act_dim and info["is_recurrent"] is recurrent
+    assert [list(d)[0] for d in info["inputs"]][0] == "observation" and [list(d)[0] for d in info["outputs"]][0] == "action"
+    stateless = torch.jit.load(str(out / "actor_stateless.pt"))
+    obs = torch.randn(1, 1, obs_dim)
+    with torch.no_grad():
+        if recurrent:
+            hidden, cell = torch.randn(1, 128) * 0.3, torch.randn(1, 128) * 0.3
+            feed = {"observation": obs, "memory_in__hidden": hidden, "memory_in__cell": cell}
+            got = stateless(*[feed[list(d)[0]] for d in info["inputs"]])
+            want, want_mem = ref_agent.actor(obs, memory={"hidden": hidden, "cell": cell}, forward_type="act_deterministic")
+            named = got if isinstance(got, dict) else dict(zip([list(d)[0] for d in info["outputs"]], got))
+            torch.testing.assert_close(named["action"], want, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(named["memory_out__hidden"], want_mem["hidden"], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(named["memory_out__cell"], want_mem["cell"], rtol=1e-5, atol=1e-6)
+        else:
+            got = stateless(obs)
+            got = got[0] if isinstance(got, (tuple, list)) else got
+            got = got["action"] if isinstance(got, dict) else got
+            want, _ = ref_agent.actor(obs, forward_type="act_deterministic")
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="Unsupported export format"):
+        agent.export(str(out), target_format="tflite")
+
+
+def test_export_standalone_torchscript_without_the_reference(tmp_path, monkeypatch):
+    """Without the reference package `target_format="jit"` traces the same twin directly; ONNX is refused, not approximated."""
+    import builtins
+
+    import torch
+
+    import cusrl_b200 as C
+
+    real_import = builtins.__import__
+
+    def no_reference(name, *a, **k):
+        if name == "cusrl" or name.startswith("cusrl."):
+            raise ImportError(name)
+        return real_import(name, *a, **k)
+
+    monkeypatch.setattr(builtins, "__import__", no_reference)
+    torch.manual_seed(6)
+    agent = C.PpoAgentFactory(num_steps_per_update=4, actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), activation_fn="ELU",
+                              device="cpu")(C.EnvironmentSpec(4, 19, 5, autoreset=True, final_state_is_missing=True))
+    agent.export(str(tmp_path), target_format="jit", verbose=False)
+    traced = torch.jit.load(str(tmp_path / "actor.pt"))
+    obs = torch.randn(3, 19)
+    lins = agent.actor.backbone.linears()
+    h = obs
+    for lin in lins:
+        h = torch.nn.functional.elu(lin(h))
+    torch.testing.assert_close(traced(obs), agent.actor.distribution.mean_head(h), rtol=1e-6, atol=1e-6)
+    with pytest.raises(RuntimeError, match="ONNX export goes through the reference"):
+        agent.export(str(tmp_path), target_format="onnx", verbose=False)

@@ -55,6 +55,8 @@ for s in "$@"; do
     lstm_tests) step lstm_tests 400 python -u -m pytest tests/test_lstm_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 120 -rf -x -k "lstm or sequence" ;;
     bench_lstm) step bench_lstm 300 python bench.py --config lstm --envs 4096 --steps 3 --warmup 2 --no-cpu-baseline --no-reference-cuda ;;
     lstm_bench) step lstm_bench 200 python tools/lstm_bench.py --debug 3 ;;
+    hostprof_lstm) step hostprof_lstm 200 python tools/host_profile.py 4096 lstm ;;
+    gemm_tests) step gemm_tests 600 python -u -m pytest tests/test_gemm_f16x3_gpu.py tests/test_gemm_gpu.py tests/test_agent_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 200 -rf -x ;;
     *) echo "unknown step $s" ;;
   esac
 done

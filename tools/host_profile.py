@@ -4,11 +4,12 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import cusrl_b200 as C
-from bench import RolloutData, run_iteration
+from bench import RolloutData, make_b200_agent, run_iteration
 dev = torch.device("cuda", 0)
 envs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+config = sys.argv[2] if len(sys.argv) > 2 else "mlp"
 env = C.SyntheticEnvironment(envs, device=dev, seed=42)
-agent = C.anymal_c_rough_ppo(device=dev).from_environment(env)
+agent = make_b200_agent(C, config, dev, env)
 data = RolloutData(24, envs, dev, seed=1000, pinned_host=False)
 for _ in range(3):
     run_iteration(agent, data)
