@@ -118,7 +118,7 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_lstm_seq_set_debug": (c_int, [c_int]),
     "cusrl_b200_lstm_seq_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "cusrl_b200_lstm_seq_fwd_f32": (
-        c_int, [P, c_int64, P, P, c_int64, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
+        c_int, [P, c_int64, P, P, c_int64, P, P, P, P, P, c_int64, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "cusrl_b200_lstm_seq_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "cusrl_b200_lstm_seq_bwd_f32": (
         c_int, [P, c_int64, P, P, P, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),

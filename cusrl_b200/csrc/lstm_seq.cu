@@ -55,7 +55,9 @@ struct LstmSeqFwdParams {
   float* hin;             // [T, Nb, H]  state entering step t: h0, then h_{t-1} (1 - done_{t-1})   (nullable)
   float* cin;             // PRIVATE layout, like gates and cseq: [T][tiles][H/4][(4 gates)][128 rows][4] -- only the backward kernel
                           // reads them, and in this layout the 32 rows of a warp are contiguous
-  float* c_last;          // [Nb, H] row-major c_{T-1} (nullable)
+  float* c_last;          // [Nb, .] row-major c_{T-1} and h_{T-1}, row pitch ld_last (nullable): the next memory
+  float* h_last;
+  int64_t ld0, ld_last;   // row pitches of h0 / c0 and of h_last / c_last (a layer's slice of a flat [N, layers * H] memory)
   __half* hx_hi;          // [2, Nbp, H] exchange pair (Nbp = tiles * 128), parity t & 1 holds the state entering step t
   __half* hx_lo;
   const float* wstats;    // weight_prep_f16 statistics of W_hh
@@ -296,13 +298,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
       if (leader && tile == group) load_x(tile, 0);   // later tiles: requested at the end of the previous tile
       float c[4] = {0.f, 0.f, 0.f, 0.f}, h[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
-        const int64_t o = (int64_t)row * H + slice * LS_HS + part * 4;
+        const int64_t o = (int64_t)row * p.ld0 + slice * LS_HS + part * 4;
         if (p.c0) ld4(p.c0 + o, c);
         if (p.h0) ld4(p.h0 + o, h);
       }
       store_pair4(reinterpret_cast<__half*>(st_hx) + rloc * 16 + part * 4, reinterpret_cast<__half*>(st_hx + 4096) + rloc * 16 + part * 4, h, s_h);
       st4(st_hin + rloc * 16 + part * 4, h);
-      st4(p.cin + ((((int64_t)0 * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, c);
+      if (p.gates) st4(p.cin + ((((int64_t)0 * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, c);
       epi_bar_sync();
       flush(tile, -1, 0, false, true);   // hin[0] = h0
       epi_bar_sync();
@@ -352,13 +354,16 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
         // accumulator and no longer reads its operand tile
         epi_bar_sync();
         if (leader) red_release_add(flag + t + 1, 1u);
-        if (!(p.debug & 1)) {   // private layouts (rows of a warp contiguous), after the hand-over
+        if (!more && valid) {   // the next memory, row-major (once per launch)
+          if (p.c_last) st4(p.c_last + (int64_t)row * p.ld_last + slice * LS_HS + part * 4, cs);
+          if (p.h_last) st4(p.h_last + (int64_t)row * p.ld_last + slice * LS_HS + part * 4, hs);
+        }
+        if (p.gates && !(p.debug & 1)) {   // private layouts (rows of a warp contiguous), after the hand-over; inference: none
           float* gr = p.gates + ((((int64_t)t * p.tiles + tile) * nquads + quad) * 4 * BM + rloc) * 4;
 #pragma unroll
           for (int q = 0; q < 4; ++q) st4(gr + q * BM * 4, g[q]);
           st4(p.cseq + ((((int64_t)t * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, cs);
           if (more) st4(p.cin + ((((int64_t)(t + 1) * p.tiles + tile) * nquads + quad) * BM + rloc) * 4, c);
-          if (!more && valid && p.c_last) st4(p.c_last + (int64_t)row * H + slice * LS_HS + part * 4, cs);
         }
       }
     }
@@ -401,16 +406,22 @@ size_t cusrl_b200_lstm_seq_workspace_bytes(int64_t T, int64_t Nb, int64_t H) {
 
 int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* Whi, const uint16_t* Wlo, int64_t ldw,
                                 const float* w_stats, const float* b_hh, const float* h0, const float* c0, const uint8_t* done,
-                                float* gates, float* cseq, float* out, float* hin, float* cin, float* c_last, int64_t T, int64_t Nb,
-                                int64_t H, void* workspace, size_t workspace_bytes, void* stream) {
-  CUSRL_REQUIRE(xp && Whi && Wlo && w_stats && gates && cseq && out && cin && workspace, CUSRL_B200_EINVAL, "lstm_seq_fwd: null pointer");
+                                int64_t ld0, float* gates, float* cseq, float* out, float* hin, float* cin, float* h_last, float* c_last,
+                                int64_t ld_last, int64_t T, int64_t Nb, int64_t H, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  CUSRL_REQUIRE(xp && Whi && Wlo && w_stats && out && workspace, CUSRL_B200_EINVAL, "lstm_seq_fwd: null pointer");
+  CUSRL_REQUIRE((gates != nullptr) == (cseq != nullptr) && (gates != nullptr) == (cin != nullptr), CUSRL_B200_EINVAL,
+                "lstm_seq_fwd: gates / cseq / cin are given together (training) or not at all (inference)");
+  CUSRL_REQUIRE(((!h0 && !c0) || (ld0 >= H && (ld0 % 4) == 0)) && ((!h_last && !c_last) || (ld_last >= H && (ld_last % 4) == 0)),
+                CUSRL_B200_EALIGN, "lstm_seq_fwd: memory row pitches must be multiples of 4 floats covering H");
   CUSRL_REQUIRE(T > 0 && Nb > 0 && T < (1 << 20) && Nb < (1ll << 30), CUSRL_B200_EINVAL, "lstm_seq_fwd: bad sizes");
   CUSRL_REQUIRE(lstm_seq_shape_ok(H), CUSRL_B200_EUNSUPPORTED, "lstm_seq_fwd: H must be a multiple of 64, at most 256 (got %lld)",
                 (long long)H);
   CUSRL_REQUIRE((ldxp % 4) == 0 && ldxp >= 4 * H && ldw >= H && (ldw % 8) == 0, CUSRL_B200_EALIGN, "lstm_seq_fwd: leading dimensions");
-  CUSRL_REQUIRE(aligned_to(xp, 16) && aligned_to(Whi, 16) && aligned_to(Wlo, 16) && aligned_to(gates, 16) && aligned_to(cseq, 16) &&
-                    aligned_to(out, 16) && (!hin || aligned_to(hin, 16)) && aligned_to(cin, 16) && (!h0 || aligned_to(h0, 16)) &&
-                    (!c0 || aligned_to(c0, 16)) && (!c_last || aligned_to(c_last, 16)) && aligned_to(workspace, 256),
+  CUSRL_REQUIRE(aligned_to(xp, 16) && aligned_to(Whi, 16) && aligned_to(Wlo, 16) && (!gates || aligned_to(gates, 16)) &&
+                    (!cseq || aligned_to(cseq, 16)) && aligned_to(out, 16) && (!hin || aligned_to(hin, 16)) &&
+                    (!cin || aligned_to(cin, 16)) && (!h0 || aligned_to(h0, 16)) && (!c0 || aligned_to(c0, 16)) &&
+                    (!c_last || aligned_to(c_last, 16)) && (!h_last || aligned_to(h_last, 16)) && aligned_to(workspace, 256),
                 CUSRL_B200_EALIGN, "lstm_seq_fwd: pointers must be 16-byte aligned (workspace: 256)");
   const size_t need = cusrl_b200_lstm_seq_workspace_bytes(T, Nb, H);
   CUSRL_REQUIRE(workspace_bytes >= need, CUSRL_B200_ESCRATCH, "lstm_seq_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -454,7 +465,8 @@ int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* W
   cudaError_t me = cudaMemsetAsync(workspace, 0, flag_bytes, s);
   CUSRL_REQUIRE(me == cudaSuccess, (int)me, "lstm_seq_fwd: cudaMemsetAsync: %s", cudaGetErrorString(me));
   p.xp = xp, p.ldxp = ldxp, p.b_hh = b_hh, p.h0 = h0, p.c0 = c0, p.done = done;
-  p.gates = gates, p.cseq = cseq, p.out = out, p.hin = hin, p.cin = cin, p.c_last = c_last, p.wstats = w_stats;
+  p.gates = gates, p.cseq = cseq, p.out = out, p.hin = hin, p.cin = cin, p.c_last = c_last, p.h_last = h_last, p.wstats = w_stats;
+  p.ld0 = ld0, p.ld_last = ld_last;
   p.T = (int)T, p.Nb = (int)Nb, p.H = (int)H, p.debug = g_lstm_debug;
   CUtensorMap tWh, tWl, tAh, tAl, tX;
   if (int e = encode_tmap_2d_f32(&tX, xp, (uint64_t)(4 * H), (uint64_t)(T * Nb), (uint64_t)ldxp, LS_HS, BM, TMAP_SW64)) return e;

@@ -134,6 +134,18 @@ def lstm_forward(x: Tensor, h0: Tensor, c0: Tensor, done: Tensor | None, lstm: n
     return _LstmFunction.apply(x, h0, c0, done, lstm.num_layers, *weights)
 
 
+def _expand_done(done: Tensor, T: int, n_rows: int, batch_shape) -> Tensor:
+    """``[T, n_rows]`` episode-end flags from ``[T, N, 1]`` (or already flat) flags."""
+    if done.numel() == T * n_rows:
+        return done.reshape(T, n_rows)
+    # batch dims the flags do not carry (SymmetricDataAugmentation: input [T, N, 1 + V, C], done [T, N, 1]): every variant of
+    # an environment shares its episode boundaries
+    d = done.squeeze(-1) if done.dim() >= 3 and done.shape[-1] == 1 else done
+    while d.dim() < 1 + len(batch_shape):
+        d = d.unsqueeze(-1)
+    return d.expand(T, *batch_shape).reshape(T, n_rows)
+
+
 @dataclass
 class RnnFactory:
     module_type: str
@@ -185,25 +197,51 @@ class Rnn(Module):
         for d in batch_shape:
             n_rows *= d
         x = input.reshape(T, n_rows, input.shape[-1])
+        if not torch.is_grad_enabled() and x.is_cuda and ops.lstm_seq_supported(H):
+            return self._forward_inference(input, x, memory, done, T, n_rows, batch_shape, sequential)
         # only a SEQUENCE input can carry a per-step memory; a single step with extra batch dims ([N, V, C]) must not be cut
         h0, c0 = self._initial(memory, input.shape[:-1] if (sequential and input.dim() >= 3) else None, n_rows, input.device)
-        if done is None:
-            d = None
-        elif done.numel() == T * n_rows:
-            d = done.reshape(T, n_rows)
-        else:
-            # batch dims the flags do not carry (SymmetricDataAugmentation: input [T, N, 1 + V, C], done [T, N, 1]): every
-            # variant of an environment shares its episode boundaries
-            d = done.squeeze(-1) if done.dim() >= 3 and done.shape[-1] == 1 else done
-            while d.dim() < 1 + len(batch_shape):
-                d = d.unsqueeze(-1)
-            d = d.expand(T, *batch_shape).reshape(T, n_rows)
+        d = None if done is None else _expand_done(done, T, n_rows, batch_shape)
         out, h_n, c_n = lstm_forward(x, h0, c0, d, self.rnn)
         out = out.reshape(*input.shape[:-1], H)
         if done is not None:
             return out, None  # like the reference without packing: no output memory for segmented sequences (rnn.py:288-296)
         to_flat = lambda m: m.transpose(0, 1).reshape(*batch_shape, L * H)  # "k n c -> n (k c)"  # noqa: E731
         return out, {"hidden": to_flat(h_n), "cell": to_flat(c_n)}
+
+    def _forward_inference(self, input: Tensor, x: Tensor, memory, done, T: int, n_rows: int, batch_shape, sequential: bool):
+        """Rollout / statistics / bootstrap-value calls (no autograd): per layer one projection GEMM and ONE sequence-kernel
+        launch that saves nothing for a backward pass, reads the layer's slice of the flat ``[N, layers * H]`` memory in
+        place and writes the next memory's slice in place -- no state transposes, no per-step tensors."""
+        L, H = self.rnn.num_layers, self.rnn.hidden_size
+        dev = x.device
+        hidden_in = cell_in = None
+        if memory is not None:
+            hidden_in, cell_in = memory["hidden"], memory["cell"]
+            if sequential and input.dim() >= 3 and tuple(hidden_in.shape[:-1]) == tuple(input.shape[:-1]):
+                hidden_in, cell_in = hidden_in[0], cell_in[0]   # sequence-aligned memory: step 0 (recurrent.py:202-212)
+            hidden_in, cell_in = hidden_in.reshape(n_rows, L * H), cell_in.reshape(n_rows, L * H)
+        d = None
+        if done is not None:
+            d = _expand_done(done, T, n_rows, batch_shape)
+        new_hidden = torch.empty(n_rows, L * H, device=dev)
+        new_cell = torch.empty(n_rows, L * H, device=dev)
+        precision = ops.tf32_passes()
+        layer_in = x
+        for layer in range(L):
+            w_ih, w_hh = getattr(self.rnn, f"weight_ih_l{layer}"), getattr(self.rnn, f"weight_hh_l{layer}")
+            b_ih, b_hh = getattr(self.rnn, f"bias_ih_l{layer}"), getattr(self.rnn, f"bias_hh_l{layer}")
+            inp2 = ops_rows(layer_in.reshape(T * n_rows, layer_in.shape[-1]))
+            xp = ops.tc_linear_fwd(inp2, ops.prepared_weight(w_ih), b_ih, 4 * H, 0, precision)
+            out = torch.empty(T, n_rows, H, device=dev)
+            sl = slice(layer * H, (layer + 1) * H)
+            ops.lstm_seq_fwd(xp, ops.prepared_weight_f16(w_hh, b_hh), b_hh, None if hidden_in is None else hidden_in[:, sl],
+                             None if cell_in is None else cell_in[:, sl], d, None, out, None, new_cell[:, sl], new_hidden[:, sl])
+            layer_in = out
+        out = layer_in.reshape(*input.shape[:-1], H)
+        if done is not None:
+            return out, None
+        return out, {"hidden": new_hidden.reshape(*batch_shape, L * H), "cell": new_cell.reshape(*batch_shape, L * H)}
 
     def step_memory(self, input: Tensor, memory=None, sequential: bool = True, **kwargs):
         return self(input, memory, sequential=sequential)[1]

@@ -1029,14 +1029,15 @@ def lstm_seq_private(T: int, Nb: int, H: int, device) -> tuple[torch.Tensor, tor
 
 
 def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torch.Tensor | None, c0: torch.Tensor | None,
-                 done: torch.Tensor | None, private: tuple[torch.Tensor, torch.Tensor, torch.Tensor], out: torch.Tensor,
-                 hin: torch.Tensor | None, c_last: torch.Tensor | None) -> None:
+                 done: torch.Tensor | None, private: tuple[torch.Tensor, torch.Tensor, torch.Tensor] | None, out: torch.Tensor,
+                 hin: torch.Tensor | None, c_last: torch.Tensor | None, h_last: torch.Tensor | None = None) -> None:
     """All T steps of one LSTM layer in one launch (cusrl_b200_lstm_seq_fwd_f32).  xp [T*Nb, 4H] = input projection incl.
     b_ih; `wp` = prepared_weight_f16(W_hh); writes out = h_t and hin = the hidden state entering each step ([T, Nb, H],
-    row-major), c_last = c_{T-1} [Nb, H], and the `private` buffers of lstm_seq_private for the backward kernel; done [T, Nb]
-    resets the carried state after the steps where it is set."""
+    row-major), h_last / c_last = h_{T-1} / c_{T-1}, and the `private` buffers of lstm_seq_private for the backward kernel
+    (None: inference, nothing is saved); done [T, Nb] resets the carried state after the steps where it is set.  h0 / c0 and
+    h_last / c_last may be column slices of a flat [N, layers * H] memory (unit inner stride, any row pitch)."""
     T, Nb, H = out.shape
-    gates, cseq, cin = private
+    gates, cseq, cin = private if private is not None else (None, None, None)
     xpp, ldxp = _rows(xp, "xp")
     lib = _lib.load()
     need = lib.cusrl_b200_lstm_seq_workspace_bytes(T, Nb, H)
@@ -1047,14 +1048,32 @@ def lstm_seq_fwd(xp: torch.Tensor, wp: dict, b_hh: torch.Tensor | None, h0: torc
     if done is not None and (done.numel() != T * Nb or not done.is_contiguous()):
         raise ValueError("lstm_seq_fwd: 'done' must be a contiguous [T, Nb] tensor")
     nbp = (Nb + 127) // 128 * 128
-    if gates.numel() != T * nbp * 4 * H or cseq.numel() != T * nbp * H or cin.numel() != T * nbp * H:
+    if private is not None and (gates.numel() != T * nbp * 4 * H or cseq.numel() != T * nbp * H or cin.numel() != T * nbp * H):
         raise ValueError("lstm_seq_fwd: private buffers must come from lstm_seq_private(T, Nb, H)")
+
+    def pitched(a, b, name):
+        """(ptr a, ptr b, common row pitch) of two optional [Nb, H] views with unit inner stride."""
+        ld = None
+        ptrs = []
+        for t in (a, b):
+            if t is None:
+                ptrs.append(None)
+                continue
+            tp, tl = _rows(t, name)
+            if t.shape != (Nb, H) or (ld is not None and tl != ld):
+                raise ValueError(f"lstm_seq_fwd: '{name}' tensors must be [{Nb}, {H}] views with one common row pitch")
+            ld = tl
+            ptrs.append(tp)
+        return ptrs[0], ptrs[1], (ld or H)
+
+    h0p, c0p, ld0 = pitched(h0, c0, "h0/c0")
+    hlp, clp, ldl = pitched(h_last, c_last, "h_last/c_last")
     code = lib.cusrl_b200_lstm_seq_fwd_f32(
         xpp, ldxp, w[0].data_ptr(), w[1].data_ptr(), w.shape[2], wp["stats"].data_ptr(),
-        None if b_hh is None else _ptr(b_hh.detach(), torch.float32, "b_hh"), _ptr(h0, torch.float32, "h0"),
-        _ptr(c0, torch.float32, "c0"), None if done is None else _flag_ptr(done, "done"), _ptr(gates, torch.float32, "gates"),
+        None if b_hh is None else _ptr(b_hh.detach(), torch.float32, "b_hh"), h0p, c0p,
+        None if done is None else _flag_ptr(done, "done"), ld0, _ptr(gates, torch.float32, "gates"),
         _ptr(cseq, torch.float32, "cseq"), _ptr(out, torch.float32, "out"), _ptr(hin, torch.float32, "hin"),
-        _ptr(cin, torch.float32, "cin"), _ptr(c_last, torch.float32, "c_last"), T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
+        _ptr(cin, torch.float32, "cin"), hlp, clp, ldl, T, Nb, H, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(code, "lstm_seq_fwd", launches=1)
 
 

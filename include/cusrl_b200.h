@@ -412,7 +412,9 @@ int cusrl_b200_mirror_rows_f32(const float* x, int64_t ldx, int64_t rows, int64_
  *   cusrl_b200_weight_prep_f16 ([4H, H], pitch ldw halves);  b_hh [4H] nullable;  h0 / c0 [Nb, H] nullable (zeros);
  *   done [T, Nb] nullable: the state handed to step t+1 is zeroed where done[t] (in-line episode reset).
  *   Writes out = h_t [T,Nb,H] and (nullable) hin [T,Nb,H] = the hidden state that ENTERED each step, both row-major (they
- *   feed dense-layer calls), c_last [Nb,H] = c_{T-1} (nullable), and the tensors only cusrl_b200_lstm_seq_bwd_f32 reads --
+ *   feed dense-layer calls), h_last / c_last = h_{T-1} / c_{T-1} (nullable, row pitch ld_last; h0 / c0 have row pitch ld0: a
+ *   layer's slice of the reference's flat [N, layers * H] memory is read and written in place), and -- given together for
+ *   training, all null for inference -- the tensors only cusrl_b200_lstm_seq_bwd_f32 reads --
  *   gates (activated i,f,g,o), cseq = c_t, cin = the cell state that entered each step -- in a PRIVATE tiled layout
  *   [T][ceil(Nb/128)][H/4][(4 gates)][128 rows][4 floats]: allocate T * ceil(Nb/128)*128 * 4H (gates) / * H (cseq, cin) floats.
  *   H must be a multiple of 64, at most 256 (cusrl_b200_lstm_seq_supported); workspace: cusrl_b200_lstm_seq_workspace_bytes
@@ -424,8 +426,9 @@ int cusrl_b200_lstm_seq_set_debug(int bits);
 size_t cusrl_b200_lstm_seq_workspace_bytes(int64_t T, int64_t Nb, int64_t H);
 int cusrl_b200_lstm_seq_fwd_f32(const float* xp, int64_t ldxp, const uint16_t* Whi, const uint16_t* Wlo, int64_t ldw,
                                 const float* w_stats, const float* b_hh, const float* h0, const float* c0, const uint8_t* done,
-                                float* gates, float* cseq, float* out, float* hin, float* cin, float* c_last, int64_t T, int64_t Nb,
-                                int64_t H, void* workspace, size_t workspace_bytes, void* stream);
+                                int64_t ld0, float* gates, float* cseq, float* out, float* hin, float* cin, float* h_last, float* c_last,
+                                int64_t ld_last, int64_t T, int64_t Nb, int64_t H, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* Backward through time of the same layer in one launch: dgates [T,Nb,4H] = pre-activation gate gradients of every step,
  * from dout [T*Nb, H] (pitch lddo; gradient w.r.t. h_t from above) and the forward's saved gates / cseq / cin; the recurrent

@@ -154,6 +154,18 @@ def test_sequence_resident_kernel_equals_per_step_path(C, monkeypatch, T, Nb, I,
         (out * gout.reshape(out.shape)).sum().backward()
         results[mode] = (out.detach().clone(), out2.detach().clone(), mem2["hidden"].clone(), mem2["cell"].clone(),
                          {k: p.grad.clone() for k, p in rnn.named_parameters()})
+        if mode:
+            # the no-autograd path (rollout, statistics, bootstrap values): same kernel, nothing saved, the flat memory read
+            # and written in place -> identical numbers
+            with torch.no_grad():
+                if T > 1:
+                    out_i, mem_i = rnn(x, memory=memory, done=done)
+                    assert mem_i is None and torch.equal(out_i, out.detach())
+                    out2_i, mem2_i = rnn(x, memory=memory)
+                else:
+                    out2_i, mem2_i = rnn(x[0], memory=memory, sequential=False)
+            assert torch.equal(out2_i, out2.detach())
+            assert torch.equal(mem2_i["hidden"], mem2["hidden"]) and torch.equal(mem2_i["cell"], mem2["cell"])
     a, b = results[True], results[False]
     for i in range(4):
         assert torch.allclose(a[i], b[i], rtol=1e-5, atol=2e-6), (i, (a[i] - b[i]).abs().max().item())

@@ -57,6 +57,7 @@ for s in "$@"; do
     lstm_bench) step lstm_bench 200 python tools/lstm_bench.py --debug 3 ;;
     hostprof_lstm) step hostprof_lstm 200 python tools/host_profile.py 4096 lstm ;;
     gemm_tests) step gemm_tests 600 python -u -m pytest tests/test_gemm_f16x3_gpu.py tests/test_gemm_gpu.py tests/test_agent_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 200 -rf -x ;;
+    ncu_lstm)   step ncu_lstm 280 ncu --set full --clock-control none --import-source on -k regex:lstm_seq_ --launch-skip 6 --launch-count 2 -o "$out/lstm_seq" -f python tools/lstm_bench.py --reps 1 --only-config3 ;;
     *) echo "unknown step $s" ;;
   esac
 done
