@@ -106,6 +106,44 @@ __global__ void __launch_bounds__(256) sample_logp_kernel(const float* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// step() of a recurrent agent: `memory[done] = 0` for up to four [N, W] memory tensors (Module.reset_memory,
+// nn/module/module.py + hook/on_policy/value.py:56 for the critic's) and, in the same pass, the copies of the reset memory
+// the rollout buffer needs (actor_memory / critic_memory of the NEXT step, next_critic_memory of this one): up to two extra
+// destinations per tensor.  Replaces four masked fills and up to six copies per environment step.
+// ------------------------------------------------------------------------------------------------
+struct MemoryResetParams {
+  float* mem[4];
+  float* dst_a[4];
+  float* dst_b[4];
+  const uint8_t* done;
+  int64_t N;
+  int width, count;   // W (a multiple of 4), number of tensors
+};
+
+__global__ void __launch_bounds__(256) memory_reset_store_kernel(const MemoryResetParams p) {
+  const int w4 = p.width >> 2;
+  const int64_t total = p.N * w4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / w4;
+    const bool reset = p.done[n] != 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k >= p.count) break;
+      float4* src = reinterpret_cast<float4*>(p.mem[k]) + i;
+      float4 v = *src;
+      if (reset) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        *src = v;
+      }
+      if (p.dst_a[k]) reinterpret_cast<float4*>(p.dst_a[k])[i] = v;
+      if (p.dst_b[k]) reinterpret_cast<float4*>(p.dst_b[k])[i] = v;
+    }
+  }
+}
+
 }  // namespace cusrl_b200
 
 using namespace cusrl_b200;
@@ -170,6 +208,28 @@ int cusrl_b200_sample_logp_f32(const float* mean, const float* sigma, const floa
   sample_logp_kernel<64><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mean, sigma, eps, N, (int)A, deterministic, std_out,
                                                                              action_out, logp_out);
   return check_launch("sample_logp_kernel");
+}
+
+int cusrl_b200_memory_reset_store_f32(float* const* mem, float* const* dst_a, float* const* dst_b, int64_t count, const uint8_t* done,
+                                      int64_t N, int64_t width, void* stream) {
+  CUSRL_REQUIRE(mem && done && count >= 1 && count <= 4, CUSRL_B200_EINVAL, "memory_reset_store: 1..4 tensors");
+  CUSRL_REQUIRE(N > 0 && width > 0 && (width % 4) == 0 && width < (1 << 20), CUSRL_B200_EINVAL,
+                "memory_reset_store: width must be a positive multiple of 4");
+  MemoryResetParams p{};
+  for (int k = 0; k < (int)count; ++k) {
+    p.mem[k] = mem[k];
+    p.dst_a[k] = dst_a ? dst_a[k] : nullptr;
+    p.dst_b[k] = dst_b ? dst_b[k] : nullptr;
+    CUSRL_REQUIRE(p.mem[k] && aligned_to(p.mem[k], 16) && (!p.dst_a[k] || aligned_to(p.dst_a[k], 16)) &&
+                      (!p.dst_b[k] || aligned_to(p.dst_b[k], 16)),
+                  CUSRL_B200_EALIGN, "memory_reset_store: tensors must be dense, 16-byte aligned");
+  }
+  p.done = done, p.N = N, p.width = (int)width, p.count = (int)count;
+  int64_t blocks = (N * (width / 4) + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  memory_reset_store_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("memory_reset_store_kernel");
 }
 
 }  // extern "C"

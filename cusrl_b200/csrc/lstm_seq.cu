@@ -534,6 +534,7 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) {
   asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void lb_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * LB_EPI_WARPS) : "memory"); }
 
 __global__ void __launch_bounds__(LB_THREADS, 1)
@@ -629,21 +630,17 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
       for (int t = T - 1; t >= 0; --t) {
         float dh[8], g[4][8], cv[8], cpv[8];
         float m = 1.f;
+        const int64_t qb = ((int64_t)t * p.tiles + tile) * (H / 4) + quad0;
         {
-          // tensors written by the forward kernel in its private layout: the 32 rows of a warp are contiguous
-          const int64_t qb = ((int64_t)t * p.tiles + tile) * (H / 4) + quad0;
+          // the forward kernel's tensors of this step (private layout: the 32 rows of a warp are contiguous) are pulled into
+          // L2 now and LOADED after the partial products: holding them in registers across the hand-over wait spilled
 #pragma unroll
           for (int hq = 0; hq < 2; ++hq) {
             const float* gp = p.gates + (((qb + hq) * 4) * BM + rloc) * 4;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(gp + q * BM * 4));
-              g[q][4 * hq] = a.x, g[q][4 * hq + 1] = a.y, g[q][4 * hq + 2] = a.z, g[q][4 * hq + 3] = a.w;
-            }
-            const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cseq + ((qb + hq) * BM + rloc) * 4));
-            cv[4 * hq] = cc.x, cv[4 * hq + 1] = cc.y, cv[4 * hq + 2] = cc.z, cv[4 * hq + 3] = cc.w;
-            const float4 ce = __ldg(reinterpret_cast<const float4*>(p.cin + ((qb + hq) * BM + rloc) * 4));
-            cpv[4 * hq] = ce.x, cpv[4 * hq + 1] = ce.y, cpv[4 * hq + 2] = ce.z, cpv[4 * hq + 3] = ce.w;
+            for (int q = 0; q < 4; ++q) prefetch_l2(gp + q * BM * 4);
+            prefetch_l2(p.cseq + ((qb + hq) * BM + rloc) * 4);
+            prefetch_l2(p.cin + ((qb + hq) * BM + rloc) * 4);
           }
         }
 #pragma unroll
@@ -666,9 +663,22 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
           {
             // [parity][tile][source slice][H/4 quads][128 rows][4]: a warp reads 512 contiguous bytes per quad
             const float* base = p.part + ((((int64_t)((t + 1) & 1) * p.tiles + tile) * p.slices) * (H / 4) + quad0) * BM * 4 + rloc * 4;
-            for (int src = 0; src < p.slices; ++src) {   // fixed order: deterministic
-              const float4 a = ld_cg4(base + (int64_t)src * H * BM), b = ld_cg4(base + (int64_t)src * H * BM + BM * 4);
-              acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w, acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
+            // fixed order: deterministic.  Four sources per round trip: a rolled loop issued one pair of loads per L2 latency
+            // (ncu: the adds of this loop were the top long-scoreboard stall after the counter poll)
+            for (int s0 = 0; s0 < p.slices; s0 += 4) {
+              float4 a[4], b[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (s0 + u < p.slices) {
+                  a[u] = ld_cg4(base + (int64_t)(s0 + u) * H * BM);
+                  b[u] = ld_cg4(base + (int64_t)(s0 + u) * H * BM + BM * 4);
+                }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (s0 + u < p.slices) {
+                  acc[0] += a[u].x, acc[1] += a[u].y, acc[2] += a[u].z, acc[3] += a[u].w;
+                  acc[4] += b[u].x, acc[5] += b[u].y, acc[6] += b[u].z, acc[7] += b[u].w;
+                }
             }
           }
 #pragma unroll
@@ -676,6 +686,21 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_cons
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+        }
+        {
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const float* gp = p.gates + (((qb + hq) * 4) * BM + rloc) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(gp + q * BM * 4));
+              g[q][4 * hq] = a.x, g[q][4 * hq + 1] = a.y, g[q][4 * hq + 2] = a.z, g[q][4 * hq + 3] = a.w;
+            }
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cseq + ((qb + hq) * BM + rloc) * 4));
+            cv[4 * hq] = cc.x, cv[4 * hq + 1] = cc.y, cv[4 * hq + 2] = cc.z, cv[4 * hq + 3] = cc.w;
+            const float4 ce = __ldg(reinterpret_cast<const float4*>(p.cin + ((qb + hq) * BM + rloc) * 4));
+            cpv[4 * hq] = ce.x, cpv[4 * hq + 1] = ce.y, cpv[4 * hq + 2] = ce.z, cpv[4 * hq + 3] = ce.w;
+          }
         }
         float dg[4][8];
         float amax = 0.f;

@@ -987,6 +987,31 @@ def mse_loss(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True) -
     return loss, grad
 
 
+def memory_reset_store(memories: list[torch.Tensor], done: torch.Tensor, dst_a: list | None = None, dst_b: list | None = None) -> None:
+    """``memory[done] = 0`` in place for up to four dense [N, W] tensors, each result also copied to ``dst_a[k]`` / ``dst_b[k]``
+    (entries may be None) in the same launch (cusrl_b200_memory_reset_store_f32)."""
+    count = len(memories)
+    N, W = memories[0].shape
+    arr = ctypes.c_void_p * count
+
+    def pointers(items):
+        if items is None:
+            return None
+        out = []
+        for m in items:
+            if m is None:
+                out.append(None)
+                continue
+            if m.shape != (N, W):
+                raise ValueError("memory_reset_store: all tensors must share one [N, W] shape")
+            out.append(_ptr(m, torch.float32, "memory"))
+        return arr(*out)
+
+    code = _lib.load().cusrl_b200_memory_reset_store_f32(pointers(memories), pointers(dst_a), pointers(dst_b), count,
+                                                         _flag_ptr(done, "done"), N, W, _stream())
+    _lib.check(code, "memory_reset_store")
+
+
 # ---------------------------------------------------------------------------------------------- K7
 def lstm_cell_fwd(xp: torch.Tensor, hp: torch.Tensor, c_in: torch.Tensor, done: torch.Tensor | None, gates: torch.Tensor,
                   c_out: torch.Tensor, h_out: torch.Tensor, c_next: torch.Tensor | None, h_next: torch.Tensor | None) -> None:

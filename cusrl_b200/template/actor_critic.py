@@ -204,9 +204,9 @@ class ActorCritic:
         """actor_critic.py:227-253; output array type follows the input (agent.py:376-391)."""
         if self.fused_rollout:
             if self._fused_rollout is None:
-                from .rollout import FusedRollout
+                from .rollout import make_fused_rollout
 
-                self._fused_rollout = FusedRollout(self)
+                self._fused_rollout = make_fused_rollout(self)
             action = self._fused_rollout.act(observation, state)
             if action is not None:
                 return action

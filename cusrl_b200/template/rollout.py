@@ -31,7 +31,7 @@ from ..nn import functional as F
 from ..nn import modules as M
 from .hook import Hook
 
-__all__ = ["FusedRollout"]
+__all__ = ["FusedRecurrentRollout", "FusedRollout", "make_fused_rollout"]
 
 _ROLLOUT_CALLBACKS = ("pre_act", "post_act", "post_step", "should_update")
 
@@ -231,3 +231,167 @@ class FusedRollout:
         agent.buffer.advance()
         self.fast_steps += 1
         return True
+
+
+class FusedRecurrentRollout(FusedRollout):
+    """The same idea for the recurrent PPO agent (LSTM actor and critic, ``RecurrentPpoAgentFactory``): a rollout step of
+    the generic flow costs ~0.9 ms of Python (some 80 small torch operations: memory bookkeeping, distribution arithmetic,
+    ~20 leaf copies of ``Buffer.push``) against ~0.25 ms of GPU work, so the rollout of BASELINE.json's config 3 was bound by
+    the host.  Here a step is
+
+      act :  observation -> padded slot;  per network: per layer one projection GEMM + one sequence-kernel launch (T = 1,
+             nothing saved, the layer's slice of the flat memory read and written in place) -> head -> ``action_dist.mean`` /
+             ``value`` slot;  ONE noise draw + ONE kernel for std / action / log-prob;
+      step:  ONE kernel for next_observation / reward / flags / done, and ONE kernel that zeroes the memories of finished
+             episodes in place (``reset_memory``) while writing the copies the buffer stores: ``actor_memory`` /
+             ``critic_memory`` of the NEXT step and ``next_critic_memory`` of this one.
+
+    Applies when actor and critic are the plain ``Actor`` / ``Value`` over ``Rnn`` backbones whose hidden size the sequence
+    kernels cover, with a ``NormalDist`` head, once both memories exist and every leaf is allocated (i.e. from the third
+    step of a run on); everything else takes the generic path, call by call."""
+
+    def _supported(self) -> bool:
+        agent = self.agent
+        if agent.device.type != "cuda" and self.REQUIRE_CUDA:
+            return False
+        actor, critic = agent.actor, agent.critic
+        if not (type(actor) is M.Actor and type(critic) is M.Value):
+            return False
+        from ..nn.recurrent import Rnn
+
+        if not (type(actor.backbone) is Rnn and type(critic.backbone) is Rnn):
+            return False
+        if not isinstance(actor.distribution, M.NormalDist) or actor.distribution.mean_head.weight.shape[0] > 64:
+            return False
+        for net, head in ((actor, actor.distribution.mean_head), (critic, critic.value_head)):
+            H = net.backbone.rnn.hidden_size
+            if not ops.lstm_seq_supported(H):
+                return False
+            if not (F.simt_head_supported(*head.weight.shape) or head.weight.shape[0] % 4 == 0):
+                return False
+        from ..hook.on_policy import ValueComputation
+
+        self._value_hook = None
+        for hook in agent.hook:
+            if isinstance(hook, ValueComputation):
+                self._value_hook = hook
+                continue
+            if any(_overrides(hook, name) for name in _ROLLOUT_CALLBACKS):
+                return False
+        return self._value_hook is not None
+
+    _MEMORY_LEAVES = ("actor_memory.hidden", "actor_memory.cell", "critic_memory.hidden", "critic_memory.cell",
+                      "next_critic_memory.hidden", "next_critic_memory.cell")
+
+    def _ready(self) -> bool:
+        agent = self.agent
+        if not self.enabled or agent.inference_mode:
+            return False
+        if agent.actor_memory is None or self._value_hook._critic_memory is None:
+            return False
+        storage = agent.buffer.storage
+        need = ["observation", "action_dist.mean", "action_dist.std", "action", "action_logp", "value", "next_observation",
+                "reward", "terminated", "truncated", "done", *self._MEMORY_LEAVES]
+        if agent.has_state:
+            need += ["state", "next_state"]
+        if not all(k in storage for k in need):
+            return False
+        extra = set(storage) - set(need) - {"next_value", "advantage", "return"}
+        return not extra
+
+    @staticmethod
+    def _head(latent: torch.Tensor, head: torch.nn.Linear, out: torch.Tensor) -> torch.Tensor:
+        if F.simt_head_supported(*head.weight.shape):
+            return ops.head_fwd(latent, head.weight, head.bias, out=out)
+        return ops.tc_linear_fwd(latent, ops.prepared_weight(head.weight), head.bias, head.weight.shape[0], 0, ops.tf32_passes(),
+                                 out=out)
+
+    def act(self, observation, state):
+        agent = self.agent
+        self._acted_fast = False
+        if not self._ready() or not self._input_ok(observation, agent.observation_dim):
+            return None
+        if agent.has_state != (state is not None) or (state is not None and not self._input_ok(state, agent.state_dim)):
+            return None
+        hook = self._value_hook
+        actor_mem, critic_mem = agent.actor_memory, hook._critic_memory
+        if not all(isinstance(m, dict) and m["hidden"].dim() == 2 and m["hidden"].is_contiguous() and m["cell"].is_contiguous()
+                   for m in (actor_mem, critic_mem)):
+            return None
+        t = agent.buffer.cursor
+        tr = agent.transition
+        tr.clear()
+        obs_slot = self._fill_wide("observation", t, observation, self._prev_next_obs, "next_observation")
+        tr["observation"] = obs_slot
+        critic_in = obs_slot
+        if state is not None:
+            critic_in = self._fill_wide("state", t, state, self._prev_next_state, "next_state")
+            tr["state"] = critic_in
+        if self._slots_hold_memory != t:
+            # the memories entering this step are not in their slots yet (first fused step of a rollout: the last step of the
+            # previous rollout must not overwrite slot 0 before the update has read it)
+            for name, mem in (("actor_memory", actor_mem), ("critic_memory", critic_mem)):
+                for leaf in ("hidden", "cell"):
+                    self._slot(f"{name}.{leaf}", t).copy_(mem[leaf])
+        tr["actor_memory"] = {leaf: self._slot(f"actor_memory.{leaf}", t) for leaf in ("hidden", "cell")}
+        tr["critic_memory"] = {leaf: self._slot(f"critic_memory.{leaf}", t) for leaf in ("hidden", "cell")}
+        # actor
+        latent, next_actor_mem = agent.actor.backbone(obs_slot, actor_mem, sequential=False)
+        agent.actor.intermediate_repr["backbone.output"] = latent
+        mean = self._head(latent, agent.actor.distribution.mean_head, self._slot("action_dist.mean", t))
+        std, action, logp = self._slot("action_dist.std", t), self._slot("action", t), self._slot("action_logp", t)
+        eps = None if agent.deterministic else M.standard_normal_like(mean)
+        ops.sample_logp(mean, agent.actor.distribution.std.param.detach(), eps, std, action, logp, agent.deterministic)
+        tr["action_dist"] = {"mean": mean, "std": std}
+        tr["action"], tr["action_logp"] = action, logp
+        # critic (ValueComputation.post_act, value.py:42-54)
+        latent_c, next_critic_mem = agent.critic.backbone(critic_in, critic_mem, sequential=False)
+        agent.critic.intermediate_repr["backbone.output"] = latent_c
+        tr["value"] = self._head(latent_c, agent.critic.value_head, self._slot("value", t))
+        tr["next_critic_memory"] = next_critic_mem
+        agent.actor_memory, hook._critic_memory = next_actor_mem, next_critic_mem
+        self._acted_fast = True
+        if observation.is_cuda:
+            return action.clone()
+        return action.to(device=observation.device)
+
+    _slots_hold_memory = -1   # buffer step whose actor_memory / critic_memory slots already hold the memories entering it
+
+    def step(self, next_observation, reward, terminated, truncated, next_state, kwargs) -> bool:
+        agent = self.agent
+        acted_fast = self._acted_fast
+        t = agent.buffer.cursor
+        if not super().step(next_observation, reward, terminated, truncated, next_state, kwargs):
+            if acted_fast:
+                # the generic step finishes this transition (its push copies every leaf, its hooks reset the memories): the
+                # slots of the next step are not prepared
+                self._slots_hold_memory = -1
+            return False
+        # super().step stored next_observation / reward / flags / done and advanced the cursor
+        T = agent.buffer.capacity
+        hook = self._value_hook
+        actor_mem, critic_mem = agent.actor_memory, hook._critic_memory
+        done = agent.buffer.storage["done"][t]
+        nxt = t + 1
+        slot = (lambda key: agent.buffer.storage[key][nxt]) if nxt < T else (lambda key: None)
+        mems = [actor_mem["hidden"], actor_mem["cell"], critic_mem["hidden"], critic_mem["cell"]]
+        dst_a = [slot("actor_memory.hidden"), slot("actor_memory.cell"), slot("critic_memory.hidden"), slot("critic_memory.cell")]
+        dst_b = [None, None, agent.buffer.storage["next_critic_memory.hidden"][t], agent.buffer.storage["next_critic_memory.cell"][t]]
+        if actor_mem["hidden"].shape == critic_mem["hidden"].shape:
+            ops.memory_reset_store(mems, done, dst_a=dst_a, dst_b=dst_b)
+        else:   # networks of different sizes: one launch per network
+            ops.memory_reset_store(mems[:2], done, dst_a=dst_a[:2], dst_b=dst_b[:2])
+            ops.memory_reset_store(mems[2:], done, dst_a=dst_a[2:], dst_b=dst_b[2:])
+        self._slots_hold_memory = nxt if nxt < T else -1
+        agent.transition["next_critic_memory"] = {leaf: agent.buffer.storage[f"next_critic_memory.{leaf}"][t] for leaf in ("hidden", "cell")}
+        return True
+
+
+def make_fused_rollout(agent) -> FusedRollout:
+    """The fused rollout implementation that applies to `agent` (feed-forward or recurrent); a disabled FusedRollout (every
+    call takes the generic path) when neither does."""
+    fused = FusedRollout(agent)
+    if fused.enabled:
+        return fused
+    recurrent = FusedRecurrentRollout(agent)
+    return recurrent if recurrent.enabled else fused

@@ -314,6 +314,12 @@ int cusrl_b200_rollout_store_step_f32(const float* next_obs, int64_t ld_next_obs
                                       void* stream);
 int cusrl_b200_sample_logp_f32(const float* mean, const float* sigma, const float* eps, int64_t N, int64_t A,
                                int deterministic, float* std_out, float* action_out, float* logp_out, void* stream);
+/* step() of a recurrent agent (Module.reset_memory + the rollout buffer's copies of the recurrent memories,
+ * nn/module/module.py, hook/on_policy/value.py:42-56, template/actor_critic.py:283-289): for `count` (1..4) dense fp32
+ * [N, width] memory tensors, rows where done[n] are zeroed IN PLACE and the resulting rows are also written to dst_a[k] /
+ * dst_b[k] (either array or any entry may be null).  Host arrays of device pointers; width a multiple of 4. */
+int cusrl_b200_memory_reset_store_f32(float* const* mem, float* const* dst_a, float* const* dst_b, int64_t count, const uint8_t* done,
+                                      int64_t N, int64_t width, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K6, precision 2 ("f16x3") -- the same dense layers (nn.Linear + activation, nn/module/mlp.py:77-90, and their autograd)

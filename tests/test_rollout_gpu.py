@@ -134,3 +134,68 @@ def test_deterministic_and_fallbacks(C, monkeypatch):
     other = factory(C.EnvironmentSpec(N, OBS, ACT, autoreset=True, final_state_is_missing=True))
     acts = _rollout(other, data, monkeypatch, "cuda")
     assert other._fused_rollout.fast_steps == 0 and float(torch.stack(acts).abs().max()) <= 1.0
+
+
+def test_fused_recurrent_rollout_matches_generic(C, monkeypatch):
+    """FusedRecurrentRollout (LSTM actor and critic): same buffer contents -- including the six recurrent-memory leaves with
+    their in-place episode resets -- same returned actions and the same update as the generic act / step flow."""
+    Tn, Nn = 8, 384
+
+    def agent_of(fused: bool):
+        torch.manual_seed(3)
+        spec = C.EnvironmentSpec(Nn, OBS, ACT, autoreset=True, final_state_is_missing=True)
+        agent = C.RecurrentPpoAgentFactory(num_steps_per_update=Tn, actor_hidden_size=256, critic_hidden_size=128, actor_num_layers=2,
+                                           critic_num_layers=1, sampler_mini_batches=2, sampler_epochs=2, device=DEV)(spec)
+        agent.fused_rollout = fused
+        return agent
+
+    def stream(seed):
+        g = torch.Generator().manual_seed(seed)
+        return {"obs": torch.randn(Tn + 1, Nn, OBS, generator=g).to(DEV), "reward": torch.randn(Tn, Nn, 1, generator=g).to(DEV),
+                "terminated": (torch.rand(Tn, Nn, 1, generator=g) < 0.1).to(DEV),
+                "truncated": (torch.rand(Tn, Nn, 1, generator=g) < 0.05).to(DEV), "noise": torch.randn(Tn, Nn, ACT, generator=g).to(DEV)}
+
+    import cusrl_b200.nn.modules as M
+
+    def rollout(agent, data):
+        step = {"t": 0}
+        monkeypatch.setattr(M, "standard_normal_like", lambda mean: data["noise"][step["t"]].reshape(mean.shape).clone())
+        actions = []
+        for t in range(Tn):
+            step["t"] = t
+            actions.append(agent.act(data["obs"][t]).clone())
+            ready = agent.step(data["obs"][t + 1], data["reward"][t], data["terminated"][t], data["truncated"][t])
+        assert ready
+        return torch.stack(actions)
+
+    generic, fused = agent_of(False), agent_of(True)
+    for r, seed in enumerate((11, 12, 13)):   # three rollouts: memories carry over, slots are overwritten in place
+        data = stream(seed)
+        a_g, a_f = rollout(generic, data), rollout(fused, data)
+        # bit-identical until the first update; afterwards to fp32 rounding (the update itself is not bit-reproducible from
+        # run to run: the gradient norm is an atomic fp64 sum, so the clip coefficient can differ in its last bit)
+        same = torch.equal if r < 2 else (lambda x, y: torch.allclose(x.float(), y.float(), rtol=1e-4, atol=1e-5))
+        assert same(a_g, a_f), r
+        assert set(generic.buffer.storage) == set(fused.buffer.storage)
+        for key in generic.buffer.storage:
+            x, y = generic.buffer.storage[key], fused.buffer.storage[key]
+            if key == "action_logp":
+                assert torch.allclose(x, y, rtol=1e-5, atol=1e-5), (r, key)
+            else:
+                assert same(x, y), (r, key, (x.float() - y.float()).abs().max().item())
+        for mem_g, mem_f in ((generic.actor_memory, fused.actor_memory),
+                             (generic.hook["value_computation"]._critic_memory, fused.hook["value_computation"]._critic_memory)):
+            assert same(mem_g["hidden"], mem_f["hidden"]) and same(mem_g["cell"], mem_f["cell"])
+        if r == 0:
+            continue   # the second rollout overwrites the buffer in place before any update
+        torch.manual_seed(20 + r)
+        mg = generic.update()
+        torch.manual_seed(20 + r)
+        mf = fused.update()
+        for k in mg:
+            assert mf[k] == pytest.approx(mg[k], rel=1e-3, abs=1e-5), (r, k)
+    from cusrl_b200.template.rollout import FusedRecurrentRollout
+
+    assert isinstance(fused._fused_rollout, FusedRecurrentRollout)
+    assert fused._fused_rollout.fast_steps == 3 * Tn - 2   # all but the two allocating steps of the first rollout
+    assert generic._fused_rollout is None

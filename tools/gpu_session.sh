@@ -57,7 +57,8 @@ for s in "$@"; do
     lstm_bench) step lstm_bench 200 python tools/lstm_bench.py --debug 3 ;;
     hostprof_lstm) step hostprof_lstm 200 python tools/host_profile.py 4096 lstm ;;
     gemm_tests) step gemm_tests 600 python -u -m pytest tests/test_gemm_f16x3_gpu.py tests/test_gemm_gpu.py tests/test_agent_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 200 -rf -x ;;
-    ncu_lstm)   step ncu_lstm 280 ncu --set full --clock-control none --import-source on -k regex:lstm_seq_ --launch-skip 6 --launch-count 2 -o "$out/lstm_seq" -f python tools/lstm_bench.py --reps 1 --only-config3 ;;
+    ncu_lstm)   step ncu_lstm 280 ncu --set full --clock-control none --import-source on -k regex:lstm_seq_ --launch-skip 3 --launch-count 2 -o "$out/lstm_seq" -f python tools/lstm_bench.py --reps 1 --only-config3 ;;
+    rollout_tests) step rollout_tests 400 python -u -m pytest tests/test_rollout_gpu.py tests/test_lstm_gpu.py tests/test_graphs_gpu.py -q -m gpu --timeout 200 -rf -x ;;
     *) echo "unknown step $s" ;;
   esac
 done

@@ -19,7 +19,9 @@ for h, u, v in zip(hdr, units, vals):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
-data = [r for r in rows[2:] if len(r) == len(h)]
+repeat = [i for i, r in enumerate(rows) if r == h]   # one table per captured kernel: summarise the first
+end = repeat[1] - 1 if len(repeat) > 1 else len(rows)
+data = [r for r in rows[2:end] if len(r) == len(h)]
 si, so = h.index("# Samples"), h.index("Source")
 stall = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
 tot = sum(int(r[si]) for r in data) or 1
