@@ -74,7 +74,6 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_clip_coef_f32": (c_int, [P, c_float, P, P, P]),
     "cusrl_b200_adam_step_f32": (c_int, [P, P, P, P, c_int64, P] + [c_float] * 5 + [c_int64, P]),
     "cusrl_b200_adam_step_dev_f32": (c_int, [P, P, P, P, c_int64, P, P, P] + [c_float] * 4 + [P]),
-    "cusrl_b200_gemm_set_config": (c_int, [c_int]),
     "cusrl_b200_weight_prep_f32": (c_int, [P, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
     "cusrl_b200_linear_fwd_tf32": (c_int, [P, c_int64, P, P, c_int64, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P]),
     "cusrl_b200_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

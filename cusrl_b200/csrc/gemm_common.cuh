@@ -1,5 +1,5 @@
 // Shared definitions of the K-major tcgen05 dense-layer kernels (gemm_tf32.cu: 1-SM MMA + TMA multicast;
-// gemm2sm_tf32.cu: cta_group::2 MMA).
+// the cta_group::2 variant was measured slower in round 1 and removed in round 2).
 #pragma once
 #include "tc_common.cuh"
 
@@ -138,10 +138,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const CUtens
   }
 }
 
-// host-side launchers of the cta_group::2 variant (gemm2sm_tf32.cu); returns CUSRL_B200_EUNSUPPORTED for unknown combos
 // grid size the launchers use for `num_items` work items (2 CTAs per cluster)
 int gemm_grid_ctas(int num_items);
-int launch_gemm_2sm(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
-                    const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s);
 
 }  // namespace cusrl_b200

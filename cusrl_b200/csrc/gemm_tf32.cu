@@ -30,7 +30,7 @@
 //     80 KB of TMA writes + 32 KB of splitter traffic + 144 KB of MMA operand reads (12 MMAs x 12 KB), i.e. 256 KB per
 //     1536 MMA cycles = 167 B/clk against 128 B/clk: the SM's own data paths, not HBM and not the tensor pipe
 //     (58 % busy under ncu), set the pace.  Tried and measured without gain: 4 stages of 16-float k-blocks, an
-//     in-kernel weight split (fewer bytes in, more shared-memory traffic), cta_group::2 (gemm2sm_tf32.cu; the peer's
+//     in-kernel weight split (fewer bytes in, more shared-memory traffic), cta_group::2 (a CTA-pair MMA variant, removed in round 2; the peer's
 //     half of B still crosses the SM boundary).  What DID matter was the epilogue: libdevice expm1f (-25 %) and
 //     row-per-thread 16-byte global stores.
 // PASSES = 1 is plain single-pass TF32.
@@ -323,7 +323,6 @@ int encode_tmap_2d_plain(CUtensorMap* map, const void* base, int elem_bytes, uin
 
 }  // namespace tc
 
-static int g_gemm_two_sm = 0;  // 1: cta_group::2 kernels (gemm2sm_tf32.cu), 0: 1-SM MMA + TMA multicast (this file)
 
 int gemm_grid_ctas(int num_items) {
   const int max_clusters = sm_count() / 2;
@@ -371,7 +370,7 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
                 CUSRL_B200_EALIGN, "linear: pointers must be 16-byte aligned");
   const int bn = N > 128 ? 256 : 128;
   CUtensorMap tA, tB, tBlo;
-  const bool deep = gemm_bk<3>() == 16 && precision == 3 && !g_gemm_two_sm;  // 16-float k-blocks, SWIZZLE_64B
+  const bool deep = gemm_bk<3>() == 16 && precision == 3;  // 16-float k-blocks, SWIZZLE_64B
   const uint32_t bk = deep ? 16 : 32;
   const int sw = deep ? TMAP_SW64 : TMAP_SW128;
   if (int e = encode_tmap_2d_f32(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, bk, BM, sw)) return e;
@@ -404,7 +403,6 @@ static int gemm_kmajor(const float* A, int64_t lda, const float* Bhi, const floa
 
 static int gemm_dispatch(int bn, int precision, int epi, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tBlo,
                          const CUtensorMap& tOut, const GemmParams& p, cudaStream_t s) {
-  if (g_gemm_two_sm) return launch_gemm_2sm(bn, precision, epi, tA, tB, tBlo, tOut, p, s);
 #define CUSRL_GEMM_CASE(BN_, P_, E_) \
   if (bn == BN_ && precision == P_ && epi == E_) return launch_gemm<BN_, P_, E_>(tA, tB, tBlo, tOut, p, s);
   CUSRL_GEMM_CASE(256, 3, EPI_BIAS_ACT)
@@ -425,11 +423,6 @@ static int gemm_dispatch(int bn, int precision, int epi, const CUtensorMap& tA, 
 using namespace cusrl_b200;
 
 extern "C" {
-
-int cusrl_b200_gemm_set_config(int two_sm) {
-  g_gemm_two_sm = two_sm ? 1 : 0;
-  return 0;
-}
 
 int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld, float* hi_t,
                                float* lo_t, int64_t ldt, void* stream) {

@@ -221,9 +221,7 @@ int cusrl_b200_adam_step_dev_f32(float* param, const float* grad, float* exp_avg
  *                 (dX is that layer's dZ), produced by the epilogue while the tile is on chip and reduced
  *                 in a fixed order through `workspace` (cusrl_b200_dgrad_workspace_bytes(K));
  *                 accumulate != 0 adds to the existing db_below.  NULL: not computed, workspace unused.
- * Tuning knob (process-wide): 0 = 1-SM MMA with TMA-multicast weight tiles (default),
- * 1 = cta_group::2 (CTA-pair MMA) forward / data-gradient kernels (measured slower, kept for A/B runs). */
-int cusrl_b200_gemm_set_config(int two_sm);
+ */
 int cusrl_b200_weight_prep_f32(const float* W, int64_t N, int64_t K, float* hi, float* lo, int64_t ld,
                                float* hi_t, float* lo_t, int64_t ldt, void* stream);
 int cusrl_b200_linear_fwd_tf32(const float* X, int64_t ldx, const float* W_hi, const float* W_lo,

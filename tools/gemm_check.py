@@ -83,7 +83,7 @@ if __name__ == "__main__":
     if mode in ("all", "small"):
         from cusrl_b200 import _lib
         if len(sys.argv) > 2:
-            _lib.load().cusrl_b200_gemm_set_config(int(sys.argv[2]))
+            pass
         check(128, 32, 128, 0, 1, with_bias=False)
         check(128, 32, 128, 0, 3, with_bias=False)
         check(256, 64, 256, 0, 1)
@@ -97,7 +97,7 @@ if __name__ == "__main__":
     if mode in ("all", "speed"):
         from cusrl_b200 import _lib
         if len(sys.argv) > 2:
-            _lib.load().cusrl_b200_gemm_set_config(int(sys.argv[2]))
+            pass
         for p in (3, 1):
             speed(393216, 235, 512, p)
             speed(393216, 512, 256, p)

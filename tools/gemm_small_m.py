@@ -4,7 +4,6 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from cusrl_b200 import ops, _lib
-_lib.load().cusrl_b200_gemm_set_config(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 dev = "cuda"
 def t(M, K, N, p, reps=20):
     x = torch.randn(M, (K + 3) // 4 * 4, device=dev)[:, :K]
