@@ -122,6 +122,7 @@ _SIGNATURES: dict[str, tuple[object, list[object]]] = {
     "cusrl_b200_lstm_seq_bwd_f32": (
         c_int, [P, c_int64, P, P, P, P, P, P, c_int64, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "cusrl_b200_memory_reset_store_f32": (c_int, [P, P, P, c_int64, P, c_int64, c_int64, P]),
+    "cusrl_b200_weight_prep_f16_multi": (c_int, [c_int64, P, P, P, P, P, P, P, P, P, P, P, P]),
     "cusrl_b200_mirror_rows_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, c_int64, c_int64, c_int64, P]),
 }
 

@@ -86,12 +86,12 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 // blocks with integer atomicMax (non-negative floats order like their bit patterns).  Blocks 0 .. row_blocks-1 take 8 rows
 // each (one warp per row, lanes along the contiguous K axis); the remaining blocks take 32 columns each (8 row groups per
 // column).  The L1 norms are rounded sums: consumers widen the bounds they build from them.
-__global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
-                                                           float* __restrict__ stats, int row_blocks) {
+__device__ __forceinline__ void weight_stats_block(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
+                                                   float* __restrict__ stats, int row_blocks, int block) {
   unsigned int* out = reinterpret_cast<unsigned int*>(stats);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if ((int)blockIdx.x < row_blocks) {
-    const int n = blockIdx.x * 8 + warp;
+  if (block < row_blocks) {
+    const int n = block * 8 + warp;
     if (n >= N) return;
     float s = 0.f, amax = 0.f;
     for (int k = lane; k < K; k += 32) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restri
     // 32 columns x 8 row groups per block: lanes along the contiguous K axis (128-byte segments), each thread sums every
     // 8th row of its column, the 8 partial sums meet in shared memory
     __shared__ float part[8][33];
-    const int k = ((int)blockIdx.x - row_blocks) * 32 + lane;
+    const int k = (block - row_blocks) * 32 + lane;
     float s0 = 0.f, s1 = 0.f;
     if (k < K) {
       int n = warp;
@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restri
 
 // hi / lo [N, ld] and transposed hi_t / lo_t [K, ldt] halves of W [N, K] with the scale of stats[WSTAT_AMAX]; the padding
 // columns (K..ld-1, N..ldt-1) are zero-initialised by the caller when it allocates the matrices.
-__global__ void __launch_bounds__(256) weight_split_f16_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ stats,
-                                                               __half* __restrict__ hi, __half* __restrict__ lo, int ld,
-                                                               __half* __restrict__ hi_t, __half* __restrict__ lo_t, int ldt) {
+__device__ __forceinline__ void weight_split_block(const float* __restrict__ w, int N, int K, const float* __restrict__ stats,
+                                                   __half* __restrict__ hi, __half* __restrict__ lo, int ld,
+                                                   __half* __restrict__ hi_t, __half* __restrict__ lo_t, int ldt, int block, int nblocks) {
   const float s = f16x3_scale(__ldg(stats + WSTAT_AMAX));
   const int total = N * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (int i = block * blockDim.x + threadIdx.x; i < total; i += nblocks * blockDim.x) {
     const int n = i / K, k = i - n * K;
     const float x = w[i] * s;
     const __half h = __float2half_rn(x);
@@ -151,6 +151,43 @@ __global__ void __launch_bounds__(256) weight_split_f16_kernel(const float* __re
       lo_t[(int64_t)k * ldt + n] = l;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ bias,
+                                                           float* __restrict__ stats, int row_blocks) {
+  weight_stats_block(w, N, K, bias, stats, row_blocks, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(256) weight_split_f16_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ stats,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo, int ld,
+                                                               __half* __restrict__ hi_t, __half* __restrict__ lo_t, int ldt) {
+  weight_split_block(w, N, K, stats, hi, lo, ld, hi_t, lo_t, ldt, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// The same two passes for up to 8 weight matrices in ONE launch each (blockIdx.y = matrix): the layers of a network are
+// re-split after every optimizer step, and three launches (+ a memset) per layer were ~0.3 ms of fixed cost per minibatch
+// on the six dense layers of the PPO agent -- a quarter of a rank's step when 65536 environments are split over 8 GPUs.
+constexpr int kPrepMax = 8;
+struct WeightPrepMulti {
+  const float* W[kPrepMax];
+  const float* bias[kPrepMax];
+  float* stats[kPrepMax];
+  __half *hi[kPrepMax], *lo[kPrepMax], *hi_t[kPrepMax], *lo_t[kPrepMax];
+  int N[kPrepMax], K[kPrepMax], ld[kPrepMax], ldt[kPrepMax], row_blocks[kPrepMax], stat_blocks[kPrepMax], split_blocks[kPrepMax];
+  int count;
+};
+__global__ void __launch_bounds__(256) weight_stats_multi_kernel(const WeightPrepMulti p) {
+  const int m = blockIdx.y;
+  if ((int)blockIdx.x >= p.stat_blocks[m]) return;
+  weight_stats_block(p.W[m], p.N[m], p.K[m], p.bias[m], p.stats[m], p.row_blocks[m], (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(256) weight_split_multi_kernel(const WeightPrepMulti p) {
+  const int m = blockIdx.y;
+  if ((int)blockIdx.x >= p.split_blocks[m]) return;
+  weight_split_block(p.W[m], p.N[m], p.K[m], p.stats[m], p.hi[m], p.lo[m], p.ld[m], p.hi_t[m], p.lo_t[m], p.ldt[m], (int)blockIdx.x,
+                     p.split_blocks[m]);
+}
+__global__ void weight_stats_zero_kernel(const WeightPrepMulti p) {
+  if ((int)threadIdx.x < 4 * p.count) p.stats[threadIdx.x >> 2][threadIdx.x & 3] = 0.f;
 }
 
 namespace tc {
@@ -241,6 +278,40 @@ int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float
   weight_split_f16_kernel<<<blocks, 256, 0, s>>>(W, (int)N, (int)K, stats, (__half*)hi, (__half*)lo, (int)ld, (__half*)hi_t,
                                                  (__half*)lo_t, (int)ldt);
   return check_launch("weight_split_f16_kernel");
+}
+
+int cusrl_b200_weight_prep_f16_multi(int64_t count, const float* const* W, const int64_t* N, const int64_t* K, const float* const* bias,
+                                     uint16_t* const* hi, uint16_t* const* lo, const int64_t* ld, uint16_t* const* hi_t,
+                                     uint16_t* const* lo_t, const int64_t* ldt, float* const* stats, void* stream) {
+  CUSRL_REQUIRE(count >= 1 && count <= kPrepMax && W && N && K && hi && lo && ld && stats, CUSRL_B200_EINVAL,
+                "weight_prep_f16_multi: 1..8 matrices");
+  WeightPrepMulti p{};
+  int max_stat = 0, max_split = 0;
+  for (int m = 0; m < (int)count; ++m) {
+    CUSRL_REQUIRE(W[m] && hi[m] && lo[m] && stats[m], CUSRL_B200_EINVAL, "weight_prep_f16_multi: null pointer");
+    CUSRL_REQUIRE(N[m] > 0 && K[m] > 0 && ld[m] >= K[m] && (ld[m] % 8) == 0 && N[m] * K[m] < (1ll << 31), CUSRL_B200_EINVAL,
+                  "weight_prep_f16_multi: bad sizes");
+    const bool t = hi_t && hi_t[m];
+    CUSRL_REQUIRE(!t || (lo_t && lo_t[m] && ldt && ldt[m] >= N[m] && (ldt[m] % 8) == 0), CUSRL_B200_EINVAL,
+                  "weight_prep_f16_multi: transposed outputs must be given together with ldt >= N, a multiple of 8");
+    p.W[m] = W[m], p.bias[m] = bias ? bias[m] : nullptr, p.stats[m] = stats[m];
+    p.hi[m] = (__half*)hi[m], p.lo[m] = (__half*)lo[m], p.hi_t[m] = t ? (__half*)hi_t[m] : nullptr, p.lo_t[m] = t ? (__half*)lo_t[m] : nullptr;
+    p.N[m] = (int)N[m], p.K[m] = (int)K[m], p.ld[m] = (int)ld[m], p.ldt[m] = t ? (int)ldt[m] : 0;
+    p.row_blocks[m] = (int)((N[m] + 7) / 8);
+    p.stat_blocks[m] = p.row_blocks[m] + (int)((K[m] + 31) / 32);
+    int sb = (int)((N[m] * K[m] + 255) / 256);
+    p.split_blocks[m] = sb > 1184 ? 1184 : sb;
+    max_stat = p.stat_blocks[m] > max_stat ? p.stat_blocks[m] : max_stat;
+    max_split = p.split_blocks[m] > max_split ? p.split_blocks[m] : max_split;
+  }
+  p.count = (int)count;
+  cudaStream_t s = (cudaStream_t)stream;
+  weight_stats_zero_kernel<<<1, 32, 0, s>>>(p);
+  if (int e = check_launch("weight_stats_zero_kernel")) return e;
+  weight_stats_multi_kernel<<<dim3((unsigned)max_stat, (unsigned)count), 256, 0, s>>>(p);
+  if (int e = check_launch("weight_stats_multi_kernel")) return e;
+  weight_split_multi_kernel<<<dim3((unsigned)max_split, (unsigned)count), 256, 0, s>>>(p);
+  return check_launch("weight_split_multi_kernel");
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ class _LstmFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, h0, c0, done, num_layers, *weights):
+        ctx.set_materialize_grads(False)   # h_n / c_n are non-differentiable outputs: no zero tensors for them in backward
         precision = ops.tf32_passes()
         T, Nb, _ = x.shape
         H = h0.shape[-1]
@@ -79,6 +80,9 @@ class _LstmFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, _dh, _dc):
         from .functional import _wgrad
+
+        if d_out is None:
+            return (None,) * (5 + len(ctx.saved_tensors))
 
         precision = ops.tf32_passes()
         T, Nb, H, num_layers = ctx.meta

@@ -730,10 +730,22 @@ def weight_prep_f16(w: torch.Tensor, bias: torch.Tensor | None, out: dict | None
 _weight_cache_f16: dict[int, tuple[tuple, dict, "weakref.ref"]] = {}
 
 
+def _f16_stamp(w: torch.Tensor, bias: torch.Tensor | None) -> tuple:
+    return (_weights_epoch, w._version, tuple(w.shape), None if bias is None else (bias.data_ptr(), bias._version))
+
+
+def _f16_alloc(w: torch.Tensor) -> dict:
+    N, K = w.shape
+    ld, ldt = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    f16 = torch.float16
+    return {"pair": torch.zeros(2, N, ld, dtype=f16, device=w.device), "pair_t": torch.zeros(2, K, ldt, dtype=f16, device=w.device),
+            "stats": torch.zeros(4, dtype=torch.float32, device=w.device), "shape": (N, K)}
+
+
 def prepared_weight_f16(w: torch.Tensor, bias: torch.Tensor | None) -> dict:
     """:func:`weight_prep_f16` of a parameter, rebuilt once per optimizer step (same protocol as :func:`prepared_weight`)."""
     key = w.data_ptr()
-    stamp = (_weights_epoch, w._version, tuple(w.shape), None if bias is None else (bias.data_ptr(), bias._version))
+    stamp = _f16_stamp(w, bias)
     hit = _weight_cache_f16.get(key)
     alive = hit is not None and hit[2]() is not None
     if alive and hit[0] == stamp:
@@ -745,6 +757,37 @@ def prepared_weight_f16(w: torch.Tensor, bias: torch.Tensor | None) -> dict:
         for k in [k for k, v in _weight_cache_f16.items() if v[2]() is None]:
             del _weight_cache_f16[k]
     return wp
+
+
+def prepare_weights_f16(layers) -> None:
+    """Refresh the f16x3 operand copies of several layers ``[(weight, bias), ...]`` at once: the stale ones are re-split by
+    ONE multi-matrix call (cusrl_b200_weight_prep_f16_multi: three launches) instead of three launches per layer; the
+    per-layer :func:`prepared_weight_f16` lookups that follow are cache hits."""
+    stale = []
+    for w, bias in layers:
+        key = w.data_ptr()
+        stamp = _f16_stamp(w, bias)
+        hit = _weight_cache_f16.get(key)
+        alive = hit is not None and hit[2]() is not None
+        if alive and hit[0] == stamp:
+            continue
+        reuse = alive and hit[0][2] == stamp[2]
+        wp = hit[1] if reuse else _f16_alloc(w)
+        stale.append((w, bias, wp))
+        _weight_cache_f16[key] = (stamp, wp, hit[2] if reuse else weakref.ref(w))
+    for i in range(0, len(stale), 8):
+        group = stale[i : i + 8]
+        n = len(group)
+        ptrs, ints = ctypes.c_void_p * n, ctypes.c_int64 * n
+        W = ptrs(*[_ptr(w.detach(), torch.float32, "weight") for w, _, _ in group])
+        B = ptrs(*[None if b is None else _ptr(b.detach(), torch.float32, "bias") for _, b, _ in group])
+        Ns, Ks = ints(*[w.shape[0] for w, _, _ in group]), ints(*[w.shape[1] for w, _, _ in group])
+        hi, lo = ptrs(*[wp["pair"][0].data_ptr() for *_, wp in group]), ptrs(*[wp["pair"][1].data_ptr() for *_, wp in group])
+        hit_, lot = ptrs(*[wp["pair_t"][0].data_ptr() for *_, wp in group]), ptrs(*[wp["pair_t"][1].data_ptr() for *_, wp in group])
+        ld, ldt = ints(*[wp["pair"].shape[2] for *_, wp in group]), ints(*[wp["pair_t"].shape[2] for *_, wp in group])
+        stats = ptrs(*[wp["stats"].data_ptr() for *_, wp in group])
+        code = _lib.load().cusrl_b200_weight_prep_f16_multi(n, W, Ns, Ks, B, hi, lo, ld, hit_, lot, ldt, stats, _stream())
+        _lib.check(code, "weight_prep_f16_multi", launches=3)
 
 
 def f16_linear_fwd(x: Pair, wp: dict, bias: torch.Tensor | None, act: int, out_pair: bool = True,

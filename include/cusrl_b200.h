@@ -346,6 +346,12 @@ int cusrl_b200_split_f16(const float* x, int64_t ld, int64_t rows, int64_t width
                          int64_t ldh, void* stream);
 int cusrl_b200_weight_prep_f16(const float* W, int64_t N, int64_t K, const float* bias, uint16_t* hi, uint16_t* lo, int64_t ld,
                                uint16_t* hi_t, uint16_t* lo_t, int64_t ldt, float* stats, void* stream);
+/* cusrl_b200_weight_prep_f16 for `count` (1..8) matrices in three launches instead of 3 x count (host arrays of per-matrix
+ * arguments; bias / hi_t / lo_t / ldt may be null or hold null entries): the layers of a network are re-split together
+ * after every optimizer step. */
+int cusrl_b200_weight_prep_f16_multi(int64_t count, const float* const* W, const int64_t* N, const int64_t* K, const float* const* bias,
+                                     uint16_t* const* hi, uint16_t* const* lo, const int64_t* ld, uint16_t* const* hi_t,
+                                     uint16_t* const* lo_t, const int64_t* ldt, float* const* stats, void* stream);
 /* K8 for precision 2: pair[i] = split(src[index[i]]) for a wide fp32 leaf (row pitch lds floats, `width` valid columns): the
  * gathered minibatch rows emitted directly as the fp16 pair the first trunk layer consumes (scale of *bound, e.g. the amax
  * of the whole leaf); out-of-range indices are clamped like cusrl_b200_gather_rows. */

@@ -233,3 +233,31 @@ def test_amax_exact_for_dense_narrow_and_pitched_inputs(rows, width, pitch):
     x = back[:, :width]
     back[rows // 2, width - 1] = -123.5
     assert ops.amax(x).item() == x.abs().max().item() == 123.5
+
+
+def test_multi_matrix_weight_prep_equals_per_matrix():
+    """cusrl_b200_weight_prep_f16_multi (all stale layers of a network in three launches) against the per-matrix call:
+    pairs, transposed pairs and norm statistics bit-identical; the cache serves the following per-layer lookups."""
+    from cusrl_b200 import build, ops
+
+    build.build()
+    torch.manual_seed(3)
+    shapes = [(512, 235), (256, 512), (128, 256), (12, 128), (1024, 256)]
+    ws = [torch.nn.Parameter(torch.randn(n, k, device="cuda") / k**0.5) for n, k in shapes]
+    bs = [torch.nn.Parameter(torch.randn(n, device="cuda") * 0.1) for n, _ in shapes]
+    bs[3] = None
+    single = [ops.weight_prep_f16(w, b) for w, b in zip(ws, bs)]
+    ops.invalidate_weight_cache()
+    ops.prepare_weights_f16(list(zip(ws, bs)))
+    before = ops.launch_count()
+    for w, b, ref in zip(ws, bs, single):
+        got = ops.prepared_weight_f16(w, b)
+        assert torch.equal(got["pair"], ref["pair"]) and torch.equal(got["pair_t"], ref["pair_t"])
+        assert torch.equal(got["stats"], ref["stats"])
+    assert ops.launch_count() == before   # all cache hits
+    # a parameter update makes exactly that layer stale
+    with torch.no_grad():
+        ws[1].mul_(1.5)
+    ops.prepare_weights_f16(list(zip(ws, bs)))
+    assert ops.launch_count() == before + 3
+    assert torch.equal(ops.prepared_weight_f16(ws[1], bs[1])["stats"], ops.weight_prep_f16(ws[1], bs[1])["stats"])

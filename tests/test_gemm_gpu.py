@@ -82,6 +82,9 @@ def test_linear_dgrad_emits_bias_gradient_of_layer_below(ops, M, N, K, act, accu
     assert torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 128), (4096, 512, 235), (5000, 256, 512), (5000, 128, 256), (3000, 16, 128),
+                                   (100, 64, 19)])
+@pytest.mark.parametrize("accumulate", [False, True])
 def test_linear_wgrad(ops, M, N, K, accumulate):
     g = torch.Generator().manual_seed(M + N + K)
     dz = torch.randn(M, N, generator=g).to(DEV)
