@@ -7,21 +7,28 @@
 //
 //   work split   a ROW TILE of 128 batch columns is advanced through time by H/16 CTAs, each owning 16 hidden units, i.e.
 //                the 64 gate columns (i, f, g, o of its units) of the recurrent product;  8 row tiles x 16 slices = 128 CTAs
-//                at the minibatch shape, all co-resident (one CTA per SM, grid <= #SMs), row-tile groups loop over more
-//                tiles when Nb is larger (rollout / statistics passes).
+//                at the minibatch shape, all co-resident (one CTA per SM; the grid is bounded by the number of 4-CTA clusters
+//                the device holds at once), row-tile groups loop over more tiles when Nb is larger (rollout / statistics).
 //   operands     W_hh slice [64 x H] as an fp16 hi/lo pair (f16x3_common.cuh) RESIDENT in shared memory for the whole
 //                launch (64 KB at H = 256); h_{t-1} of the row tile [128 x H] as a pair arrives by TMA every step (128 KB)
-//                from a double-buffered exchange array in L2 that the slices' epilogues write.
-//   step         3 x (H/16) tcgen05 kind::f16 MMAs (M = 128, N = 64) into one TMEM accumulator -> epilogue warps:
+//                from a double-buffered exchange array in L2 that the slices' epilogues write -- read from L2 once per
+//                4-CTA cluster and multicast; the step's slice of the input projection arrives by TMA too.
+//   step         3 x (H/16) tcgen05 kind::f16 MMAs (M = 128, N = 64) into one TMEM accumulator -> 16 epilogue warps:
 //                tcgen05.ld, + input projection (+ b_hh), gate nonlinearities, c_t (carried in REGISTERS across steps),
-//                h_t, in-line reset where done[t] (the reference's split / pad / scatter), all saved tensors of the
+//                h_t, in-line reset where done[t] (the reference's split / pad / scatter), the tensors saved for the
 //                backward pass, and h_t re-split into the exchange pair.
 //   hand-over    per (row tile, step) one counter in global memory: every slice's epilogue stores its part of h_t, meets at
 //                a named barrier and one thread adds to the counter with release semantics (the barrier makes the release
 //                cumulative over the CTA's writes); the TMA producers of the tile's CTAs acquire-poll the counter, order the
-//                generic-proxy writes before their async-proxy reads (fence.proxy.async) and load.  The tensors saved for
-//                the backward pass are written AFTER the hand-over, off the critical path.  No cluster, no cooperative
-//                launch, no host involvement.
+//                generic-proxy writes before their async-proxy reads (fence.proxy.async) and load.  No cooperative launch,
+//                no host involvement.
+//   data layout  TMEM lanes are accumulator ROWS, so with the natural thread mapping a warp's global access touches 32 rows
+//                = 32 L1 wavefronts per instruction; that, not latency or bandwidth, bounded the first versions (7 000
+//                wavefront cycles per forward step, 27 600 per backward step).  Tensors only the backward twin reads (gates,
+//                c_t, c_in, and the backward's partial products) therefore use a private tiled layout
+//                [T][tile][H/4][(gate)][128 rows][4] in which a warp's rows are contiguous, and row-major outputs (h_t, h_in,
+//                the exchange pair, dgates) are transposed through the operand tile while it is idle.
+//                Inference calls (gates == null) save nothing and read / write a layer's slice of a flat memory in place.
 //
 // Numerics: fp32-equivalent recurrent product (three fp16 MMAs, fp32 accumulation), |h| < 1 fixes the scale of the h pair
 // (2^14), W_hh's scale comes from its exact amax (weight_prep_f16); everything else is the fp32 arithmetic of
