@@ -37,7 +37,7 @@ class Stub:
 
     def __getattr__(self, name):
         fn = getattr(real, name)
-        if name in QUERIES or name.endswith("_bytes") or "set_" in name:
+        if name in QUERIES or name.endswith("_bytes") or name.endswith("_supported") or ("_set_" in name and "reset" not in name):
             return fn
 
         def launch(*a):
