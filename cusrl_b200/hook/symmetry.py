@@ -14,8 +14,10 @@ transition / batch keys, loss names, errors.  What changes is where the arithmet
   ``value``, ``return``) are repeated along the new axis as the reference does.
 
 Mirror functions that are arbitrary callables (anything that is not a ``MirrorDef``, here or the reference's own) are
-simply called, as in the reference.  Gradients through a mirror transform (``MirrorSymmetryLoss`` mirrors the action mean
-of the mirrored observation, ``[B, action_dim]``) use torch indexing: they are tiny and need autograd.
+simply called, as in the reference.  Gradients through a ``MirrorDef`` (``MirrorSymmetryLoss`` mirrors the action mean of
+the mirrored observation) run on the same kernel: the adjoint of an index permutation with sign flips is another one.
+CPU tensors (the spec's mirror definitions are built and self-checked on the CPU, cusrl_test/_helpers.py:17-35) and index
+maps that are not permutations take torch indexing.
 """
 
 from __future__ import annotations
@@ -62,10 +64,31 @@ class MirrorDef:
             cached = self._tables[device] = (dest, mult)
         return cached
 
+    def inverse_tables(self, device: torch.device) -> tuple[Tensor, Tensor] | None:
+        """Tables of the adjoint transform (gradient of the output -> gradient of the input) when the index map is a
+        permutation: ``g_in[dest[j]] = g_out[j] * mult[j]``, i.e. another index-permute + sign-flip.  None otherwise."""
+        cached = self._tables.get(("inv", device))  # type: ignore[arg-type]
+        if cached is None:
+            n = self.destination.numel()
+            dest = (self.destination % n).tolist()
+            if sorted(dest) != list(range(n)):
+                cached = (None, None)
+            else:
+                inv = [0] * n
+                for j, d in enumerate(dest):
+                    inv[d] = j
+                inv_t = torch.tensor(inv, dtype=torch.int32, device=device).reshape(1, n)
+                mult = self.multiplier.to(device=device, dtype=torch.float32)[torch.tensor(inv, device=device)].reshape(1, n).contiguous()
+                cached = (inv_t.contiguous(), mult)
+            self._tables[("inv", device)] = cached  # type: ignore[index]
+        return None if cached[0] is None else cached
+
     def __call__(self, input: Tensor) -> Tensor:
         if _kernel_ok(input, self):
             dest, mult = self.tables(input.device)
             return ops.mirror_rows(input, dest, mult, layout="same")
+        if _kernel_ok(input, self, allow_grad=True) and self.inverse_tables(input.device) is not None:
+            return _MirrorFunction.apply(input, self)   # differentiable, still the kernel (forward and adjoint)
         self.destination = self.destination.to(input.device)
         self.multiplier = self.multiplier.to(dtype=input.dtype, device=input.device)
         return input[..., self.destination] * self.multiplier
@@ -92,9 +115,22 @@ def _as_mirror_def(mirror: Any) -> MirrorDef | None:
     return None
 
 
-def _kernel_ok(x: Tensor, mirror: MirrorDef) -> bool:
+def _kernel_ok(x: Tensor, mirror: MirrorDef, allow_grad: bool = False) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 1 and x.shape[-1] == mirror.destination.numel()
-            and x.numel() > 0 and not (torch.is_grad_enabled() and x.requires_grad))
+            and x.numel() > 0 and (allow_grad or not (torch.is_grad_enabled() and x.requires_grad)))
+
+
+class _MirrorFunction(torch.autograd.Function):
+    """``mirror(x)`` with autograd: forward and adjoint are both index-permute + sign-flip transforms, both on the kernel."""
+
+    @staticmethod
+    def forward(ctx, x, mirror):
+        ctx.mirror = mirror
+        return ops.mirror_rows(x.detach(), *mirror.tables(x.device), layout="same")
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ops.mirror_rows(grad.contiguous(), *ctx.mirror.inverse_tables(grad.device), layout="same"), None
 
 
 def _identity_plus(mirror: MirrorDef, device: torch.device) -> tuple[Tensor, Tensor]:

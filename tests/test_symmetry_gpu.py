@@ -68,6 +68,11 @@ def test_mirror_kernel_bit_exact_in_every_layout(C, width, rows):
     xg = xd.clone().requires_grad_(True)
     yg = mirror(xg)
     assert yg.requires_grad and torch.equal(yg.detach().cpu(), ref)
+    gout = torch.randn(rows, width, generator=g).to(DEV)
+    (yg * gout).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    ((xr[..., mirror.destination] * mirror.multiplier) * gout.cpu()).sum().backward()
+    assert torch.equal(xg.grad.cpu(), xr.grad)   # the adjoint is an index permutation with sign flips too: exact
 
 
 def _make_agent(C, variant: str):
