@@ -85,6 +85,9 @@ def f16_trunk_forward(x: torch.Tensor, linears, act_code: int, last_act: bool):
     is fp32.  Returns (x pair, [hidden pairs..., fp32 output])."""
     ops.prepare_weights_f16(linears)   # every stale layer of the stack re-split by one multi-matrix call
     xp = ops.attached_pair(x)   # the sampler may already have produced the pair while gathering the minibatch
+    if xp is None and ops.is_pair_only(x):
+        raise RuntimeError("this minibatch leaf was gathered as an fp16 pair only (sampler.pair_only) and the pair is no longer "
+                           "attached to it (the tensor was modified in place?)")
     if xp is None:
         xp = ops.split_f16(x if x.stride(-1) == 1 else x.contiguous())
         if x.stride(-1) == 1:
@@ -173,6 +176,9 @@ class _MlpHeadFunction(torch.autograd.Function):
         ctx.f16 = ops.GEMM_PRECISION == 2 and x.shape[0] >= ops.F16X3_MIN_ROWS and f16x3_supported(weights, biases)
         if ctx.f16:
             return _f16_forward(ctx, x, act_code, last_act, has_head, n, params)
+        if ops.is_pair_only(x):
+            raise RuntimeError("this minibatch leaf was gathered as an fp16 pair only (sampler.pair_only) but the layer stack "
+                               "takes the fp32 path: set sampler.pair_only = frozenset()")
         x = _rows_ok(x)
         acts = []
         h = x

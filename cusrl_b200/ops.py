@@ -868,6 +868,23 @@ def attach_pair(tensor: torch.Tensor, pair: Pair) -> None:
     _attached_pairs[tensor.data_ptr()] = (weakref.ref(tensor), (tuple(tensor.shape), tuple(tensor.stride()), tensor._version), pair)
 
 
+_pair_only: dict[int, "weakref.ref"] = {}
+
+
+def mark_pair_only(tensor: torch.Tensor) -> None:
+    """`tensor` is a minibatch leaf whose fp32 rows were NOT gathered (only its attached fp16 pair is current)."""
+    _pair_only[tensor.data_ptr()] = weakref.ref(tensor)
+
+
+def unmark_pair_only(tensor: torch.Tensor) -> None:
+    _pair_only.pop(tensor.data_ptr(), None)
+
+
+def is_pair_only(tensor: torch.Tensor) -> bool:
+    ref = _pair_only.get(tensor.data_ptr())
+    return ref is not None and ref() is not None
+
+
 def attached_pair(tensor: torch.Tensor) -> Pair | None:
     hit = _attached_pairs.get(tensor.data_ptr())
     if hit is None or hit[0]() is None:

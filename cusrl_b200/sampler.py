@@ -47,6 +47,9 @@ class MiniBatchSampler(Sampler):
                 raise ValueError("'num_mini_batches' values must be positive")
         self.shuffle = shuffle
         self.fields = None if fields is None else tuple(fields)
+        # leaves whose fp32 minibatch copy may be skipped when their fp16 pair is emitted (set by the agent when it can prove
+        # that nothing but the f16x3 first layers consumes them: ActorCritic._configure_sampler)
+        self.pair_only: frozenset[str] = frozenset()
         self._dst: dict[tuple, torch.Tensor] = {}
         self._pair_dst: dict[tuple, object] = {}
         self._pair_bounds: dict[str, torch.Tensor] = {}
@@ -104,6 +107,7 @@ class MiniBatchSampler(Sampler):
         T, N = buffer.capacity, buffer.get_parallelism()
         out: dict[str, torch.Tensor] = {}
         groups: dict[int, tuple[torch.Tensor, list]] = {}
+        emit_pairs = not self.temporal and ops.GEMM_PRECISION == 2 and idx.numel() >= ops.F16X3_MIN_ROWS
         if self.temporal:
             n_mb = idx.numel()
             all_rows = (torch.arange(T, device=idx.device).unsqueeze(1) * N + idx.unsqueeze(0)).reshape(-1)
@@ -122,12 +126,17 @@ class MiniBatchSampler(Sampler):
             src2 = back.reshape(T * N, -1)
             dst2 = dst.reshape(rows.numel(), -1)
             pair = (src2 if src2.shape[1] == dst2.shape[1] else src2[:, : min(src2.shape[1], dst2.shape[1])], dst2)
-            groups.setdefault(id(rows), (rows, []))[1].append(pair)
             out[key] = view
+            if emit_pairs and key in self.pair_only and leaf.dim() == 3 and leaf.dtype == torch.float32:
+                ops.mark_pair_only(view)   # its fp16 pair is emitted below; the fp32 rows are not gathered
+                continue
+            if self.pair_only:
+                ops.unmark_pair_only(view)
+            groups.setdefault(id(rows), (rows, []))[1].append(pair)
         for rows, pairs in groups.values():
             for i in range(0, len(pairs), 24):  # at most CUSRL_B200_MAX_GATHER_FIELDS (24) fields per launch
                 ops.gather_rows(pairs[i : i + 24], rows)
-        if not self.temporal and ops.GEMM_PRECISION == 2 and idx.numel() >= ops.F16X3_MIN_ROWS:
+        if emit_pairs:
             # f16x3 dense layers: the network inputs are ALSO emitted as fp16 hi / lo pairs by the gather itself (scale from
             # the amax of the whole leaf, computed once per update), so the first layer does not re-read the minibatch to
             # split it; the fp32 leaf stays in the batch for every other consumer
@@ -179,6 +188,7 @@ class AutoMiniBatchSampler(Sampler):
                  fields: Sequence[str] | None = None, memory_first_step_only: bool = False):
         self.num_epochs, self.num_mini_batches, self.shuffle, self.fields = num_epochs, num_mini_batches, shuffle, fields
         self.memory_first_step_only = memory_first_step_only
+        self.pair_only: frozenset[str] = frozenset()
         self._impl: MiniBatchSampler | None = None
 
     def _resolve(self, buffer: Buffer) -> MiniBatchSampler:
@@ -187,6 +197,7 @@ class AutoMiniBatchSampler(Sampler):
         if not isinstance(self._impl, cls) or type(self._impl) is not cls:
             self._impl = cls(self.num_epochs, self.num_mini_batches, self.shuffle, self.fields)
             self._impl.memory_first_step_only = self.memory_first_step_only
+        self._impl.pair_only = self.pair_only
         return self._impl
 
     def indices(self, buffer: Buffer):

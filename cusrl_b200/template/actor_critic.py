@@ -164,6 +164,34 @@ class ActorCritic:
         distributed.broadcast_parameters([self.optimizer.flat_param] if hasattr(self.optimizer, "flat_param")
                                          else self.parameters())
         self.hook.apply_schedule(0)
+        self._configure_sampler()
+
+    def _configure_sampler(self) -> None:
+        """Minibatch gather of the network inputs.  With the f16x3 dense layers the sampler emits ``observation`` / ``state``
+        minibatches directly as the fp16 pairs the first layers consume; the fp32 copy of those leaves (940 of the 1 004
+        bytes a sample's gather moves) is then read by nobody -- PROVIDED every hook is one of this package's PPO hooks
+        (which hand the batch leaf to the networks and nothing else) and both networks are MLPs the pair path covers.  Only
+        then is the sampler told that it may skip that copy; any other hook (a user's, the reference's, observation
+        normalisation, symmetry, ...) keeps the full gather."""
+        from ..hook import on_policy as P
+        from ..hook.auxiliary import RandomNetworkDistillation
+        from ..nn import functional as F
+        from ..nn import modules as M
+
+        sampler = self.sampler
+        if not hasattr(sampler, "pair_only"):
+            return
+        known = (P.ModuleInitialization, P.ValueComputation, P.GeneralizedAdvantageEstimation, P.AdvantageNormalization,
+                 P.AdvantageReduction, P.ValueLoss, P.OnPolicyPreparation, P.PpoSurrogateLoss, P.EntropyLoss, P.GradientClipping,
+                 P.OnPolicyStatistics, P.AdaptiveLRSchedule, RandomNetworkDistillation)
+        ok = all(type(hook) in known for hook in self.hook)
+        for net in (self.actor, self.critic):
+            backbone = getattr(net, "backbone", None)
+            ok = ok and type(net) in (M.Actor, M.Value) and type(backbone) is M.Mlp
+            if ok:
+                lins = backbone.linears()
+                ok = F.f16x3_supported([m.weight for m in lins], [m.bias for m in lins])
+        sampler.pair_only = frozenset(("observation", "state")) if ok else frozenset()
 
     # ---- parameters / modules --------------------------------------------------------------------
     def named_parameters(self):
