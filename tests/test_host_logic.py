@@ -369,3 +369,30 @@ def test_trainer_refuses_environments_without_autoreset():
 
     with pytest.raises(ValueError, match="autoreset"):
         C.Trainer(Env(), Agent())
+
+
+def test_sampler_may_skip_the_fp32_input_gather_only_when_provably_unused():
+    """ActorCritic._configure_sampler: `sampler.pair_only` is set for the plain PPO preset (every hook one of this package's
+    PPO hooks, MLP networks the f16x3 path covers) and stays empty as soon as anything else could read the fp32 minibatch
+    observation: a user hook, observation normalisation, symmetry hooks, recurrent networks."""
+    import cusrl_b200 as C
+
+    spec = C.EnvironmentSpec(8, 19, 4, autoreset=True, final_state_is_missing=True)
+    plain = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), device="cpu")(spec)
+    assert plain.sampler.pair_only == frozenset(("observation", "state"))
+
+    class Peek(C.Hook):
+        pass
+
+    factory = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), device="cpu").to_underlying()
+    factory.register_hook(Peek())
+    assert factory(spec).sampler.pair_only == frozenset()
+    normalised = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), normalize_observation=True, device="cpu")
+    assert normalised(spec).sampler.pair_only == frozenset()
+    recurrent = C.RecurrentPpoAgentFactory(actor_hidden_size=64, critic_hidden_size=64, device="cpu")(spec)
+    assert recurrent.sampler.pair_only == frozenset()
+    sym = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), device="cpu").to_underlying()
+    sym.register_hook(C.MirrorSymmetryLoss(0.1), after="ppo_surrogate_loss")
+    sym_spec = C.EnvironmentSpec(8, 19, 4, autoreset=True, final_state_is_missing=True,
+                                 mirror_observation=C.MirrorDef(list(range(19)), []), mirror_action=C.MirrorDef(list(range(4)), []))
+    assert sym(sym_spec).sampler.pair_only == frozenset()

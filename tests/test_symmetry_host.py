@@ -135,3 +135,33 @@ def test_symmetry_hooks_validate_their_arguments_and_spec():
     with pytest.raises(ValueError, match="mirror_observation"):
         hook.init()
     assert SymmetricDataAugmentation().training_only and not TransitionMirroring().training_only
+
+
+def test_mirror_adjoint_tables_are_the_transpose_of_the_transform():
+    """The differentiable CUDA path applies `inverse_tables` in its backward: it must be the exact adjoint of the forward
+    index-permute + sign-flip (checked here against autograd through torch indexing), and absent for non-permutations."""
+    mirror = MirrorDef(*R.mirror_tables(12, seed=22))
+    x = torch.randn(6, 12, requires_grad=True)
+    g = torch.randn(6, 12)
+    (mirror(x) * g).sum().backward()
+    inv_dest, inv_mult = mirror.inverse_tables(torch.device("cpu"))
+    assert torch.equal(x.grad, g[..., inv_dest[0].long()] * inv_mult[0])
+    assert MirrorDef([0, 0, 1], []).inverse_tables(torch.device("cpu")) is None
+
+
+def test_expanded_done_flags_and_std_vector_helpers():
+    from cusrl_b200.hook.on_policy import _std_vector
+    from cusrl_b200.nn.recurrent import _expand_done
+
+    done = torch.rand(5, 4, 1) < 0.5
+    assert torch.equal(_expand_done(done, 5, 4, (4,)), done.reshape(5, 4))
+    wide = _expand_done(done, 5, 12, (4, 3))          # [T, N, 1] flags for a [T, N, 3 variants, C] input
+    assert wide.shape == (5, 12) and torch.equal(wide.reshape(5, 4, 3)[:, :, 2], done.reshape(5, 4))
+    param = torch.nn.Parameter(torch.rand(7) + 0.5)
+    assert _std_vector(param.expand(9, 7), param) is param               # the plain NormalDist: the parameter itself
+    assert _std_vector(param.expand(9, 2, 7), param) is param
+    mixed = (param.expand(9, 7) + param.flip(0).expand(9, 7)) / 2         # a wrapper that post-processes the std
+    vec = _std_vector(mixed, param)
+    assert vec.shape == (7,) and torch.equal(vec, mixed[0])
+    vec.sum().backward()
+    assert torch.allclose(param.grad, torch.ones(7))                     # gradient reaches the parameter through row 0
