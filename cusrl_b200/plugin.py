@@ -31,9 +31,10 @@ from cusrl.zoo import register_experiment
 import cusrl_b200
 from cusrl_b200.preset import anymal_c_rough_ppo
 
-__all__ = ["ALGORITHM_NAME", "SyntheticAnymalEnvironment", "make_synthetic_env"]
+__all__ = ["ALGORITHM_NAME", "RECURRENT_ALGORITHM_NAME", "SyntheticAnymalEnvironment", "make_synthetic_env"]
 
 ALGORITHM_NAME = "ppo-b200"  # experiment names may not contain ':', '_', '/' or '\\' (cusrl/zoo/experiment.py:218-223)
+RECURRENT_ALGORITHM_NAME = "ppo-b200-lstm"  # the recurrent preset (LSTM 2 x 256 actor and critic, preset/ppo.py:185-298)
 
 
 class SyntheticAnymalEnvironment(cusrl.template.Environment):
@@ -79,6 +80,8 @@ def _register() -> None:
     common = dict(algorithm_name=ALGORITHM_NAME, agent_meta_factory=anymal_c_rough_ppo, num_iterations=1500,
                   checkpoint_interval=100, trainer_hooks=hooks)
     register_experiment(environment_name="Synthetic-AnymalC-Rough-v0", training_env_factory=make_synthetic_env, **common)
+    recurrent = dict(common, algorithm_name=RECURRENT_ALGORITHM_NAME, agent_meta_factory=cusrl_b200.RecurrentPpoAgentFactory)
+    register_experiment(environment_name="Synthetic-AnymalC-Rough-v0", training_env_factory=make_synthetic_env, **recurrent)
     try:  # the real simulator adapter, when IsaacLab is installed (same env list as cusrl/zoo/isaaclab/locomotion.py:40-47)
         from cusrl.environment import make_isaaclab_env
     except Exception:  # pragma: no cover - IsaacLab absent
@@ -87,6 +90,10 @@ def _register() -> None:
         environment_name=[f"Isaac-Velocity-Rough-{robot}-v0" for robot in
                           ("Anymal-B", "Anymal-C", "Anymal-D", "Unitree-A1", "Unitree-Go1", "Unitree-Go2")],
         training_env_factory=make_isaaclab_env, playing_env_factory_kwargs={"play": True}, **common)
+    register_experiment(
+        environment_name=[f"Isaac-Velocity-Rough-{robot}-v0" for robot in
+                          ("Anymal-B", "Anymal-C", "Anymal-D", "Unitree-A1", "Unitree-Go1", "Unitree-Go2")],
+        training_env_factory=make_isaaclab_env, playing_env_factory_kwargs={"play": True}, **recurrent)
 
 
 _register()

@@ -50,6 +50,9 @@ def test_plugin_registers_and_reference_trainer_accepts_the_agent(reference):
     assert trainer.agent.parallelism == 8 and trainer.agent.observation_dim == 235
     assert [h.name for h in trainer.agent.hook][:3] == ["module_initialization", "value_computation",
                                                         "generalized_advantage_estimation"]
+    # the recurrent preset is registered next to it (python -m cusrl train -alg ppo-b200-lstm -m cusrl_b200.plugin)
+    lstm = get_experiment("Synthetic-AnymalC-Rough-v0", plugin.RECURRENT_ALGORITHM_NAME).to_training_factory()
+    assert type(lstm.agent_factory).__name__ == "RecurrentPpoAgentFactory" and lstm.agent_factory.actor_hidden_size == 256
 
 
 def test_checkpoints_move_between_the_reference_agent_and_this_one(reference):
