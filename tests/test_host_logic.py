@@ -396,3 +396,71 @@ def test_sampler_may_skip_the_fp32_input_gather_only_when_provably_unused():
     sym_spec = C.EnvironmentSpec(8, 19, 4, autoreset=True, final_state_is_missing=True,
                                  mirror_observation=C.MirrorDef(list(range(19)), []), mirror_action=C.MirrorDef(list(range(4)), []))
     assert sym(sym_spec).sampler.pair_only == frozenset()
+
+
+def test_adaptive_lr_schedule_rolls_back_an_update_that_exceeds_max_kl():
+    """The reference's rollback test (cusrl_test/hook/on_policy/test_lr_schedule.py:38-63) against this implementation of
+    the KL-adaptive schedule: an update whose KL exceeds `max_kl_divergence` is undone (parameters AND optimizer state back
+    to the pre-update checkpoint) while the learning-rate scale decided from that KL is kept."""
+    import math
+
+    spec = C.EnvironmentSpec(8, 19, 4, autoreset=True, final_state_is_missing=True)
+    factory = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), desired_kl_divergence=None,
+                                device="cpu").to_underlying()
+    factory.register_hook(C.AdaptiveLRSchedule(0.01, max_kl_divergence=0.02, scale_factor=0.2))
+    agent = factory(spec)
+    hook = agent.hook["adaptive_lr_schedule"]
+    actor_param = next(agent.actor.parameters())
+    original = actor_param.detach().clone()
+    hook.pre_update(agent.buffer)
+    with torch.no_grad():
+        actor_param.add_(1.0)
+    agent.metrics.clear()
+    agent.record(kl_divergence=0.03)
+    hook.post_update()
+    assert torch.allclose(actor_param, original)
+    assert hook._lr_scale == pytest.approx(math.exp(-0.2))          # log(0.03 / 0.01) > threshold 1 -> clip to 1 -> exp(-0.2)
+    for base_lr, group in zip(hook._base_lrs, agent.optimizer.param_groups):
+        scaled = any(n.startswith("actor.") for n in group["param_names"])
+        assert group["lr"] == pytest.approx(base_lr * (hook._lr_scale if scaled else 1.0))
+    assert agent.metrics["update_rejected"].mean.item() == pytest.approx(1.0)
+    # an update inside the limit is kept
+    hook.pre_update(agent.buffer)
+    with torch.no_grad():
+        actor_param.add_(0.5)
+    agent.metrics.clear()
+    agent.record(kl_divergence=0.012)
+    hook.post_update()
+    assert torch.allclose(actor_param, original + 0.5)
+    assert agent.metrics["update_rejected"].mean.item() == pytest.approx(0.0)
+
+
+def test_advantage_reduction_weighted_sum_mean_and_weight_updates():
+    """The reference's own tests (cusrl_test/hook/on_policy/test_advantage.py:9-34) against this AdvantageReduction: the
+    vector advantage of a multi-term reward is reduced to the scalar the surrogate needs."""
+    from types import SimpleNamespace
+
+    hook = C.AdvantageReduction(reduction="sum", weight=(1.0, 2.0))
+    hook.agent = SimpleNamespace(to_tensor=lambda value: torch.as_tensor(value, dtype=torch.float32))
+    hook.init()
+    batch = {"advantage": torch.tensor([[1.0, 2.0], [3.0, 4.0]])}
+    assert hook.objective({}, batch) is None
+    assert torch.allclose(batch["advantage"], torch.tensor([[5.0], [11.0]]))
+    hook.update_attribute("weight", (0.5, 0.5))
+    batch = {"advantage": torch.tensor([[2.0, 6.0]])}
+    hook.objective({}, batch)
+    assert torch.allclose(batch["advantage"], torch.tensor([[4.0]]))
+    hook.update_attribute("weight", None)
+    batch = {"advantage": torch.tensor([[2.0, 6.0]])}
+    hook.objective({}, batch)
+    assert torch.allclose(batch["advantage"], torch.tensor([[8.0]]))
+
+    mean = C.AdvantageReduction(reduction="mean")
+    mean.agent = hook.agent
+    mean.init()
+    batch = {"advantage": torch.tensor([[1.0, 3.0]])}
+    mean.objective({}, batch)
+    assert torch.allclose(batch["advantage"], torch.tensor([[2.0]]))
+    with pytest.raises(ValueError, match="Unsupported reduction"):
+        C.AdvantageReduction(reduction="max")
+    assert mean.name == "advantage_reduction" and mean.training_only
