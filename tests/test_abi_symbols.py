@@ -57,3 +57,35 @@ def test_ops_refuse_cpu_tensors():
     flags = torch.zeros(2, 3, 1, dtype=torch.bool)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.gae(x, flags, x, x, 0.99, 0.95)
+
+
+def test_every_compute_entry_point_rejects_null_arguments_before_any_cuda_call():
+    """Every launch entry point of the header, called with null pointers and zero sizes on a box WITHOUT a GPU, must come
+    back with a negative argument-error code and a message: no crash, no CUDA call (a positive cudaError_t would mean the
+    validation let the call through).  Run in a child process so that a crashing entry point fails this test instead of
+    taking the test session down."""
+    import subprocess
+    import sys
+    import textwrap
+
+    script = textwrap.dedent("""
+        import ctypes
+        from cusrl_b200 import _lib
+        lib = _lib.load()
+        skip = ("_set_", "_supported", "_bytes", "abi_version", "last_error", "sm_count")
+        bad = []
+        names = [n for n in _lib._SIGNATURES if not any(s in n for s in skip)]
+        for name in names:
+            _, argtypes = _lib._SIGNATURES[name]
+            args = [0.0 if a in (ctypes.c_float, ctypes.c_double)
+                    else 0 if a in (ctypes.c_int, ctypes.c_int64, ctypes.c_size_t) else None for a in argtypes]
+            code = getattr(lib, name)(*args)
+            if code >= 0 or not lib.cusrl_b200_last_error():
+                bad.append((name, code))
+        print(len(names), bad)
+    """)
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300,
+                         cwd=str(_lib.PKG_DIR.parent))
+    assert out.returncode == 0, out.stderr[-2000:]
+    count, bad = out.stdout.strip().split(" ", 1)
+    assert int(count) >= 40 and bad == "[]", out.stdout
