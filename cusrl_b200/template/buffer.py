@@ -75,6 +75,8 @@ class Buffer(MutableMapping):
         # hand-shakes between ADJACENT B200 hooks that fuse their kernels across the hook boundary (hook/on_policy.py:
         # next_value -> GAE -> advantage statistics in one launch); never part of the data contract
         self.private: dict[str, Any] = {}
+        # bumped whenever a leaf is allocated or dropped: holders of resolved slot addresses (template/rollout.py) re-resolve
+        self.layout_version = 0
 
     # ---- bookkeeping ---------------------------------------------------------------------------
     def get_parallelism(self) -> int:
@@ -82,6 +84,7 @@ class Buffer(MutableMapping):
 
     def clear(self) -> None:
         self.cursor, self.full = 0, False
+        self.layout_version += 1
         self.private.clear()
         self.storage.clear()
         self._backing.clear()
@@ -141,6 +144,7 @@ class Buffer(MutableMapping):
         for _, leaf in flatten_nested(self.schema[name], ""):  # schema leaves are the dotted leaf names
             self.storage.pop(leaf, None)
             self._backing.pop(leaf, None)
+        self.layout_version += 1
         del self.schema[name]
 
     # ---- rollout writes --------------------------------------------------------------------------
@@ -190,6 +194,7 @@ class Buffer(MutableMapping):
             view = back
         self._backing[key] = back
         self.storage[key] = view
+        self.layout_version += 1
         return view
 
     def _check_schema(self, name: str, data: Nested) -> None:

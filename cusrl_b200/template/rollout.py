@@ -26,7 +26,7 @@ from typing import Any
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..nn import functional as F
 from ..nn import modules as M
 from .hook import Hook
@@ -53,29 +53,95 @@ def _same_array(x: torch.Tensor, prev: tuple) -> bool:
 
 
 class _Net:
-    """Forward-only launch plan of one trunk + head with persistent activation buffers."""
+    """Forward-only launch plan of one trunk + head with persistent activation buffers.
+
+    On the 3xTF32 path (fewer rows than ``ops.F16X3_MIN_ROWS``: the regime in which a rollout step is bound by the time the
+    host needs to ISSUE its ~11 launches, not by the GPU) the launches are *bound*: every argument that does not depend on
+    the buffer step -- operand copies of the weights, biases, the activation buffers, shapes -- is resolved to a plain
+    integer once, and a step passes only the input rows, the output slot and the stream.  The binding is re-made when a
+    parameter moved or its operand copies were re-allocated; stale operand copies are re-split exactly as before
+    (``ops.prepared_weight``), detected by the weights' version counters and the optimizer's epoch."""
 
     def __init__(self, backbone: M.Mlp, head: torch.nn.Linear, rows: int, device: torch.device):
         self.linears = backbone.linears()
         self.act = F.ACTIVATIONS[backbone.activation]
         self.head = head
+        self.rows = rows
         self.acts = [torch.empty(rows, lin.out_features, device=device) for lin in self.linears]
+        self._weights = [lin.weight for lin in self.linears]
+        self._params = [p for lin in self.linears for p in (lin.weight, lin.bias) if p is not None]
+        self._params += [p for p in (head.weight, head.bias) if p is not None]
+        self._f16_ok = F.f16x3_supported(self._weights, [lin.bias for lin in self.linears])
+        self._stamp = self._ptrs = self._wps = None
+        self._first = self._rest = self._head_args = None
+
+    def uses_f16x3(self) -> bool:
+        return ops.GEMM_PRECISION == 2 and self.rows >= ops.F16X3_MIN_ROWS and self._f16_ok
 
     def forward(self, x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """f16x3 trunk (large row counts: the step is bound by the GPU)."""
         pairs = [(lin.weight, lin.bias) for lin in self.linears]
-        if ops.GEMM_PRECISION == 2 and x.shape[0] >= ops.F16X3_MIN_ROWS and F.f16x3_supported(*zip(*pairs)):
-            _, acts = F.f16_trunk_forward(x, pairs, self.act, True)
-            self.acts[-1] = acts[-1]
-            return ops.head_fwd(acts[-1], self.head.weight, self.head.bias, out=out)
+        _, acts = F.f16_trunk_forward(x, pairs, self.act, True)
+        self.acts[-1] = acts[-1]
+        return ops.head_fwd(acts[-1], self.head.weight, self.head.bias, out=out)
+
+    # ---- bound 3xTF32 launches ------------------------------------------------------------------------------------------------
+    def _bind(self, wps) -> None:
+        lib = _lib.load()
+        self._linear_fn, self._head_fn = lib.cusrl_b200_linear_fwd_tf32, lib.cusrl_b200_head_fwd_f32
         precision = ops.tf32_passes()
-        h = x
-        for lin, buf in zip(self.linears, self.acts):
-            h = ops.tc_linear_fwd(h, ops.prepared_weight(lin.weight), lin.bias, lin.out_features, self.act, precision, out=buf)
-        return ops.head_fwd(h, self.head.weight, self.head.bias, out=out)
+        f32 = torch.float32
+        calls = []
+        src = None
+        for lin, wp, buf in zip(self.linears, wps, self.acts):
+            yp, ldy = ops._rows(buf, "y")
+            tail = (wp["hi"].data_ptr(), wp["lo"].data_ptr(), wp["hi"].stride(0), ops._ptr(lin.bias, f32, "bias"), yp, ldy,
+                    self.rows, lin.out_features, lin.in_features, self.act, precision)
+            calls.append(tail if src is None else src + tail)
+            src = (yp, ldy)
+        self._first, self._rest = calls[0], calls[1:]
+        head = self.head
+        No, K = head.weight.shape
+        self._head_args = (src[0], src[1], ops._ptr(head.weight.detach(), f32, "weight"),
+                           ops._ptr(None if head.bias is None else head.bias.detach(), f32, "bias"))
+        self._head_tail = (self.rows, K, No)
+        self._wps = wps
+
+    def launch(self, x_ptr: int, ldx: int, out_ptr: int, stream: int) -> None:
+        """Trunk + head into the dense ``[rows, No]`` slot at `out_ptr`; `x_ptr` / `ldx`: fp32 input rows (validated by the
+        caller once per slot)."""
+        stamp = (ops._weights_epoch, *[w._version for w in self._weights])
+        ptrs = [p.data_ptr() for p in self._params]
+        if stamp != self._stamp or ptrs != self._ptrs:
+            wps = [ops.prepared_weight(w) for w in self._weights]   # re-splits the stale ones
+            if ptrs != self._ptrs or self._wps is None or any(a is not b for a, b in zip(wps, self._wps)):
+                self._bind(wps)
+            self._stamp, self._ptrs = stamp, ptrs
+        fn = self._linear_fn
+        code = fn(x_ptr, ldx, *self._first, stream)
+        if code:
+            _lib.check(code, "linear_fwd")
+        for args in self._rest:
+            code = fn(*args, stream)
+            if code:
+                _lib.check(code, "linear_fwd")
+        code = self._head_fn(*self._head_args, out_ptr, *self._head_tail, stream)
+        if code:
+            _lib.check(code, "head_fwd")
+        _lib.KERNEL_LAUNCHES += 2 + len(self._rest)
+
+
+class _StepSlots:
+    """The slots of ONE buffer step with their addresses resolved (views kept alive: they also go into the transition)."""
+
+    __slots__ = ("views", "obs", "state", "prev_next_obs", "prev_next_state", "mean", "std", "action", "logp", "value",
+                 "store_obs", "store_state", "store_tail", "transition_act", "transition_step")
 
 
 class FusedRollout:
     REQUIRE_CUDA = True   # tools/host_overhead_cpu.py (kernels stubbed out) clears it to drive this control flow on the CPU
+
+    _NARROW = ("action_dist.mean", "action_dist.std", "action", "action_logp", "value", "reward", "terminated", "truncated", "done")
 
     def __init__(self, agent):
         self.agent = agent
@@ -87,6 +153,9 @@ class FusedRollout:
         self._prev_next_state: Any = None
         self._acted_fast = False
         self.fast_steps = 0
+        self._layout_key: Any = None         # (buffer.layout_version, number of leaves) the cached decisions below belong to
+        self._layout_ok = False
+        self._slots: dict[int, _StepSlots] = {}
 
     # ---- applicability ---------------------------------------------------------------------------------------------------
     def _supported(self) -> bool:
@@ -114,19 +183,36 @@ class FusedRollout:
                 return False
         return any(isinstance(h, ValueComputation) for h in agent.hook)
 
-    def _ready(self) -> bool:
-        agent = self.agent
-        if not self.enabled or agent.inference_mode:
-            return False
-        storage = agent.buffer.storage
+    def _needed_leaves(self) -> list[str]:
         need = ["observation", "action_dist.mean", "action_dist.std", "action", "action_logp", "value", "next_observation",
                 "reward", "terminated", "truncated", "done"]
-        if agent.has_state:
+        if self.agent.has_state:
             need += ["state", "next_state"]
+        return need
+
+    def _layout_supported(self) -> bool:
+        storage = self.agent.buffer.storage
+        need = self._needed_leaves()
         if not all(k in storage for k in need):
             return False  # not allocated yet: the generic path's first push does that
         extra = set(storage) - set(need) - {"next_value", "advantage", "return"}
-        return not extra  # leaves this path does not know how to fill (user transition fields)
+        if extra:
+            return False  # leaves this path does not know how to fill (user transition fields)
+        return all(storage[k].is_contiguous() for k in self._NARROW)   # their kernels write dense rows
+
+    def _sync_layout(self) -> bool:
+        """Decisions and resolved slot addresses are cached per buffer layout (leaves are allocated by the first pushes and
+        then stay put); any allocation / removal of a leaf drops them."""
+        buffer = self.agent.buffer
+        key = (buffer.layout_version, len(buffer.storage))
+        if key != self._layout_key:
+            self._layout_key = key
+            self._slots = {}
+            self._layout_ok = self._layout_supported()
+        return self._layout_ok
+
+    def _ready(self) -> bool:
+        return self.enabled and not self.agent.inference_mode and self._sync_layout()
 
     def _input_ok(self, x, width: int, dtype=torch.float32) -> bool:
         return (isinstance(x, torch.Tensor) and x.dtype == dtype and x.dim() == 2 and x.shape[0] == self.agent.parallelism
@@ -147,15 +233,53 @@ class FusedRollout:
     def _slot(self, key: str, t: int) -> torch.Tensor:
         return self.agent.buffer.storage[key][t]
 
+    def _step_slots(self, t: int) -> _StepSlots:
+        """Views and addresses of buffer step `t`, resolved once per buffer layout (was: ~25 ``storage[key][t]`` views and as
+        many pointer / stride / dtype look-ups per environment step)."""
+        slots = self._slots.get(t)
+        if slots is not None:
+            return slots
+        agent = self.agent
+        storage, T = agent.buffer.storage, agent.buffer.capacity
+        f32 = torch.float32
+        s = _StepSlots()
+        v = s.views = {k: storage[k][t] for k in self._needed_leaves()}
+        s.obs = ops._rows(v["observation"], "observation slot")
+        s.prev_next_obs = ops._rows(storage["next_observation"][(t - 1) % T], "next_observation slot")
+        s.state = s.prev_next_state = None
+        if agent.has_state:
+            s.state = ops._rows(v["state"], "state slot")
+            s.prev_next_state = ops._rows(storage["next_state"][(t - 1) % T], "next_state slot")
+        s.mean, s.std, s.action, s.logp, s.value = (ops._ptr(v[k], f32, k + " slot") for k in (
+            "action_dist.mean", "action_dist.std", "action", "action_logp", "value"))
+        s.store_obs = (*ops._rows(v["next_observation"], "next_observation slot"), agent.observation_dim)
+        s.store_state = ((*ops._rows(v["next_state"], "next_state slot"), agent.state_dim) if agent.has_state
+                         else (None, 0, 0))
+        s.store_tail = (ops._flag_ptr(v["terminated"], "terminated slot"), ops._flag_ptr(v["truncated"], "truncated slot"),
+                        ops._flag_ptr(v["done"], "done slot"), agent.parallelism)
+        s.transition_act = {"observation": v["observation"], "action_dist": {"mean": v["action_dist.mean"], "std": v["action_dist.std"]},
+                            "action": v["action"], "action_logp": v["action_logp"], "value": v["value"]}
+        if agent.has_state:
+            s.transition_act["state"] = v["state"]
+        s.transition_step = {k: v[k] for k in ("next_observation", "reward", "terminated", "truncated", "done")}
+        if agent.has_state:
+            s.transition_step["next_state"] = v["next_state"]
+        self._slots[t] = s
+        return s
+
     def _fill_wide(self, key: str, t: int, value: torch.Tensor, prev_obj: Any, prev_key: str) -> torch.Tensor:
-        slot = self._slot(key, t)
-        T = self.agent.buffer.capacity
+        slots = self._step_slots(t)
+        wide_state = key == "state"
+        dst = slots.state if wide_state else slots.obs
         if prev_obj is not None and _same_array(value, prev_obj):
             # the array the caller passed to step() one call ago: already on the device in the previous step's slot
-            ops.copy_rows_padded(self._slot(prev_key, (t - 1) % T), slot)
+            src = slots.prev_next_state if wide_state else slots.prev_next_obs
         else:
-            ops.copy_rows_padded(self._device_rows(value, key), slot)
-        return slot
+            rows = self._device_rows(value, key)
+            src = (rows.data_ptr(), rows.stride(0))
+        code = _lib.load().cusrl_b200_copy_rows_padded_f32(*src, *dst, value.shape[0], value.shape[1], ops._stream())
+        _lib.check(code, "copy_rows_padded")
+        return slots.views[key]
 
     # ---- act ------------------------------------------------------------------------------------------------------------------
     def act(self, observation, state):
@@ -171,25 +295,36 @@ class FusedRollout:
             self._nets = (_Net(agent.actor.backbone, agent.actor.distribution.mean_head, n, dev),
                           _Net(agent.critic.backbone, agent.critic.value_head, n, dev))
         t = agent.buffer.cursor
+        slots = self._step_slots(t)
+        views = slots.views
         tr = agent.transition
         tr.clear()
         obs_slot = self._fill_wide("observation", t, observation, self._prev_next_obs, "next_observation")
-        tr["observation"] = obs_slot
-        critic_in = obs_slot
+        critic_in, critic_rows = obs_slot, slots.obs
         if state is not None:
-            critic_in = self._fill_wide("state", t, state, self._prev_next_state, "next_state")
-            tr["state"] = critic_in
+            critic_in, critic_rows = self._fill_wide("state", t, state, self._prev_next_state, "next_state"), slots.state
         actor_net, critic_net = self._nets
-        mean = actor_net.forward(obs_slot, self._slot("action_dist.mean", t))
+        mean = views["action_dist.mean"]
+        if actor_net.uses_f16x3():
+            actor_net.forward(obs_slot, mean)
+        else:
+            actor_net.launch(*slots.obs, slots.mean, ops._stream())
         agent.actor.intermediate_repr["backbone.output"] = actor_net.acts[-1]
-        std, action, logp = self._slot("action_dist.std", t), self._slot("action", t), self._slot("action_logp", t)
         eps = None if agent.deterministic else M.standard_normal_like(mean)
-        ops.sample_logp(mean, agent.actor.distribution.std.param.detach(), eps, std, action, logp, agent.deterministic)
-        tr["action_dist"] = {"mean": mean, "std": std}
-        tr["action"], tr["action_logp"] = action, logp
-        tr["value"] = critic_net.forward(critic_in, self._slot("value", t))
+        code = _lib.load().cusrl_b200_sample_logp_f32(
+            slots.mean, ops._ptr(agent.actor.distribution.std.param.detach(), torch.float32, "sigma"),
+            ops._ptr(eps, torch.float32, "eps"), mean.shape[0], mean.shape[1], int(agent.deterministic), slots.std, slots.action,
+            slots.logp, ops._stream())
+        _lib.check(code, "sample_logp")
+        if critic_net.uses_f16x3():
+            critic_net.forward(critic_in, views["value"])
+        else:
+            critic_net.launch(*critic_rows, slots.value, ops._stream())
         agent.critic.intermediate_repr["backbone.output"] = critic_net.acts[-1]
+        tr.update(slots.transition_act)
+        tr["action_dist"] = dict(slots.transition_act["action_dist"])   # a private dict per step, like the generic flow
         self._acted_fast = True
+        action = views["action"]
         if observation.is_cuda:
             return action.clone()   # the slot is overwritten one rollout later: hand out a private copy
         return action.to(device=observation.device)
@@ -202,30 +337,33 @@ class FusedRollout:
         if not self._acted_fast:
             return False
         self._acted_fast = False
-        n = agent.parallelism
         ok = (not any(v is not None for v in kwargs.values()) and self._input_ok(next_observation, agent.observation_dim)
               and self._input_ok(reward, agent.value_dim) and self._input_ok(terminated, 1, torch.bool)
               and self._input_ok(truncated, 1, torch.bool)
               and (agent.has_state == (next_state is not None))
               and (next_state is None or self._input_ok(next_state, agent.state_dim)))
-        if not ok:
+        if not ok or not self._sync_layout():
             # the generic step must find the act outputs in the transition dict: they are the slot views, and push()
             # recognises tensors that already live in their slot
             return False
         t = agent.buffer.cursor
-        tr = agent.transition
-        slots = {k: self._slot(k, t) for k in ("next_observation", "reward", "terminated", "truncated", "done")}
-        ns_slot = self._slot("next_state", t) if next_state is not None else None
-        ops.rollout_store_step(
-            self._device_rows(next_observation, "next_observation"), slots["next_observation"],
-            None if next_state is None else self._device_rows(next_state, "next_state"), ns_slot,
-            self._device_rows(reward.contiguous(), "reward"), slots["reward"],
-            self._device_rows(terminated.contiguous(), "terminated"), self._device_rows(truncated.contiguous(), "truncated"),
-            slots["terminated"], slots["truncated"], slots["done"])
-        tr.update(next_observation=slots["next_observation"], reward=slots["reward"], terminated=slots["terminated"],
-                  truncated=slots["truncated"], done=slots["done"])
-        if ns_slot is not None:
-            tr["next_state"] = ns_slot
+        slots = self._step_slots(t)
+        views = slots.views
+        obs_rows = self._device_rows(next_observation, "next_observation")
+        if next_state is None:
+            state_src = (None, 0)
+        else:
+            state_rows = self._device_rows(next_state, "next_state")
+            state_src = (state_rows.data_ptr(), state_rows.stride(0))
+        f32 = torch.float32
+        code = _lib.load().cusrl_b200_rollout_store_step_f32(
+            obs_rows.data_ptr(), obs_rows.stride(0), *slots.store_obs, *state_src, *slots.store_state,
+            ops._ptr(self._device_rows(reward.contiguous(), "reward"), f32, "reward"), ops._ptr(views["reward"], f32, "reward slot"),
+            reward.shape[-1],
+            ops._flag_ptr(self._device_rows(terminated.contiguous(), "terminated"), "terminated"),
+            ops._flag_ptr(self._device_rows(truncated.contiguous(), "truncated"), "truncated"), *slots.store_tail, ops._stream())
+        _lib.check(code, "rollout_store_step")
+        agent.transition.update(slots.transition_step)
         self._prev_next_obs = (next_observation, _fingerprint(next_observation))
         self._prev_next_state = None if next_state is None else (next_state, _fingerprint(next_state))
         agent.buffer.advance()
@@ -283,21 +421,16 @@ class FusedRecurrentRollout(FusedRollout):
     _MEMORY_LEAVES = ("actor_memory.hidden", "actor_memory.cell", "critic_memory.hidden", "critic_memory.cell",
                       "next_critic_memory.hidden", "next_critic_memory.cell")
 
+    def _needed_leaves(self) -> list[str]:
+        return [*super()._needed_leaves(), *self._MEMORY_LEAVES]
+
     def _ready(self) -> bool:
         agent = self.agent
         if not self.enabled or agent.inference_mode:
             return False
         if agent.actor_memory is None or self._value_hook._critic_memory is None:
             return False
-        storage = agent.buffer.storage
-        need = ["observation", "action_dist.mean", "action_dist.std", "action", "action_logp", "value", "next_observation",
-                "reward", "terminated", "truncated", "done", *self._MEMORY_LEAVES]
-        if agent.has_state:
-            need += ["state", "next_state"]
-        if not all(k in storage for k in need):
-            return False
-        extra = set(storage) - set(need) - {"next_value", "advantage", "return"}
-        return not extra
+        return self._sync_layout()
 
     @staticmethod
     def _head(latent: torch.Tensor, head: torch.nn.Linear, out: torch.Tensor) -> torch.Tensor:

@@ -26,6 +26,7 @@ ap.add_argument("--count-ops", action="store_true", help="count ATen operators d
 ap.add_argument("--graphs", action="store_true",
                 help="drive the CUDA-graph runner with torch.cuda.graph mocked (capture = run the host code, replay = "
                      "nothing): checks its control flow and shows the host time a replayed step costs")
+ap.add_argument("--rollout-only", action="store_true", help="time only the 24 x (act, step) of an iteration")
 args = ap.parse_args()
 
 real = _lib.load()
@@ -119,6 +120,17 @@ if pr:
 times = []
 for _ in range(args.iters):
     t0 = time.perf_counter()
+    if args.rollout_only:
+        for t in range(data.T):
+            agent.act(data.obs[t])
+            agent.step(data.obs[t + 1], data.reward[t], data.terminated[t], data.truncated[t])
+        times.append(time.perf_counter() - t0)
+        if pr:
+            pr.disable()
+        agent.update()
+        if pr:
+            pr.enable()
+        continue
     run_iteration(agent, data)
     times.append(time.perf_counter() - t0)
 if pr:
