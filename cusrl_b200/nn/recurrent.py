@@ -171,6 +171,7 @@ class Rnn(Module):
     """LSTM backbone with the reference's memory convention (``Rnn.forward``, rnn.py:200-250)."""
 
     Factory = RnnFactory
+    REQUIRE_CUDA = True   # tools/host_overhead_cpu.py (kernels stubbed out) clears it to drive the inference path on the CPU
 
     def __init__(self, rnn: nn.LSTM):
         if rnn.hidden_size % 4:
@@ -201,7 +202,7 @@ class Rnn(Module):
         for d in batch_shape:
             n_rows *= d
         x = input.reshape(T, n_rows, input.shape[-1])
-        if not torch.is_grad_enabled() and x.is_cuda and ops.lstm_seq_supported(H):
+        if not torch.is_grad_enabled() and (x.is_cuda or not self.REQUIRE_CUDA) and ops.lstm_seq_supported(H):
             return self._forward_inference(input, x, memory, done, T, n_rows, batch_shape, sequential)
         # only a SEQUENCE input can carry a per-step memory; a single step with extra batch dims ([N, V, C]) must not be cut
         h0, c0 = self._initial(memory, input.shape[:-1] if (sequential and input.dim() >= 3) else None, n_rows, input.device)

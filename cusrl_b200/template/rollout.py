@@ -22,6 +22,7 @@ through the generic path: its ``Buffer.push`` is what allocates the leaves.
 
 from __future__ import annotations
 
+import os
 from typing import Any
 
 import torch
@@ -107,9 +108,8 @@ class _Net:
         self._head_tail = (self.rows, K, No)
         self._wps = wps
 
-    def launch(self, x_ptr: int, ldx: int, out_ptr: int, stream: int) -> None:
-        """Trunk + head into the dense ``[rows, No]`` slot at `out_ptr`; `x_ptr` / `ldx`: fp32 input rows (validated by the
-        caller once per slot)."""
+    def refresh(self) -> None:
+        """Re-split stale operand copies (on the CURRENT stream) and re-bind the launches if anything moved."""
         stamp = (ops._weights_epoch, *[w._version for w in self._weights])
         ptrs = [p.data_ptr() for p in self._params]
         if stamp != self._stamp or ptrs != self._ptrs:
@@ -117,6 +117,13 @@ class _Net:
             if ptrs != self._ptrs or self._wps is None or any(a is not b for a, b in zip(wps, self._wps)):
                 self._bind(wps)
             self._stamp, self._ptrs = stamp, ptrs
+
+    def launch(self, x_ptr: int, ldx: int, out_ptr: int, stream: int, refresh: bool = True) -> None:
+        """Trunk + head into the dense ``[rows, No]`` slot at `out_ptr`, on `stream`; `x_ptr` / `ldx`: fp32 input rows
+        (validated by the caller once per slot).  `refresh=False`: the caller has called :meth:`refresh` itself (it must run on
+        the stream that owns the operand copies, which need not be `stream`)."""
+        if refresh:
+            self.refresh()
         fn = self._linear_fn
         code = fn(x_ptr, ldx, *self._first, stream)
         if code:
@@ -153,6 +160,10 @@ class FusedRollout:
         self._prev_next_state: Any = None
         self._acted_fast = False
         self.fast_steps = 0
+        # CUSRL_B200_ROLLOUT_STREAMS=1: actor and critic of a step on one stream (the default puts the critic on a second one
+        # when the step is latency-bound, see act)
+        self._two_streams = agent.device.type == "cuda" and os.environ.get("CUSRL_B200_ROLLOUT_STREAMS", "2") == "2"
+        self._streams: Any = None
         self._layout_key: Any = None         # (buffer.layout_version, number of leaves) the cached decisions below belong to
         self._layout_ok = False
         self._slots: dict[int, _StepSlots] = {}
@@ -233,6 +244,14 @@ class FusedRollout:
     def _slot(self, key: str, t: int) -> torch.Tensor:
         return self.agent.buffer.storage[key][t]
 
+    def _stream_objects(self):
+        """(fork event, join event, side stream) of the two-stream act, created on first use."""
+        if self._streams is None:
+            device = self.agent.device
+            with torch.cuda.device(device):
+                self._streams = (torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Stream(device=device))
+        return self._streams
+
     def _step_slots(self, t: int) -> _StepSlots:
         """Views and addresses of buffer step `t`, resolved once per buffer layout (was: ~25 ``storage[key][t]`` views and as
         many pointer / stride / dtype look-ups per environment step)."""
@@ -305,6 +324,18 @@ class FusedRollout:
             critic_in, critic_rows = self._fill_wide("state", t, state, self._prev_next_state, "next_state"), slots.state
         actor_net, critic_net = self._nets
         mean = views["action_dist.mean"]
+        join = None
+        if self._two_streams and not critic_net.uses_f16x3():
+            # small row counts: a step is a chain of ~11 launch-latency-bound kernels, and the critic's four do not depend on
+            # the actor's six -- they run on a second stream, forked after the observation reached its slot and joined before
+            # act() returns (every later consumer of the value slot / the critic's activations is ordered after the join)
+            critic_net.refresh()   # on the main stream: other consumers of the operand copies live there
+            main = torch.cuda.current_stream()
+            fork, join, side = self._stream_objects()
+            fork.record(main)
+            side.wait_event(fork)
+            critic_net.launch(*critic_rows, slots.value, side.cuda_stream, refresh=False)
+            join.record(side)
         if actor_net.uses_f16x3():
             actor_net.forward(obs_slot, mean)
         else:
@@ -316,7 +347,9 @@ class FusedRollout:
             ops._ptr(eps, torch.float32, "eps"), mean.shape[0], mean.shape[1], int(agent.deterministic), slots.std, slots.action,
             slots.logp, ops._stream())
         _lib.check(code, "sample_logp")
-        if critic_net.uses_f16x3():
+        if join is not None:
+            main.wait_event(join)
+        elif critic_net.uses_f16x3():
             critic_net.forward(critic_in, views["value"])
         else:
             critic_net.launch(*critic_rows, slots.value, ops._stream())

@@ -62,6 +62,7 @@ import cusrl_b200 as C  # noqa: E402
 from cusrl_b200.template.rollout import FusedRollout  # noqa: E402
 
 FusedRollout.REQUIRE_CUDA = False
+C.Rnn.REQUIRE_CUDA = False
 from bench import RolloutData, run_iteration  # noqa: E402
 
 dev = torch.device("cpu")
