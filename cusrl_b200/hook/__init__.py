@@ -1,4 +1,5 @@
 from .auxiliary import RandomNetworkDistillation
+from .control import EmptyCudaCache
 from .mdp import ObservationNanToNum, ObservationNormalization
 from .symmetry import (
     MirrorDef,
@@ -27,6 +28,7 @@ __all__ = [
     "AdaptiveLRSchedule",
     "AdvantageNormalization",
     "AdvantageReduction",
+    "EmptyCudaCache",
     "EntropyLoss",
     "GeneralizedAdvantageEstimation",
     "GradientClipping",

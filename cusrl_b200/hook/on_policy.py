@@ -84,31 +84,69 @@ def _leaf(buffer: Buffer, name: str, like: Tensor) -> Tensor:
 
 # =================================================================================================
 class ModuleInitialization(Hook):
-    """Orthogonal initialisation of linear layers at ``init`` (reference hook/control/initialization.py:66-125).
-    The Anymal preset sets ``orthogonal_init=False`` (zoo/isaaclab/locomotion.py:56) -> no-op there."""
+    """Orthogonal initialisation at ``init`` of the linear AND recurrent layers (and attention / convolution layers of user
+    modules) of actor and critic (reference hook/control/initialization.py:11-125: same arguments, same per-module rules,
+    same traversal order -> same consumption of the random stream).  The Anymal preset sets ``orthogonal_init=False``
+    (zoo/isaaclab/locomotion.py:56) -> no-op there; the recurrent preset keeps the default, so its LSTM weights are
+    orthogonal with gain sqrt(2) and its biases zero."""
 
     def __init__(self, scale: float = math.sqrt(2), scale_dist: float = math.sqrt(2) * 0.1, zero_bias: bool = True,
+                 conv_a: float = 0.0, conv_mode: str = "fan_in", conv_nonlinearity: str = "leaky_relu",
                  init_actor: bool = True, init_critic: bool = True):
         super().__init__()
         self.scale, self.scale_dist, self.zero_bias = scale, scale_dist, zero_bias
+        self.conv_a, self.conv_mode, self.conv_nonlinearity = conv_a, conv_mode, conv_nonlinearity
         self.init_actor, self.init_critic = init_actor, init_critic
-
-    def _init_linear(self, module: nn.Linear, gain: float) -> None:
-        nn.init.orthogonal_(module.weight, gain=gain)
-        if self.zero_bias and module.bias is not None:
-            nn.init.zeros_(module.bias)
 
     def init(self) -> None:
         if self.init_actor:
-            for m in self.agent.actor.modules():
-                if isinstance(m, nn.Linear):
-                    self._init_linear(m, self.scale)
+            for module in self.agent.actor.modules():
+                self._init_module(module, self.scale, self.zero_bias)
             if self.scale_dist != self.scale:
-                self._init_linear(self.agent.actor.distribution.mean_head, self.scale_dist)
+                self._init_linear(self.agent.actor.distribution.mean_head, self.scale_dist, self.zero_bias)
         if self.init_critic:
-            for m in self.agent.critic.modules():
-                if isinstance(m, nn.Linear):
-                    self._init_linear(m, self.scale)
+            for module in self.agent.critic.modules():
+                self._init_module(module, self.scale, self.zero_bias)
+
+    def _init_module(self, module: nn.Module, scale: float, zero_bias: bool) -> None:
+        if isinstance(module, nn.Linear):
+            self._init_linear(module, scale, zero_bias)
+        elif isinstance(module, (nn.RNN, nn.LSTM, nn.GRU)):
+            self._init_rnn(module, scale, zero_bias)
+        elif isinstance(module, nn.MultiheadAttention):
+            self._init_mha(module, scale, zero_bias)
+        elif isinstance(module, nn.Conv2d):
+            self._init_conv2d(module, zero_bias)
+
+    @staticmethod
+    def _zero(*tensors) -> None:
+        for tensor in tensors:
+            if tensor is not None:
+                nn.init.zeros_(tensor)
+
+    def _init_linear(self, module: nn.Linear, scale: float, zero_bias: bool) -> None:
+        nn.init.orthogonal_(module.weight, gain=scale)
+        if zero_bias:
+            self._zero(module.bias)
+
+    def _init_rnn(self, module: nn.RNNBase, scale: float, zero_bias: bool) -> None:
+        for layer in range(module.num_layers):   # recurrent matrix first, like the reference (random-stream order)
+            for kind in ("hh", "ih"):
+                nn.init.orthogonal_(getattr(module, f"weight_{kind}_l{layer}"), gain=scale)
+            if zero_bias:
+                self._zero(getattr(module, f"bias_hh_l{layer}", None), getattr(module, f"bias_ih_l{layer}", None))
+
+    def _init_mha(self, module: nn.MultiheadAttention, scale: float, zero_bias: bool) -> None:
+        packed = module.in_proj_weight is not None
+        for weight in ((module.in_proj_weight,) if packed else (module.q_proj_weight, module.k_proj_weight, module.v_proj_weight)):
+            nn.init.orthogonal_(weight, gain=scale)
+        if zero_bias:
+            self._zero(module.in_proj_bias, module.bias_k, module.bias_v)
+
+    def _init_conv2d(self, module: nn.Conv2d, zero_bias: bool) -> None:
+        nn.init.kaiming_normal_(module.weight, a=self.conv_a, mode=self.conv_mode, nonlinearity=self.conv_nonlinearity)
+        if zero_bias:
+            self._zero(module.bias)
 
 
 # =================================================================================================

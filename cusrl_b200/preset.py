@@ -28,7 +28,7 @@ def ppo_hook_suite(
     gae_lamda_value: float | None = None, normalize_advantage: bool = True, value_loss_weight: float = 0.5,
     value_loss_clip: float | None = None, surrogate_clip_ratio: float = 0.2, surrogate_loss_weight: float = 1.0,
     entropy_loss_weight: float = 0.01, max_grad_norm: float | None = 1.0, grad_clip_groups: dict[str, float] | None = None,
-    desired_kl_divergence: float | None = None, max_kl_divergence: float | None = None,
+    desired_kl_divergence: float | None = None, max_kl_divergence: float | None = None, empty_cuda_cache: bool = False,
 ) -> list:
     """Same order as the reference's ``ppo_hook_suite`` (preset/ppo.py:37-65)."""
     hooks = [
@@ -45,6 +45,7 @@ def ppo_hook_suite(
         H.OnPolicyStatistics(sampler=AutoMiniBatchSampler()),
         (H.AdaptiveLRSchedule(desired_kl_divergence, max_kl_divergence=max_kl_divergence)
          if desired_kl_divergence is not None else None),
+        H.EmptyCudaCache() if empty_cuda_cache else None,
     ]
     return [h for h in hooks if h is not None]
 

@@ -464,3 +464,69 @@ def test_advantage_reduction_weighted_sum_mean_and_weight_updates():
     with pytest.raises(ValueError, match="Unsupported reduction"):
         C.AdvantageReduction(reduction="max")
     assert mean.name == "advantage_reduction" and mean.training_only
+
+
+def test_module_initialization_rules_like_the_reference_tests():
+    """cusrl_test/hook/control/test_module_initialization.py:19-45 against this hook: orthogonal rows with the requested
+    gains, zero biases, the distribution head's own gain, and recurrent layers without biases."""
+    import math
+    from types import SimpleNamespace
+
+    from torch import nn
+
+    class Actor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = nn.Linear(3, 2)
+            self.distribution = nn.Module()
+            self.distribution.mean_head = nn.Linear(2, 1)
+
+    actor = Actor()
+    critic = nn.Sequential(nn.Linear(3, 2), nn.ReLU(), nn.Linear(2, 1))
+    hook = C.ModuleInitialization(scale=math.sqrt(2), scale_dist=0.1, zero_bias=True)
+    hook.agent = SimpleNamespace(actor=actor, critic=critic)
+    hook.init()
+    assert torch.allclose(actor.backbone.bias, torch.zeros_like(actor.backbone.bias))
+    assert torch.allclose(actor.distribution.mean_head.bias, torch.zeros_like(actor.distribution.mean_head.bias))
+    assert torch.allclose(critic[0].bias, torch.zeros_like(critic[0].bias))
+    assert actor.distribution.mean_head.weight.norm().item() == pytest.approx(0.1)
+    assert critic[0].weight[0].norm().item() == pytest.approx(math.sqrt(2))
+    for rnn_cls, gates in ((nn.RNN, 1), (nn.GRU, 3), (nn.LSTM, 4)):
+        module = rnn_cls(input_size=3, hidden_size=4, num_layers=2, bias=False)
+        C.ModuleInitialization()._init_module(module, scale=1.0, zero_bias=True)
+        for layer in range(module.num_layers):
+            w = getattr(module, f"weight_hh_l{layer}")
+            assert w.shape == (4 * gates, 4) and not hasattr(module, f"bias_hh_l{layer}")
+            assert torch.allclose(w.T @ w, torch.eye(4), atol=1e-5)           # orthonormal columns, gain 1
+
+
+def test_ppo_hook_suite_options_like_the_reference_tests():
+    """cusrl_test/preset/test_ppo.py:16-36: optional hooks appear exactly when switched on, in the reference's order."""
+    hooks = C.ppo_hook_suite(normalize_observation=True, desired_kl_divergence=0.01, max_kl_divergence=0.02, empty_cuda_cache=True)
+    kinds = [type(h) for h in hooks]
+    assert C.ObservationNormalization in kinds and C.AdaptiveLRSchedule in kinds and C.EmptyCudaCache in kinds
+    assert kinds[-1] is C.EmptyCudaCache and kinds[1] is C.ObservationNormalization and all(h is not None for h in hooks)
+    assert hooks[-1].name == "empty_cuda_cache"
+    hooks[-1].post_update()                                   # a no-op without a GPU, must not raise
+    kinds = {type(h) for h in C.ppo_hook_suite(normalize_observation=False, desired_kl_divergence=None, empty_cuda_cache=False)}
+    assert not kinds & {C.ObservationNormalization, C.AdaptiveLRSchedule, C.EmptyCudaCache}
+
+
+def test_metrics_like_the_reference_tests():
+    """cusrl_test/utils/test_metrics.py:7-38: count-weighted means, prefixed summary keys, empty / None values ignored,
+    conversion errors name the metric."""
+    from cusrl_b200.metrics import Metrics
+
+    metrics = Metrics()
+    metrics.record({"loss": torch.tensor([1.0, 3.0])}, accuracy=0.5, ignored=None)
+    metrics.record(loss=torch.tensor([5.0, 7.0, 9.0]))
+    assert len(metrics) == 2 and metrics["loss"].count == 5
+    assert metrics.summary("train") == pytest.approx({"train/loss": 5.0, "train/accuracy": 0.5})
+    metrics = Metrics()
+    metrics.record(empty=torch.tensor([]), missing=None)
+    assert len(metrics) == 0
+    metrics.record(value=[1.0, 2.0])
+    metrics.clear()
+    assert list(metrics.items()) == []
+    with pytest.raises(ValueError, match="bad_metric"):
+        metrics.record(bad_metric=object())

@@ -226,3 +226,45 @@ def test_export_standalone_torchscript_without_the_reference(tmp_path, monkeypat
     torch.testing.assert_close(traced(obs), agent.actor.distribution.mean_head(h), rtol=1e-6, atol=1e-6)
     with pytest.raises(RuntimeError, match="ONNX export goes through the reference"):
         agent.export(str(tmp_path), target_format="onnx", verbose=False)
+
+
+def test_module_initialization_matches_the_reference_hook_seed_for_seed(reference):
+    """`ModuleInitialization` (cusrl/hook/control/initialization.py:66-125) initialises linear, recurrent, attention and
+    convolution layers; this implementation must draw the same numbers from the same random stream on the same modules --
+    in particular the recurrent preset's LSTM gets orthogonal weights (gain sqrt 2) and zero biases, not torch's default."""
+    from types import SimpleNamespace
+
+    import torch
+    from torch import nn
+
+    import cusrl_b200 as C
+
+    def modules():
+        torch.manual_seed(3)
+        actor = nn.Module()
+        actor.backbone = nn.LSTM(7, 8, 2)
+        actor.distribution = nn.Module()
+        actor.distribution.mean_head = nn.Linear(8, 3)
+        critic = nn.Sequential(nn.GRU(7, 8, 1), nn.Linear(8, 1), nn.MultiheadAttention(8, 2), nn.Conv2d(2, 3, 3))
+        return actor, critic
+
+    results = []
+    for cls in (reference.hook.ModuleInitialization, C.ModuleInitialization):
+        actor, critic = modules()
+        torch.manual_seed(11)
+        hook = cls(scale=1.3, scale_dist=0.05)
+        hook.agent = SimpleNamespace(actor=actor, critic=critic)
+        hook.init()
+        results.append(([p.detach().clone() for m in (actor, critic) for p in m.parameters()], torch.rand(4)))
+    (ref_params, ref_next), (our_params, our_next) = results
+    assert len(ref_params) == len(our_params) and torch.equal(ref_next, our_next)      # same position in the random stream
+    for a, b in zip(ref_params, our_params):
+        assert torch.equal(a, b)
+
+    # and through the recurrent preset: both presets leave an LSTM with orthogonal weights and zero biases
+    spec = C.EnvironmentSpec(4, 19, 5, autoreset=True, final_state_is_missing=True)
+    agent = C.RecurrentPpoAgentFactory(device="cpu", actor_hidden_size=64, critic_hidden_size=64)(spec)
+    lstm = agent.actor.backbone.rnn
+    w_hh = lstm.weight_hh_l0.detach()                       # [4H, H]: orthonormal columns times the gain
+    assert torch.allclose(w_hh.T @ w_hh, 2.0 * torch.eye(64), atol=1e-4)
+    assert float(lstm.bias_ih_l0.abs().max()) == 0.0 and float(lstm.bias_hh_l1.abs().max()) == 0.0
