@@ -87,6 +87,16 @@ class ObservationNormalization(Hook):
         else:
             self.state_rms = None
 
+    def pre_export(self, graph) -> None:
+        """The deployed policy normalises its observation with the frozen running statistics (observation.py:248-255).  The
+        node is a plain-torch twin of ``observation_rms`` (same mean / std / clamp; the B200 module runs kernels and cannot
+        be traced), also when the hook is inactive -- like the reference, export visits every hook."""
+        from ..template.export import _Affine
+
+        rms = self.observation_rms
+        graph.add_node(_Affine(rms.mean, rms.std, getattr(rms, "clamp", None)), module_name="observation_rms",
+                       input_names={"input": "observation"}, output_names="observation", expose_outputs=False)
+
     def pre_act(self, transition) -> None:
         observation, state = transition["observation"], transition.get("state")
         if self._last_done is None or not self.agent.environment_spec.final_state_is_missing:

@@ -101,6 +101,9 @@ class Metrics:
     def keys(self):
         return self._data.keys()
 
+    def values(self):
+        return self._data.values()
+
     def get(self, name: str, default=None):
         return self._data.get(name, default)
 

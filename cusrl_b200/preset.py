@@ -133,9 +133,15 @@ class RecurrentPpoAgentFactory(PpoAgentFactory):
     actor_hidden_size: int = 256
     critic_num_layers: int = 2
     critic_hidden_size: int = 256
+    # The reference defaults this to True (preset/ppo.py:241-243): its recurrent update re-packs variable-length sequences
+    # every minibatch and fragments the caching allocator.  Every tensor of this implementation's update has a static shape
+    # (episode boundaries are in-line resets), so the default is off; True appends the same `EmptyCudaCache` hook.
+    empty_cuda_cache: bool = False
 
     def to_underlying(self) -> ActorCriticFactory:
         base = super().to_underlying()
+        if self.empty_cuda_cache:
+            base.register_hook(H.EmptyCudaCache())
         base.actor_factory = Actor.Factory(
             backbone_factory=Rnn.Factory(self.rnn_type, num_layers=self.actor_num_layers, hidden_size=self.actor_hidden_size),
             distribution_factory=NormalDist.Factory(init_std=self.init_distribution_std))

@@ -339,6 +339,12 @@ class ActorCritic:
             self.record(**objectives)
         self.hook.post_objective(metadata, batch)
 
+    def resize_buffer(self, capacity: int) -> None:
+        """actor_critic.py:327-330: a different rollout length; the leaves are re-allocated by the next pushes."""
+        if self.buffer_capacity != capacity:
+            self.buffer_capacity = capacity
+            self.buffer.resize(capacity)
+
     def set_inference_mode(self, mode: bool = True, deterministic: bool | None = True) -> None:
         self.inference_mode = mode
         if deterministic is not None:

@@ -89,22 +89,40 @@ class PlainActor(nn.Module):
         return action, memory_out
 
 
-def _graph_nodes(agent, with_environment_normalization: bool) -> tuple[list, list]:
-    """(nodes before the actor, nodes after it) as (module, name, input key, output key)."""
+def _spec_nodes(agent, with_environment_normalization: bool) -> tuple[list, list]:
+    """Normalisation the ENVIRONMENT declares (actor_critic.py:353-362,392-401): (nodes before the actor, nodes after it)."""
     spec = agent.environment_spec
     pre, post = [], []
     obs_norm = getattr(spec, "observation_normalization", None)
     if with_environment_normalization and obs_norm is not None:
         pre.append((_Affine(agent.to_tensor(obs_norm[1]), agent.to_tensor(obs_norm[0])), "observation_normalization"))
-    for hook in agent.hook:
-        rms = getattr(hook, "observation_rms", None)
-        if rms is not None and hook.active:   # ObservationNormalization.pre_export (hook/mdp/observation.py:248-255)
-            pre.append((_Affine(rms.mean, rms.std, getattr(rms, "clamp", None)), "observation_rms"))
     act_denorm = getattr(spec, "action_denormalization", None)
     if with_environment_normalization and act_denorm is not None:
         post.append((_Affine(agent.to_tensor(act_denorm[1]), agent.to_tensor(act_denorm[0]), denormalize=True),
                      "action_denormalization"))
     return pre, post
+
+
+class _ChainGraph:
+    """Stand-in for the reference's ``FlowGraph`` when the reference is not importable: records the nodes the hooks' export
+    callbacks add.  Only what a linear chain can express is accepted -- a node that maps ``observation`` to ``observation``
+    (before the actor) or ``action`` to ``action`` (after it); anything else needs the reference's exporter."""
+
+    def __init__(self):
+        self.pre: list = []
+        self.post: list = []
+        self.actor_added = False
+
+    def add_node(self, module, module_name: str, input_names, output_names, **kwargs) -> None:
+        sources = list(input_names.values()) if isinstance(input_names, dict) else list(input_names)
+        outputs = [output_names] if isinstance(output_names, str) else list(output_names)
+        if sources == ["observation"] and outputs == ["observation"] and not self.actor_added:
+            self.pre.append((module, module_name))
+        elif sources == ["action"] and outputs == ["action"] and self.actor_added:
+            self.post.append((module, module_name))
+        else:
+            raise RuntimeError(f"export node '{module_name}' ({sources} -> {outputs}) cannot be expressed without the reference's "
+                               "FlowGraph exporter: run the export with the reference package importable")
 
 
 class _Deployed(nn.Module):
@@ -135,7 +153,7 @@ def export_agent(agent, output_dir: str, *, target_format: str = "onnx", with_en
         raise ValueError(f"Unsupported export format '{target_format}'")
     os.makedirs(output_dir, exist_ok=True)
     actor = PlainActor(agent.actor).eval()
-    pre, post = _graph_nodes(agent, with_environment_normalization)
+    pre, post = _spec_nodes(agent, with_environment_normalization)
     obs_dim = agent.environment_spec.observation_dim
     inputs: dict[str, Any] = {"observation": torch.zeros(sequence_len, batch_size, obs_dim, device=agent.device)}
     try:
@@ -147,6 +165,7 @@ def export_agent(agent, output_dir: str, *, target_format: str = "onnx", with_en
         for module, name in pre:
             graph.add_node(module, module_name=name, input_names={"input": "observation"}, output_names="observation",
                            expose_outputs=False)
+        agent.hook.pre_export(graph)     # e.g. ObservationNormalization adds its running statistics (observation.py:248-255)
         names_in, names_out = {"observation": "observation"}, ["action"]
         if actor.is_recurrent:
             with torch.no_grad():
@@ -159,6 +178,7 @@ def export_agent(agent, output_dir: str, *, target_format: str = "onnx", with_en
                        extra_kwargs={"forward_type": "act_deterministic"},
                        info={"observation_dim": obs_dim, "action_dim": agent.action_dim, "is_recurrent": actor.is_recurrent},
                        expose_outputs=True)
+        agent.hook.post_export(graph)
         for module, name in post:
             graph.add_node(module, module_name=name, input_names={"input": "action"}, output_names="action", expose_outputs=False)
         if target_format == "onnx":
@@ -172,7 +192,11 @@ def export_agent(agent, output_dir: str, *, target_format: str = "onnx", with_en
                                "target_format='jit'")
         import yaml
 
-        deployed = _Deployed(pre, actor, post).eval()
+        chain = _ChainGraph()
+        agent.hook.pre_export(chain)
+        chain.actor_added = True
+        agent.hook.post_export(chain)
+        deployed = _Deployed(pre + chain.pre, actor, chain.post + post).eval()
         example = [inputs["observation"]]
         if actor.is_recurrent:
             with torch.no_grad():

@@ -166,6 +166,13 @@ class Hook:
 
     def apply_schedule(self, iteration: int) -> None: ...
 
+    def pre_export(self, graph) -> None:
+        """Before the actor node is added to the export graph (reference template/hook.py:344-349): a hook that transforms
+        the observation at rollout time adds the same transformation here (``graph.add_node``)."""
+
+    def post_export(self, graph) -> None:
+        """After the actor node was added (template/hook.py:351-356)."""
+
     @classmethod
     def warn(cls, message: str) -> None:
         if distributed.is_main_process():
@@ -292,3 +299,14 @@ class HookComposite(Hook):
     def apply_schedule(self, iteration: int) -> None:
         for hook in self.active_hooks():
             hook.apply_schedule(iteration)
+
+    def pre_export(self, graph) -> None:
+        """Every hook, active or not, like the reference (template/hook.py:473-479)."""
+        for hook in self:
+            if callable(fn := getattr(hook, "pre_export", None)):
+                fn(graph)
+
+    def post_export(self, graph) -> None:
+        for hook in self:
+            if callable(fn := getattr(hook, "post_export", None)):
+                fn(graph)

@@ -530,3 +530,39 @@ def test_metrics_like_the_reference_tests():
     assert list(metrics.items()) == []
     with pytest.raises(ValueError, match="bad_metric"):
         metrics.record(bad_metric=object())
+
+
+def test_small_api_mirrors_resize_buffer_metrics_values_recurrent_empty_cache():
+    """Members of the reference surface that are one-liners but must exist: ``ActorCritic.resize_buffer``
+    (actor_critic.py:327-330), ``Metrics.values`` (utils/metrics.py:53-54), ``RecurrentPpoAgentFactory.empty_cuda_cache``
+    (preset/ppo.py:241-243; off by default here, see preset.py) and the export callbacks on every hook (template/hook.py:344-356)."""
+    from cusrl_b200.metrics import Metrics
+
+    spec = C.EnvironmentSpec(8, 19, 4, autoreset=True, final_state_is_missing=True)
+    agent = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), device="cpu")(spec)
+    agent.buffer.push({"observation": torch.zeros(8, 19)})
+    version = agent.buffer.layout_version
+    agent.resize_buffer(agent.buffer_capacity)                       # same capacity: nothing happens
+    assert agent.buffer.layout_version == version and "observation" in agent.buffer
+    agent.resize_buffer(12)
+    assert agent.buffer_capacity == 12 and agent.buffer.capacity == 12 and "observation" not in agent.buffer
+    assert agent.buffer.layout_version > version
+    metrics = Metrics()
+    metrics.record(a=1.0, b=2.0)
+    assert [m.count for m in metrics.values()] == [1, 1]
+    names = [h.name for h in C.RecurrentPpoAgentFactory(device="cpu", empty_cuda_cache=True).to_underlying().hooks]
+    assert names[-1] == "empty_cuda_cache"
+    assert "empty_cuda_cache" not in [h.name for h in C.RecurrentPpoAgentFactory(device="cpu").to_underlying().hooks]
+    calls = []
+
+    class Probe(C.Hook):
+        def pre_export(self, graph):
+            calls.append(("pre", graph))
+
+        def post_export(self, graph):
+            calls.append(("post", graph))
+
+    composite = C.HookComposite([Probe().active_(False), C.EmptyCudaCache()])      # inactive hooks are visited too
+    composite.pre_export("g")
+    composite.post_export("g")
+    assert calls == [("pre", "g"), ("post", "g")]

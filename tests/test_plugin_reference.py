@@ -268,3 +268,66 @@ def test_module_initialization_matches_the_reference_hook_seed_for_seed(referenc
     w_hh = lstm.weight_hh_l0.detach()                       # [4H, H]: orthonormal columns times the gain
     assert torch.allclose(w_hh.T @ w_hh, 2.0 * torch.eye(64), atol=1e-4)
     assert float(lstm.bias_ih_l0.abs().max()) == 0.0 and float(lstm.bias_hh_l1.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("with_reference", [True, False])
+def test_export_runs_the_hooks_export_callbacks(reference, tmp_path, monkeypatch, with_reference):
+    """``ActorCritic.export`` calls ``hook.pre_export(graph)`` / ``hook.post_export(graph)`` (actor_critic.py:365,390): the
+    B200 ``ObservationNormalization`` adds its running statistics in front of the actor (observation.py:248-255) and a
+    REFERENCE-side user hook appends a node behind it -- through the reference's FlowGraph, and through the stand-in chain
+    when the reference is not importable."""
+    import torch
+    import yaml
+    from torch import nn
+
+    import cusrl_b200 as C
+
+    class Halve(nn.Module):
+        def forward(self, input):
+            return input * 0.5
+
+    class HalveAction(reference.template.Hook):          # the reference's own Hook base class
+        def post_export(self, graph):
+            graph.add_node(Halve(), module_name="halve", input_names={"input": "action"}, output_names="action",
+                           expose_outputs=False)
+
+    torch.manual_seed(8)
+    factory = C.PpoAgentFactory(num_steps_per_update=4, actor_hidden_dims=(32, 64), critic_hidden_dims=(32, 64), activation_fn="ELU",
+                                normalize_observation=True, device="cpu").to_underlying()
+    factory.register_hook(HalveAction())
+    agent = factory(C.EnvironmentSpec(4, 19, 5, autoreset=True, final_state_is_missing=True))
+    rms = agent.hook["observation_normalization"].observation_rms
+    with torch.no_grad():
+        rms.mean.copy_(torch.randn(19))
+        rms.var.copy_(torch.rand(19) + 0.5)
+        rms.std.copy_(rms.var.sqrt())
+    obs = torch.randn(1, 1, 19)
+    h = (obs - rms.mean) / rms.std
+    clamp = getattr(rms, "clamp", None)
+    if clamp is not None:
+        h = h.clamp(-clamp, clamp)
+    for lin in agent.actor.backbone.linears():
+        h = torch.nn.functional.elu(lin(h))
+    want = agent.actor.distribution.mean_head(h) * 0.5
+
+    if with_reference:
+        agent.export(str(tmp_path), target_format="jit", verbose=False)
+        info = yaml.safe_load((tmp_path / "actor.yml").read_text())
+        assert [list(d)[0] for d in info["inputs"]] == ["observation"]
+        got = torch.jit.load(str(tmp_path / "actor_stateless.pt"))(obs)
+        got = got[0] if isinstance(got, (tuple, list)) else got
+        got = got["action"] if isinstance(got, dict) else got
+    else:
+        import builtins
+
+        real_import = builtins.__import__
+
+        def no_reference(name, *a, **k):
+            if name == "cusrl" or name.startswith("cusrl."):
+                raise ImportError(name)
+            return real_import(name, *a, **k)
+
+        monkeypatch.setattr(builtins, "__import__", no_reference)
+        agent.export(str(tmp_path), target_format="jit", verbose=False)
+        got = torch.jit.load(str(tmp_path / "actor.pt"))(obs)
+    torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
