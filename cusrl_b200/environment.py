@@ -10,9 +10,6 @@ Isaac-Velocity-Rough-Anymal-C-v0 shapes (obs 235, act 12, reward 1) named in BAS
 
 from __future__ import annotations
 
-from collections.abc import Callable
-from dataclasses import dataclass
-
 import torch
 
 from .runtime import device as resolve_device
@@ -20,19 +17,54 @@ from .runtime import device as resolve_device
 __all__ = ["EnvironmentSpec", "SyntheticEnvironment"]
 
 
-@dataclass
 class EnvironmentSpec:
-    num_instances: int
-    observation_dim: int
-    action_dim: int
-    state_dim: int | None = None
-    reward_dim: int = 1
-    autoreset: bool = False
-    final_state_is_missing: bool = False
-    # symmetry transforms read by the symmetry hooks and by ObservationNormalization (template/environment.py:130-132,156-158)
-    mirror_action: Callable[[torch.Tensor], torch.Tensor] | None = None
-    mirror_observation: Callable[[torch.Tensor], torch.Tensor] | None = None
-    mirror_state: Callable[[torch.Tensor], torch.Tensor] | None = None
+    """The reference's specification object (cusrl/template/environment.py:24-176): same attribute names and defaults, extra
+    keyword arguments become attributes, ``get(key, default)``.  The hot path reads ``num_instances``, the four dimensions,
+    ``autoreset`` and ``final_state_is_missing``; the symmetry hooks read ``mirror_*``; ``ObservationNormalization`` reads the
+    ``*_stat_groups`` / ``*_excluded_indices`` / ``observation_is_subset_of_state`` fields; ``agent.export`` reads
+    ``observation_normalization`` / ``action_denormalization``.
+
+    Positional arguments: the reference's order ``EnvironmentSpec(observation_dim, action_dim, *, num_instances=1, ...)`` when
+    exactly two are given, and this package's original order ``EnvironmentSpec(num_instances, observation_dim, action_dim,
+    state_dim=None, reward_dim=1, ...)`` otherwise (every call site of the tests and tools)."""
+
+    _POSITIONAL = ("num_instances", "observation_dim", "action_dim", "state_dim", "reward_dim", "autoreset",
+                   "final_state_is_missing", "mirror_action", "mirror_observation", "mirror_state")
+    _DEFAULTS: dict = dict(
+        num_instances=1, state_dim=None, reward_dim=1, action_denormalization=None, action_space=None, autoreset=False,
+        demonstration_sampler=None, device="cpu", environment_instance=None, final_state_is_missing=False, mirror_action=None,
+        mirror_observation=None, mirror_state=None, observation_is_subset_of_state=None, observation_stat_groups=(),
+        observation_normalization=None, observation_normalization_excluded_indices=None, observation_space=None,
+        state_stat_groups=(), state_normalization=None, state_normalization_excluded_indices=None, timestep=None)
+
+    def __init__(self, *args, **kwargs):
+        if len(args) == 2 and "action_dim" not in kwargs:
+            names = ("observation_dim", "action_dim")          # the reference's positional order
+        else:
+            names = self._POSITIONAL
+        if len(args) > len(names):
+            raise TypeError(f"EnvironmentSpec takes at most {len(names)} positional arguments ({len(args)} given)")
+        for name, value in zip(names, args):
+            if name in kwargs:
+                raise TypeError(f"EnvironmentSpec got multiple values for argument '{name}'")
+            kwargs[name] = value
+        for required in ("observation_dim", "action_dim"):
+            if required not in kwargs:
+                raise TypeError(f"EnvironmentSpec missing required argument '{required}'")
+        values = {**self._DEFAULTS, **kwargs}
+        values["device"] = torch.device(values["device"])
+        values["observation_stat_groups"] = tuple(values["observation_stat_groups"])
+        values["state_stat_groups"] = tuple(values["state_stat_groups"])
+        for key, value in values.items():     # unknown keywords become attributes, like the reference's **kwargs
+            setattr(self, key, value)
+
+    def get(self, key: str, default=None):
+        return self.__dict__.get(key, default)
+
+    def __repr__(self) -> str:
+        shown = {k: v for k, v in self.__dict__.items() if k in ("num_instances", "observation_dim", "action_dim", "state_dim",
+                                                                  "reward_dim", "autoreset", "final_state_is_missing")}
+        return "EnvironmentSpec(" + ", ".join(f"{k}={v!r}" for k, v in shown.items()) + ")"
 
 
 class SyntheticEnvironment:

@@ -566,3 +566,25 @@ def test_small_api_mirrors_resize_buffer_metrics_values_recurrent_empty_cache():
     composite.pre_export("g")
     composite.post_export("g")
     assert calls == [("pre", "g"), ("post", "g")]
+
+
+def test_environment_spec_accepts_the_reference_call_styles():
+    """cusrl/template/environment.py:118-176 and cusrl_test/template/test_hook.py:39-43: keyword construction with the
+    reference's field names and defaults, the reference's two positional arguments, extra keywords / attributes, ``get``;
+    and this package's original positional order, which every test and tool uses."""
+    ref_style = C.EnvironmentSpec(35, 12, state_dim=42)
+    assert (ref_style.observation_dim, ref_style.action_dim, ref_style.state_dim, ref_style.num_instances) == (35, 12, 42, 1)
+    assert ref_style.reward_dim == 1 and ref_style.autoreset is False and ref_style.final_state_is_missing is False
+    assert ref_style.device == torch.device("cpu") and ref_style.observation_stat_groups == () and ref_style.timestep is None
+    assert ref_style.observation_normalization is None and ref_style.action_denormalization is None
+    legacy = C.EnvironmentSpec(8, 19, 5, 11, 2, autoreset=True, final_state_is_missing=True)
+    assert (legacy.num_instances, legacy.observation_dim, legacy.action_dim, legacy.state_dim, legacy.reward_dim) == (8, 19, 5, 11, 2)
+    keyword = C.EnvironmentSpec(num_instances=4, observation_dim=3, action_dim=2, observation_stat_groups=[slice(0, 2)], foo=123)
+    assert keyword.foo == 123 and keyword.get("foo") == 123 and keyword.get("bar", 7) == 7
+    assert keyword.observation_stat_groups == (slice(0, 2),)
+    keyword.baz = 5                                          # new attributes can be added later (EnvironmentSpecOverride)
+    assert keyword.get("baz") == 5
+    with pytest.raises(TypeError, match="observation_dim"):
+        C.EnvironmentSpec(3)
+    with pytest.raises(TypeError, match="multiple values"):
+        C.EnvironmentSpec(3, 4, 5, observation_dim=2)
