@@ -48,6 +48,14 @@ class Module(nn.Module):
         self.input_dim, self.output_dim, self.is_recurrent = input_dim, output_dim, is_recurrent
         self.intermediate_repr: dict[str, Any] = {}
 
+    @property
+    def device(self) -> torch.device:
+        """Device of the first parameter, else of the first buffer, else the CPU (module.py:88-97)."""
+        tensor = next(self.parameters(), None)
+        if tensor is None:
+            tensor = next(self.buffers(), None)
+        return torch.device("cpu") if tensor is None else tensor.device
+
     def clear_intermediate_repr(self) -> None:
         self.intermediate_repr.clear()
 
