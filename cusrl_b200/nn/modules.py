@@ -225,9 +225,20 @@ class Actor(Module):
         self.intermediate_repr["backbone.output"] = latent
         return mean, memory
 
-    def forward(self, observation: Tensor, memory=None, done: Tensor | None = None, **kw):
-        mean, memory = self._mean(observation, memory, done)
-        return self.distribution.params_from_mean(mean), memory
+    def forward(self, observation: Tensor, memory=None, done: Tensor | None = None, forward_type: str | None = "forward",
+                deterministic: bool = False, **kw):
+        """Router of the reference's actor (actor.py:70-99): ``forward`` -> (distribution parameters, memory), ``explore`` ->
+        (parameters, (action, log-prob), memory), ``act`` / ``act_deterministic`` -> (action, memory)."""
+        if forward_type == "forward":
+            mean, memory = self._mean(observation, memory, done)
+            return self.distribution.params_from_mean(mean), memory
+        if forward_type == "explore":
+            return self.explore(observation, memory, deterministic)
+        if forward_type == "act":
+            return self.act(observation, memory, deterministic)
+        if forward_type == "act_deterministic":
+            return self.act(observation, memory, True)
+        raise ValueError(f"Unsupported 'forward_type' value: {forward_type!r}")
 
     def explore(self, observation: Tensor, memory=None, deterministic: bool = False, **kw):
         mean, memory = self._mean(observation, memory, None)

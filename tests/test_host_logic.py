@@ -588,3 +588,23 @@ def test_environment_spec_accepts_the_reference_call_styles():
         C.EnvironmentSpec(3)
     with pytest.raises(TypeError, match="multiple values"):
         C.EnvironmentSpec(3, 4, 5, observation_dim=2)
+
+
+def test_actor_forward_type_router(monkeypatch):
+    """The reference's actor routes on ``forward_type`` (nn/module/actor.py:70-99); deployment code (Player, export,
+    InferenceWrapper) calls ``actor(obs, forward_type="act_deterministic")``.  Dispatch only: the kernels need a GPU."""
+    actor = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), device="cpu")(
+        C.EnvironmentSpec(4, 19, 5)).actor
+    calls = []
+    monkeypatch.setattr(type(actor), "explore", lambda self, obs, memory=None, deterministic=False, **kw: calls.append(("explore", deterministic)))
+    monkeypatch.setattr(type(actor), "act", lambda self, obs, memory=None, deterministic=False, **kw: calls.append(("act", deterministic)))
+    obs = torch.zeros(4, 19)
+    actor(obs, forward_type="explore")
+    actor(obs, forward_type="explore", deterministic=True)
+    actor(obs, forward_type="act")
+    actor(obs, forward_type="act_deterministic")
+    assert calls == [("explore", False), ("explore", True), ("act", False), ("act", True)]
+    with pytest.raises(ValueError, match="Unsupported 'forward_type'"):
+        actor(obs, forward_type="sample")
+    with pytest.raises(RuntimeError, match="CUDA"):        # the default route reaches the kernels, which refuse CPU tensors
+        actor(obs)
