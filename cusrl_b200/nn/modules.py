@@ -132,6 +132,17 @@ class StddevVector(nn.Module):
         return self.param.expand(*input.shape[:-1], -1)
 
 
+class _DeterministicWrapper(nn.Module):
+    """``distribution.deterministic()``: latent -> most likely action (distribution.py:181-187)."""
+
+    def __init__(self, distribution: nn.Module):
+        super().__init__()
+        self.dist = distribution
+
+    def forward(self, backbone_feat: Tensor, **kwargs) -> Tensor:
+        return self.dist.determine(backbone_feat, **kwargs)
+
+
 @dataclass(slots=True)
 class NormalDistFactory:
     init_std: float | None = None
@@ -156,6 +167,21 @@ class NormalDist(Module):
 
     def params_from_mean(self, mean: Tensor) -> dict[str, Tensor]:
         return {"mean": mean, "std": self.std(mean)}
+
+    # The reference's Distribution interface (distribution.py:49-178).  The agent does not go through it -- the actor fuses
+    # the mean head into the trunk's autograd node -- but hooks and deployment code may call the distribution on a latent.
+    def forward(self, backbone_feat: Tensor, **kwargs) -> dict[str, Tensor]:
+        return self.params_from_mean(F.linear_head(backbone_feat, self.mean_head.weight, self.mean_head.bias))
+
+    def sample(self, backbone_feat: Tensor, **kwargs) -> tuple[dict[str, Tensor], tuple[Tensor, Tensor]]:
+        dist_params = self(backbone_feat, **kwargs)
+        return dist_params, self.sample_from_dist(dist_params)
+
+    def determine(self, backbone_feat: Tensor, **kwargs) -> Tensor:
+        return self(backbone_feat, **kwargs)["mean"]
+
+    def deterministic(self) -> nn.Module:
+        return _DeterministicWrapper(self)
 
     # torch Normal arithmetic (distribution.py:195-218), kept in torch for the small rollout-time tensors
     @staticmethod

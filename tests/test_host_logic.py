@@ -608,3 +608,30 @@ def test_actor_forward_type_router(monkeypatch):
         actor(obs, forward_type="sample")
     with pytest.raises(RuntimeError, match="CUDA"):        # the default route reaches the kernels, which refuse CPU tensors
         actor(obs)
+
+
+def test_normal_dist_interface_like_the_reference_tests(monkeypatch):
+    """cusrl_test/nn/module/test_distribution.py:7-24 against this NormalDist (identity bijector): shapes of parameters /
+    sample / log-prob / entropy, KL of a distribution with itself, the deterministic wrapper; and the closed forms against
+    torch.distributions.  The mean head is a kernel (CUDA only): it is replaced by torch's linear for this CPU test."""
+    import cusrl_b200.nn.functional as F
+
+    monkeypatch.setattr(F, "linear_head", lambda x, w, b: torch.nn.functional.linear(x, w, b))
+    torch.manual_seed(0)
+    dist = C.NormalDist(input_dim=4, output_dim=2, init_std=0.7)
+    latent = torch.randn(3, 4)
+    params = dist(latent)
+    sample, logp = dist.sample_from_dist(params)
+    assert params["mean"].shape == (3, 2) and params["std"].shape == (3, 2) and sample.shape == (3, 2) and logp.shape == (3, 1)
+    assert torch.allclose(dist.deterministic()(latent), params["mean"]) and torch.allclose(dist.determine(latent), params["mean"])
+    params2, (sample2, logp2) = dist.sample(latent)
+    assert torch.equal(params2["mean"], params["mean"]) and sample2.shape == (3, 2) and logp2.shape == (3, 1)
+    normal = torch.distributions.Normal(params["mean"], params["std"])
+    assert torch.allclose(dist.compute_logp(params, sample), normal.log_prob(sample).sum(-1, keepdim=True), atol=1e-6)
+    assert torch.allclose(dist.compute_entropy(params), normal.entropy().sum(-1, keepdim=True), atol=1e-6)
+    assert torch.allclose(dist.compute_kl_div(params, params), torch.zeros(3, 1), atol=1e-6)
+    other = {"mean": params["mean"] + 0.3, "std": params["std"] * 1.5}
+    kl = torch.distributions.kl_divergence(normal, torch.distributions.Normal(other["mean"], other["std"])).sum(-1, keepdim=True)
+    assert torch.allclose(dist.compute_kl_div(params, other), kl, atol=1e-6)
+    with pytest.raises(ValueError, match="identity bijector"):
+        C.NormalDist.Factory(bijector="exp")(4, 2)
