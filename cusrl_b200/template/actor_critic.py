@@ -110,7 +110,7 @@ class ActorCritic:
 
     Factory = ActorCriticFactory
     MODULES = ["actor", "critic", "hook"]
-    STATEFULS = ["optimizer"]
+    STATEFULS = ["optimizer", "grad_scaler"]
 
     def __init__(self, environment_spec: EnvironmentSpec, actor_factory, critic_factory, optimizer_factory,
                  sampler: Sampler, hooks: Iterable[Hook], num_steps_per_update: int, name: str = "Agent",
@@ -159,6 +159,8 @@ class ActorCritic:
         self.actor = self.setup_module(self.actor)
         self.critic = self.setup_module(self.critic)
         self.optimizer = self.optimizer_factory(self.named_parameters())
+        # fp32 only: a DISABLED scaler, kept so that checkpoints carry the reference's "grad_scaler" entry (actor_critic.py:171,210)
+        self.grad_scaler = torch.GradScaler(device=str(self.device), enabled=False)
         self._set_training_mode(False)
         self.hook.post_init()
         distributed.broadcast_parameters([self.optimizer.flat_param] if hasattr(self.optimizer, "flat_param")
@@ -209,6 +211,10 @@ class ActorCritic:
 
     def autocast(self):
         return nullcontext()
+
+    @property
+    def grad_scaler_enabled(self) -> bool:
+        return False
 
     def record(self, metrics: Mapping[str, Any] | None = None, /, **kwargs) -> None:
         self.metrics.record(metrics, **kwargs)

@@ -81,11 +81,12 @@ def test_checkpoints_move_between_the_reference_agent_and_this_one(reference):
         assert list(our_sd[module]) == list(ref_sd[module])
         assert all(our_sd[module][k].shape == ref_sd[module][k].shape for k in ref_sd[module])
     assert list(our_sd["hook"]) == list(ref_sd["hook"])
+    assert list(our_sd) == list(ref_sd) and our_sd["grad_scaler"] == ref_sd["grad_scaler"] == {}   # disabled scaler, same entry
     assert our_sd["optimizer"]["param_groups"][0]["param_names"] == ref_sd["optimizer"]["param_groups"][0]["param_names"]
     assert set(ref_sd["optimizer"]["param_groups"][0]) <= set(our_sd["optimizer"]["param_groups"][0])
 
     # reference -> here
-    ours.load_state_dict({k: v for k, v in ref_sd.items() if k != "grad_scaler"})
+    ours.load_state_dict(ref_sd)
     for (name, p), (rname, rp) in zip(ours.named_parameters(), ref_agent.named_parameters()):
         assert name == rname and torch.equal(p.detach(), rp.detach())
     opt = ours.optimizer
@@ -101,7 +102,7 @@ def test_checkpoints_move_between_the_reference_agent_and_this_one(reference):
     # here -> reference: torch.optim.Adam accepts what FlatAdam writes
     back = ours.state_dict()
     fresh = RefFactory(**kwargs)(spec)
-    fresh.load_state_dict({**back, "grad_scaler": ref_sd["grad_scaler"]})
+    fresh.load_state_dict(back)
     for (_, p), (_, rp) in zip(fresh.named_parameters(), ref_agent.named_parameters()):
         assert torch.equal(p.detach(), rp.detach())
     got = fresh.optimizer.state_dict()["state"]
