@@ -332,3 +332,62 @@ def test_export_runs_the_hooks_export_callbacks(reference, tmp_path, monkeypatch
         agent.export(str(tmp_path), target_format="jit", verbose=False)
         got = torch.jit.load(str(tmp_path / "actor.pt"))(obs)
     torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("options", [
+    {}, {"final_missing": True}, {"symmetric": True}, {"max_count": 40}, {"subset": slice(0, 6)}, {"subset": [9, 2, 4, 0, 7, 5]},
+    {"groups": True}, {"symmetric": True, "subset": slice(0, 6)}], ids=lambda o: "+".join(o) or "plain")
+def test_observation_normalization_options_match_the_live_reference_hook(reference, options):
+    """Every specification option `ObservationNormalization` reads (observation.py:59-255; the cases of
+    cusrl_test/hook/mdp/test_observation_normalization.py: symmetry, observation-is-subset-of-state as slice and index list,
+    statistic groups, excluded indices, a count window, missing final states) driven step by step next to the REFERENCE's own
+    hook on the same inputs: normalised tensors and running statistics must be identical (CPU tensors: the host logic and
+    torch arithmetic of this hook; the kernels behind the same code on CUDA tensors are covered by tests/test_obsnorm.py)."""
+    from types import SimpleNamespace
+
+    import torch
+
+    import cusrl_b200 as C
+
+    obs_dim, state_dim, N = 6, 10, 16
+
+    def run(hook_cls, mirror_cls):
+        spec = dict(final_state_is_missing=options.get("final_missing", False), mirror_observation=None, mirror_state=None,
+                    observation_is_subset_of_state=options.get("subset"), observation_stat_groups=(), state_stat_groups=(),
+                    observation_normalization_excluded_indices=None, state_normalization_excluded_indices=None)
+        if options.get("symmetric"):
+            spec["mirror_observation"] = mirror_cls([1, 0, 2, 4, 3, 5], [False, False, True, False, False, False])
+            spec["mirror_state"] = mirror_cls([1, 0, 2, 4, 3, 5, 7, 6, 8, 9],
+                                              [False, False, True, False, False, False, True, True, False, True])
+        if options.get("groups"):
+            spec.update(observation_stat_groups=(slice(0, 3),), state_stat_groups=((0, 3), slice(6, 10)),
+                        observation_normalization_excluded_indices=slice(4, 6), state_normalization_excluded_indices=(4, 5))
+        agent = SimpleNamespace(environment_spec=SimpleNamespace(**spec), observation_dim=obs_dim, state_dim=state_dim,
+                                has_state=True, inference_mode=False, setup_module=lambda m: m, to_tensor=torch.as_tensor,
+                                device=torch.device("cpu"), parallelism=N)
+        hook = hook_cls(options.get("max_count"))
+        hook.pre_init(agent)
+        hook.init()
+        g = torch.Generator().manual_seed(3)
+        subset = options.get("subset")
+        trace = []
+        for _ in range(6):
+            state = torch.randn(N, state_dim, generator=g) * 2 + 1
+            observation = state[:, subset].clone() if subset is not None else torch.randn(N, obs_dim, generator=g) * 3 - 1
+            transition = {"observation": observation, "state": state}
+            hook.pre_act(transition)
+            next_state = torch.randn(N, state_dim, generator=g) * 2 + 1
+            next_observation = next_state[:, subset].clone() if subset is not None else torch.randn(N, obs_dim, generator=g) * 3 - 1
+            step = {"next_observation": next_observation, "next_state": next_state, "done": torch.rand(N, 1, generator=g) < 0.3}
+            hook.post_step(step)
+            trace += [transition["observation"], transition["state"], step["next_observation"], step["next_state"],
+                      hook.observation_rms.mean.clone(), hook.observation_rms.var.clone(), hook.state_rms.mean.clone(),
+                      hook.state_rms.var.clone(), torch.tensor(float(hook.observation_rms.count)),
+                      torch.tensor(float(hook.state_rms.count))]
+        return trace
+
+    theirs = run(reference.hook.ObservationNormalization, reference.hook.auxiliary.symmetry.MirrorDef)
+    ours = run(C.ObservationNormalization, C.MirrorDef)
+    assert len(theirs) == len(ours)
+    for i, (a, b) in enumerate(zip(theirs, ours)):
+        torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-6, msg=lambda m, i=i: f"trace entry {i}: {m}")
