@@ -391,3 +391,48 @@ def test_observation_normalization_options_match_the_live_reference_hook(referen
     assert len(theirs) == len(ours)
     for i, (a, b) in enumerate(zip(theirs, ours)):
         torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-6, msg=lambda m, i=i: f"trace entry {i}: {m}")
+
+
+@pytest.mark.parametrize("kwargs", [
+    dict(desired_kl_divergence=0.01), dict(desired_kl_divergence=0.015, max_kl_divergence=0.04),
+    dict(desired_kl_divergence=0.01, warmup_iterations=5, initial_scale=0.2), dict(desired_kl_divergence=0.01, scale_all_params=True),
+    dict(desired_kl_divergence=0.02, scale_factor=0.5, threshold=0.5)], ids=lambda k: "+".join(sorted(k)))
+def test_adaptive_lr_schedule_follows_the_live_reference_hook(reference, kwargs):
+    """`AdaptiveLRSchedule` (lr_schedule.py:19-239) with each of its options, next to the REFERENCE's own hook inside the
+    reference's own agent, over 40 iterations of the same KL statistics: learning-rate scale, every param group's learning
+    rate and the accept / reject decisions (`max_kl_divergence`) must be identical."""
+    import random
+
+    import cusrl_b200 as C
+
+    rng = random.Random(1)
+    kls = [0.01 * 2 ** rng.uniform(-3, 3) for _ in range(40)]
+
+    def drive(theirs: bool):
+        if theirs:
+            factory = reference.preset.ppo.PpoAgentFactory(actor_hidden_dims=(16, 8), critic_hidden_dims=(16, 8),
+                                                           desired_kl_divergence=None, device="cpu").to_underlying()
+            factory.register_hook(reference.hook.AdaptiveLRSchedule(**kwargs))
+            agent = factory(reference.EnvironmentSpec(19, 5, num_instances=4))
+        else:
+            factory = C.PpoAgentFactory(actor_hidden_dims=(64, 128), critic_hidden_dims=(64, 128), desired_kl_divergence=None,
+                                        device="cpu").to_underlying()
+            factory.register_hook(C.AdaptiveLRSchedule(**kwargs))
+            agent = factory(C.EnvironmentSpec(19, 5, num_instances=4))       # the reference's call style
+        hook = agent.hook["adaptive_lr_schedule"]
+        trace = []
+        for iteration, kl in enumerate(kls):
+            agent.iteration = iteration
+            hook.apply_schedule(iteration)
+            hook.pre_update(agent.buffer)
+            agent.metrics.clear()
+            agent.record(kl_divergence=kl)
+            hook.post_update()
+            rejected = float(agent.metrics["update_rejected"].mean) if "update_rejected" in agent.metrics.keys() else None
+            trace.append((hook._lr_scale, [group["lr"] for group in agent.optimizer.param_groups], rejected))
+        return trace
+
+    for step, (a, b) in enumerate(zip(drive(True), drive(False))):
+        assert b[0] == pytest.approx(a[0], rel=1e-12), step
+        assert b[1] == pytest.approx(a[1], rel=1e-12), step
+        assert b[2] == a[2], step
