@@ -436,3 +436,45 @@ def test_adaptive_lr_schedule_follows_the_live_reference_hook(reference, kwargs)
         assert b[0] == pytest.approx(a[0], rel=1e-12), step
         assert b[1] == pytest.approx(a[1], rel=1e-12), step
         assert b[2] == a[2], step
+
+
+@pytest.mark.parametrize("temporal", [False, True])
+@pytest.mark.parametrize("T,N,epochs,mini_batches,shuffle", [(6, 8, 3, 4, True), (5, 7, 2, 3, True), (4, 9, 3, (2, 3, 5), True),
+                                                              (6, 8, 2, 4, False), (3, 5, 1, 1, True)])
+def test_sampler_index_streams_follow_the_live_reference_sampler(reference, temporal, T, N, epochs, mini_batches, shuffle):
+    """Same seed -> the same minibatches as the REFERENCE's own samplers (mini_batch_sampler.py:52-114): permutation draws
+    (one per epoch, `randperm(out=)` from the second on), the dropped remainder, per-epoch minibatch counts, no shuffling,
+    metadata; flat `t*N + n` indices for the transition sampler, environment columns for the temporal one."""
+    import torch
+
+    import cusrl_b200 as C
+
+    Ref = reference.TemporalMiniBatchSampler if temporal else reference.MiniBatchSampler
+    Ours = C.TemporalMiniBatchSampler if temporal else C.MiniBatchSampler
+    if (N if temporal else T * N) < (max(mini_batches) if isinstance(mini_batches, tuple) else mini_batches):
+        pytest.skip("more minibatches than samples")
+    marker = torch.arange(T * N, dtype=torch.float32).reshape(T, N, 1)           # value = flat index t*N + n
+    ref_buffer = reference.template.Buffer(T, N, device="cpu")
+    our_buffer = C.Buffer(T, N, device="cpu")
+    for t in range(T):
+        ref_buffer.push({"marker": marker[t]})
+        our_buffer.push({"marker": marker[t]})
+    torch.manual_seed(123)
+    theirs = [(meta, batch["marker"]) for meta, batch in Ref(epochs, mini_batches, shuffle)(ref_buffer)]
+    torch.manual_seed(123)
+    # the index slices are views of ONE permutation buffer that `randperm(out=)` rewrites every epoch: copy them as they come
+    ours = [(meta, idx.clone()) for meta, idx in Ours(epochs, mini_batches, shuffle).indices(our_buffer)]
+    assert len(theirs) == len(ours)
+    for (ref_meta, ref_rows), (meta, idx) in zip(theirs, ours):
+        assert meta == ref_meta
+        if temporal:      # the reference yields [T, n_mb, 1] sequences of the selected environment columns
+            assert torch.equal(ref_rows[0, :, 0].long(), idx) and ref_rows.shape == (T, idx.numel(), 1)
+        else:
+            assert torch.equal(ref_rows[:, 0].long(), idx)
+    # and both leave torch's generator at the same position
+    torch.manual_seed(123)
+    list(Ref(epochs, mini_batches, shuffle)(ref_buffer))
+    after_theirs = torch.rand(3)
+    torch.manual_seed(123)
+    list(Ours(epochs, mini_batches, shuffle).indices(our_buffer))
+    assert torch.equal(torch.rand(3), after_theirs)
