@@ -11,8 +11,10 @@ legs may import this module; the product package ``cusrl_b200`` never does.
 Parity pinning: the oracle is checked against (a) the reference's own known-answer tests
 (cusrl_test/hook/on_policy/test_gae.py:8-31, test_ppo.py:8-32, test_advantage.py:37-48,
 cusrl_test/sampler/test_mini_batch_sampler.py:8-90) and (b) golden vectors produced by importing the
-live reference in the build container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
-See tests/test_oracle_golden.py.
+live reference in the build container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``),
+see tests/test_oracle_golden.py; and (c) the reference's own functions and hooks run LIVE next to the
+oracle on randomised inputs of many shapes (tests/test_oracle_live_reference.py, bit-identical; the
+reference package travels as baseline/_ref).
 """
 
 from __future__ import annotations
