@@ -143,3 +143,27 @@ def test_objective_terms_match_the_reference_functions(reference, B, A, loss_cli
     assert torch.equal(O.normal_entropy_ref(std), dist.compute_entropy(params))
     other = {"mean": mean + 0.1, "std": std * 1.3}
     assert torch.equal(O.normal_kl_ref(mean, std, other["mean"], other["std"]), dist.compute_kl_div(params, other))
+
+
+@pytest.mark.parametrize("T,N,I,H,L,p_done", [(6, 5, 7, 8, 1, 0.2), (9, 4, 3, 12, 2, 0.4), (5, 6, 10, 4, 3, 0.0), (4, 3, 5, 8, 2, 1.0),
+                                              (1, 7, 6, 8, 2, 0.5), (12, 2, 235, 16, 2, 0.1)])
+def test_lstm_in_line_reset_form_matches_the_reference_rnn(reference, T, N, I, H, L, p_done):
+    """`lstm_sequence_ref` (the in-line state reset where `done`) next to the REFERENCE's `Rnn` (nn.LSTM behind its split-at-
+    done / pad / scatter machinery, rnn.py:264-299, recurrent.py:160-272) on random sequences: no episode end, every step an
+    episode end, one step, three layers, the Anymal observation width; initial memory given per step like a minibatch's."""
+    g = torch.Generator().manual_seed(7)
+    torch.manual_seed(0)
+    rnn = reference.Rnn.Factory("LSTM", hidden_size=H, num_layers=L)(I)
+    x = torch.randn(T, N, I, generator=g)
+    done = torch.rand(T, N, 1, generator=g) < p_done
+    # a stored per-step memory [T, N, L*H] of which only step 0 is consumed (recurrent.py:202-212)
+    hidden = torch.randn(T, N, L * H, generator=g) * 0.5
+    cell = torch.randn(T, N, L * H, generator=g) * 0.5
+    with torch.no_grad():
+        theirs, _ = rnn(x, memory={"hidden": hidden, "cell": cell}, done=done)
+    lstm = next(m for m in rnn.modules() if isinstance(m, torch.nn.LSTM))
+    weights = [tuple(getattr(lstm, f"{name}_l{layer}").detach() for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+               for layer in range(L)]
+    to_lnh = lambda m: m[0].reshape(N, L, H).transpose(0, 1).contiguous()  # noqa: E731   "n (k c) -> k n c"
+    ours, _, _ = O.lstm_sequence_ref(x, done, to_lnh(hidden), to_lnh(cell), weights)
+    torch.testing.assert_close(ours, theirs, rtol=1e-5, atol=1e-5)       # the reference's own tolerance (test_rnn.py:163)
