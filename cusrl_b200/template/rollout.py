@@ -141,7 +141,7 @@ class _Net:
 class _StepSlots:
     """The slots of ONE buffer step with their addresses resolved (views kept alive: they also go into the transition)."""
 
-    __slots__ = ("views", "obs", "state", "prev_next_obs", "prev_next_state", "mean", "std", "action", "logp", "value",
+    __slots__ = ("t", "views", "obs", "state", "mean", "std", "action", "logp", "value",
                  "store_obs", "store_state", "store_tail", "transition_act", "transition_step")
 
 
@@ -259,16 +259,13 @@ class FusedRollout:
         if slots is not None:
             return slots
         agent = self.agent
-        storage, T = agent.buffer.storage, agent.buffer.capacity
+        storage = agent.buffer.storage
         f32 = torch.float32
         s = _StepSlots()
         v = s.views = {k: storage[k][t] for k in self._needed_leaves()}
+        s.t = t
         s.obs = ops._rows(v["observation"], "observation slot")
-        s.prev_next_obs = ops._rows(storage["next_observation"][(t - 1) % T], "next_observation slot")
-        s.state = s.prev_next_state = None
-        if agent.has_state:
-            s.state = ops._rows(v["state"], "state slot")
-            s.prev_next_state = ops._rows(storage["next_state"][(t - 1) % T], "next_state slot")
+        s.state = ops._rows(v["state"], "state slot") if agent.has_state else None
         s.mean, s.std, s.action, s.logp, s.value = (ops._ptr(v[k], f32, k + " slot") for k in (
             "action_dist.mean", "action_dist.std", "action", "action_logp", "value"))
         s.store_obs = (*ops._rows(v["next_observation"], "next_observation slot"), agent.observation_dim)
@@ -290,9 +287,11 @@ class FusedRollout:
         slots = self._step_slots(t)
         wide_state = key == "state"
         dst = slots.state if wide_state else slots.obs
-        if prev_obj is not None and _same_array(value, prev_obj):
-            # the array the caller passed to step() one call ago: already on the device in the previous step's slot
-            src = slots.prev_next_state if wide_state else slots.prev_next_obs
+        if prev_obj is not None and prev_obj[2] is self._slots.get(prev_obj[2].t) and _same_array(value, prev_obj):
+            # the array the caller passed to step() one call ago: already on the device in the slot that step wrote (the slots
+            # object must still be the current one of its step: a re-allocated buffer starts empty)
+            held = prev_obj[2]
+            src = held.store_state[:2] if wide_state else held.store_obs[:2]
         else:
             rows = self._device_rows(value, key)
             src = (rows.data_ptr(), rows.stride(0))
@@ -397,8 +396,10 @@ class FusedRollout:
             ops._flag_ptr(self._device_rows(truncated.contiguous(), "truncated"), "truncated"), *slots.store_tail, ops._stream())
         _lib.check(code, "rollout_store_step")
         agent.transition.update(slots.transition_step)
-        self._prev_next_obs = (next_observation, _fingerprint(next_observation))
-        self._prev_next_state = None if next_state is None else (next_state, _fingerprint(next_state))
+        # remembered WITH the slots of the step that holds the copy: the hand-over reads that step's slot, wherever the cursor
+        # is by then (wrap-around, or a caller that moved it)
+        self._prev_next_obs = (next_observation, _fingerprint(next_observation), slots)
+        self._prev_next_state = None if next_state is None else (next_state, _fingerprint(next_state), slots)
         agent.buffer.advance()
         self.fast_steps += 1
         return True

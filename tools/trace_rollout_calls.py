@@ -68,12 +68,22 @@ for it in range(ITERATIONS):
     for t in range(T):
         LOG.append(("--act", (it, t)))
         hand_back = it != 1      # iteration 1: act() receives a fresh array, not the one step() got as next_observation
-        agent.act(obs[t] if hand_back else obs[t].clone(), state[t] if (hand_back or state[t] is None) else state[t].clone())
+        # the Trainer's loop: the observation of step 0 of a later iteration is the last next_observation of the one before
+        o, st = (obs[T], state[T]) if (it > 0 and t == 0) else (obs[t], state[t])
+        agent.act(o if hand_back else o.clone(), st if (hand_back or st is None) else st.clone())
         LOG.append(("--step", (it, t)))
         agent.step(obs[t + 1], reward[t], terminated[t], truncated[t], state[t + 1])
     n = len(LOG)
     agent.update()       # re-splits nothing here (stubbed), but bumps the weights' epoch like a real optimizer step
     del LOG[n:]          # the update's own launches are not under test
+# a caller that moves the cursor between step() and act(): the hand-over must still read the slot that step() wrote
+LOG.append(("--extra", ()))
+for t in range(3):
+    agent.act(obs[t], state[t])
+    agent.step(obs[t + 1], reward[t], terminated[t], truncated[t], state[t + 1])
+agent.buffer.reset_cursor()
+LOG.append(("--moved", ()))
+agent.act(obs[3], state[3])
 
 # ---- pointer -> name+offset --------------------------------------------------------------------------------------------------
 registry: list[tuple[int, int, str]] = []
@@ -115,7 +125,7 @@ if args.out:
 print(f"fast steps {rollout.fast_steps}, {len(LOG)} log lines")
 
 if args.check:
-    assert rollout.fast_steps == ITERATIONS * T - 1, rollout.fast_steps     # only the allocating first step is generic
+    assert rollout.fast_steps == ITERATIONS * T - 1 + 3, rollout.fast_steps     # only the allocating first step is generic (+ the 3 of the moved-cursor scenario)
     pitch_obs = agent.buffer.backing("observation").stride(1) * 4            # padded row pitch in bytes
     assert pitch_obs == 944
     per_step = {}
@@ -143,7 +153,7 @@ if args.check:
             copy = calls[0][1]
             # handed back = the very array the previous FUSED step() received (t == 0: obs[0] never was a next_observation;
             # step 1 of the run: the step before it was the generic, allocating one)
-            handed_back = it != 1 and t > 0 and (it, t) != (0, 1)
+            handed_back = it != 1 and (t > 0 or it > 0) and (it, t) != (0, 1)
             prev = f"buf.next_observation+{((t - 1) % T) * N * pitch_obs}"
             assert copy[0] == (prev if handed_back else "stage.observation+0"), (it, t, copy)
             assert copy[2] == off("observation", pitch_obs) and copy[3] == 236 and copy[4:6] == [N, OBS]
@@ -166,4 +176,6 @@ if args.check:
             assert s[10:13] == ["stage.reward+0", off("reward", 4), 1]
             assert s[13:15] == ["stage.terminated+0", "stage.truncated+0"]
             assert s[15:19] == [off("terminated", 1), off("truncated", 1), off("done", 1), N]
+    moved = [a for n, a in per_step[("moved",)] if "copy_rows_padded" in n][0]
+    assert moved[0] == f"buf.next_observation+{2 * N * pitch_obs}" and moved[2] == "buf.observation+0", moved
     print("addressing rules hold")
