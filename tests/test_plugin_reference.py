@@ -478,3 +478,40 @@ def test_sampler_index_streams_follow_the_live_reference_sampler(reference, temp
     torch.manual_seed(123)
     list(Ours(epochs, mini_batches, shuffle).indices(our_buffer))
     assert torch.equal(torch.rand(3), after_theirs)
+
+
+@pytest.mark.parametrize("kind", ["ppo", "anymal", "lstm", "rnd", "state"])
+def test_same_seed_gives_the_reference_agents_initial_parameters(reference, kind):
+    """Drop-in at construction: with the same torch seed the agent built by this package has the SAME parameter names, the
+    same initial values bit for bit (module creation order, default initialisers, `ModuleInitialization`'s orthogonal pass
+    over linear and recurrent layers, the RND hook's Xavier initialisation, `init_distribution_std`) and leaves torch's
+    generator at the same position as the reference's agent -- default PPO preset, the Anymal-C preset values
+    (zoo/isaaclab/locomotion.py:48-59), the recurrent preset, PPO + RND, PPO with a critic state."""
+    import torch
+
+    import cusrl_b200 as C
+
+    def build(theirs: bool):
+        pkg = reference if theirs else C
+        presets = reference.preset.ppo if theirs else C
+        torch.manual_seed(42)
+        if kind == "anymal":
+            factory = presets.PpoAgentFactory(num_steps_per_update=24, actor_hidden_dims=(512, 256, 128), critic_hidden_dims=(512, 256, 128),
+                                              activation_fn="ELU", lr=1e-3, sampler_epochs=5, sampler_mini_batches=4, orthogonal_init=False,
+                                              entropy_loss_weight=0.005, desired_kl_divergence=0.015, device="cpu")
+        elif kind == "lstm":
+            factory = presets.RecurrentPpoAgentFactory(device="cpu")
+        elif kind == "rnd":
+            factory = presets.PpoAgentFactory(device="cpu").to_underlying()
+            factory.register_hook(pkg.hook.RandomNetworkDistillation(pkg.Mlp.Factory([128, 128]), output_dim=16, reward_scale=0.1),
+                                  before="value_computation")
+        else:
+            factory = presets.PpoAgentFactory(device="cpu", init_distribution_std=0.6 if kind == "state" else None)
+        agent = factory(pkg.EnvironmentSpec(235, 12, num_instances=8, state_dim=40 if kind == "state" else None))
+        return dict(agent.named_parameters()), torch.rand(3)
+
+    (ref_params, ref_next), (our_params, our_next) = build(True), build(False)
+    assert list(our_params) == list(ref_params)
+    for name, value in ref_params.items():
+        assert torch.equal(our_params[name].detach(), value.detach()), name
+    assert torch.equal(our_next, ref_next)
