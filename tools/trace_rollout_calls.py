@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--state-dim", type=int, default=0)
 ap.add_argument("--out", default=None)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--recurrent", action="store_true", help="the recurrent preset (FusedRecurrentRollout); trace only, no --check")
 args = ap.parse_args()
 
 real = _lib.load()
@@ -51,11 +52,17 @@ import cusrl_b200 as C  # noqa: E402
 from cusrl_b200.template.rollout import FusedRollout  # noqa: E402
 
 FusedRollout.REQUIRE_CUDA = False
+if hasattr(C.Rnn, "REQUIRE_CUDA"):
+    C.Rnn.REQUIRE_CUDA = False     # drive the recurrent inference path (one sequence-kernel launch per layer) on CPU tensors
 state_dim = args.state_dim or None
 N, T, OBS, ACT = 64, 6, 235, 12
 torch.manual_seed(0)
 spec = C.EnvironmentSpec(N, OBS, ACT, state_dim=state_dim, autoreset=True, final_state_is_missing=True)
-agent = C.anymal_c_rough_ppo(num_steps_per_update=T, device=torch.device("cpu"))(spec)
+if args.recurrent:
+    agent = C.RecurrentPpoAgentFactory(num_steps_per_update=T, actor_hidden_size=128, critic_hidden_size=128, actor_num_layers=2,
+                                       critic_num_layers=1, device=torch.device("cpu"))(spec)
+else:
+    agent = C.anymal_c_rough_ppo(num_steps_per_update=T, device=torch.device("cpu"))(spec)
 agent.cuda_graphs = False
 g = torch.Generator().manual_seed(1)
 obs = [torch.randn(N, OBS, generator=g) for _ in range(T + 1)]
@@ -124,6 +131,8 @@ if args.out:
     Path(args.out).write_text("".join(name + " " + " ".join(map(str, a)) + "\n" for name, a in lines))
 print(f"fast steps {rollout.fast_steps}, {len(LOG)} log lines")
 
+if args.check and args.recurrent:
+    raise SystemExit("--check covers the feed-forward step; use --recurrent --out to diff two versions of the code")
 if args.check:
     assert rollout.fast_steps == ITERATIONS * T - 1 + 3, rollout.fast_steps     # only the allocating first step is generic (+ the 3 of the moved-cursor scenario)
     pitch_obs = agent.buffer.backing("observation").stride(1) * 4            # padded row pitch in bytes
