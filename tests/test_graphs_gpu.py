@@ -78,7 +78,7 @@ def _lstm(C, dev):
 def test_graph_replay_matches_eager_training(C, monkeypatch, name, make, envs, iters):
     # the kernels' numerics in this comparison were validated on a B200 with the LSTM at torch's default initialisation:
     # keep those weights (ModuleInitialization's orthogonal initialisation of recurrent layers is host-side torch code,
-    # covered on the CPU by tests/test_host_logic.py against the reference's hook, seed for seed)
+    # covered on the CPU by tests/test_plugin_reference.py against the reference's hook, seed for seed)
     monkeypatch.setattr(C.ModuleInitialization, "_init_rnn", lambda *args, **kwargs: None)
     eager, hist_e = _run(C, make, envs, iters, cuda_graphs=False)
     graphed, hist_g = _run(C, make, envs, iters, cuda_graphs=True)

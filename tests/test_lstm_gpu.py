@@ -84,7 +84,7 @@ def test_recurrent_ppo_trainer_and_train_rollout_consistency(C, monkeypatch):
     mean recomputed from the stored memories equals the mean stored during the rollout to 1e-4."""
     # the kernels' numerics in this comparison were validated on a B200 with the LSTM at torch's default initialisation:
     # keep those weights (ModuleInitialization's orthogonal initialisation of recurrent layers is host-side torch code,
-    # covered on the CPU by tests/test_host_logic.py against the reference's hook, seed for seed)
+    # covered on the CPU by tests/test_plugin_reference.py against the reference's hook, seed for seed)
     monkeypatch.setattr(C.ModuleInitialization, "_init_rnn", lambda *args, **kwargs: None)
     env = C.SyntheticEnvironment(256, device="cuda", seed=9, p_term=0.05, p_trunc=0.01)
     factory = C.RecurrentPpoAgentFactory(device="cuda", entropy_loss_weight=0.005, desired_kl_divergence=0.015).to_underlying()

@@ -141,7 +141,7 @@ def test_fused_recurrent_rollout_matches_generic(C, monkeypatch):
     their in-place episode resets -- same returned actions and the same update as the generic act / step flow."""
     # the kernels' numerics in this comparison were validated on a B200 with the LSTM at torch's default initialisation:
     # keep those weights (ModuleInitialization's orthogonal initialisation of recurrent layers is host-side torch code,
-    # covered on the CPU by tests/test_host_logic.py against the reference's hook, seed for seed)
+    # covered on the CPU by tests/test_plugin_reference.py against the reference's hook, seed for seed)
     monkeypatch.setattr(C.ModuleInitialization, "_init_rnn", lambda *args, **kwargs: None)
     Tn, Nn = 8, 384
 
