@@ -27,7 +27,7 @@ from typing import Any
 
 import torch
 
-from .. import _lib, ops
+from .. import _lib, distributed, ops
 from ..nn import functional as F
 from ..nn import modules as M
 from .hook import Hook
@@ -161,8 +161,11 @@ class FusedRollout:
         self._acted_fast = False
         self.fast_steps = 0
         # CUSRL_B200_ROLLOUT_STREAMS=1: actor and critic of a step on one stream (the default puts the critic on a second one
-        # when the step is latency-bound, see act)
-        self._two_streams = agent.device.type == "cuda" and os.environ.get("CUSRL_B200_ROLLOUT_STREAMS", "2") == "2"
+        # when the step is latency-bound, see act).  Single-process runs only: that is the configuration the second stream was
+        # measured and validated in (profiles/r02_rollout_host.md); a multi-rank job keeps the one-stream step unless the knob
+        # is set explicitly.
+        knob = os.environ.get("CUSRL_B200_ROLLOUT_STREAMS")
+        self._two_streams = agent.device.type == "cuda" and (knob == "2" or (knob is None and not distributed.enabled()))
         self._streams: Any = None
         self._layout_key: Any = None         # (buffer.layout_version, number of leaves) the cached decisions below belong to
         self._layout_ok = False
