@@ -47,6 +47,29 @@ def main(out_path: str):
     D.reduce_gradients(agent.optimizer)
     res["grad_mean"] = float(agent.optimizer.flat_grad[0])
     res["grad_uniform"] = bool((agent.optimizer.flat_grad == agent.optimizer.flat_grad[0]).all())
+    # RunningMeanStd across ranks (nn/layer/rms.py:157-196): every rank streams DIFFERENT batches of different sizes; with
+    # per-step synchronisation, and with the deferred protocol (local updates, one `synchronize()` per update), both ranks
+    # must end with the statistics of the pooled data (population variance, count = all samples)
+    from cusrl_b200.nn.rms import RunningMeanStd
+
+    def batches(r):
+        gr = torch.Generator().manual_seed(500 + r)
+        return [torch.randn(5 + 3 * r + k, 6, generator=gr) * (1 + r) + 2 * r - k for k in range(4)]
+
+    pooled = torch.cat([b for r in range(world) for b in batches(r)])
+    pooled_var, pooled_mean = torch.var_mean(pooled, dim=0, correction=0)
+    for mode in ("every_step", "deferred"):
+        rms = RunningMeanStd(6)
+        for batch in batches(rank):
+            rms.update(batch, synchronize=(mode == "every_step"))
+        if mode == "deferred":
+            res["rms_deferred_is_local_before_sync"] = rms.count == sum(b.shape[0] for b in batches(rank))
+            rms.synchronize()
+        both = D.gather_stack(torch.cat([rms.mean, rms.var]))
+        res[f"rms_{mode}"] = bool(torch.allclose(rms.mean, pooled_mean, rtol=1e-5, atol=1e-5)
+                                  and torch.allclose(rms.var, pooled_var, rtol=1e-4, atol=1e-5)
+                                  and rms.count == pooled.shape[0] and torch.allclose(both[0], both[1], rtol=0, atol=1e-6)
+                                  and torch.allclose(rms.std, torch.sqrt(rms.var + rms.epsilon)))
     # C5
     res["avg_dict"] = D.average_dict({"a": float(rank), "only0": 5.0} if rank == 0 else {"a": float(rank)})
     D.barrier()

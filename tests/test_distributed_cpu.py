@@ -24,3 +24,5 @@ def test_two_rank_gloo_collectives(tmp_path):
     assert res["params_equal_after_broadcast"]                     # broadcast_parameters (actor_critic.py:224)
     assert res["grad_mean"] == pytest.approx(1.5) and res["grad_uniform"]  # reduce_gradients: mean, not sum
     assert res["avg_dict"]["a"] == pytest.approx(0.5) and res["avg_dict"]["only0"] == pytest.approx(5.0)
+    # observation normalisation's running statistics: per-step and deferred cross-rank synchronisation give the pooled statistics
+    assert res["rms_every_step"] and res["rms_deferred"] and res["rms_deferred_is_local_before_sync"]
