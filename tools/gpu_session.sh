@@ -59,6 +59,7 @@ for s in "$@"; do
     gemm_tests) step gemm_tests 600 python -u -m pytest tests/test_gemm_f16x3_gpu.py tests/test_gemm_gpu.py tests/test_agent_gpu.py tests/test_baseline_shapes_gpu.py -q -m gpu --timeout 200 -rf -x ;;
     ncu_lstm)   step ncu_lstm 280 ncu --set full --clock-control none --import-source on -k regex:lstm_seq_ --launch-skip 3 --launch-count 2 -o "$out/lstm_seq" -f python tools/lstm_bench.py --reps 1 --only-config3 ;;
     rollout_tests) step rollout_tests 400 python -u -m pytest tests/test_rollout_gpu.py tests/test_lstm_gpu.py tests/test_graphs_gpu.py -q -m gpu --timeout 200 -rf -x ;;
+    bench_small) step bench_small 200 bash -c "for e in 4096 8192; do python bench.py --config mlp --envs \$e --steps 10 --warmup 5 --no-cpu-baseline --no-reference-cuda; CUSRL_B200_ROLLOUT_STREAMS=1 python bench.py --config mlp --envs \$e --steps 10 --warmup 5 --no-cpu-baseline --no-reference-cuda; done" ;;   # profiles/r02_rollout_host.md: two-stream vs one-stream rollout step
     *) echo "unknown step $s" ;;
   esac
 done
